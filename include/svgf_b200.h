@@ -1,0 +1,213 @@
+/* svgf_b200.h -- C ABI of the B200-native SVGF + 1-spp path-trace hot path.
+ *
+ * This is the drop-in boundary for the reference's per-frame path
+ *     pathtrace(uchar4* pbo, int frame)            /root/reference/src/pathtrace.h:8  (pathtrace.cu:404-452)
+ *       -> denoise(vec3* out, vec3* in, GBufferTexel*)   src/denoise.h:8            (denoise.cu:349-402)
+ * and its lifecycle calls pathtraceInit/Free (pathtrace.h:6-7) and denoiseInit/Free (denoise.h:6-7).
+ * Plain pointers and sizes only; no C++/torch/glm types. Every function returns 0 on success or a
+ * negative svgf_status; svgf_last_error() gives the text. Nothing here ever falls back to a CPU path:
+ * if the CUDA device or the kernels are unavailable the call fails.
+ *
+ * The reference's data contract is kept byte for byte: the structs below have the sizes and field offsets
+ * of the reference's structs, so a Scene built by the reference's loader
+ * can be handed over without conversion (see INTEGRATION.md for the C++ shim that does this).
+ */
+#ifndef SVGF_B200_H
+#define SVGF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVGF_ABI_VERSION 1
+
+typedef enum svgf_status {
+    SVGF_OK = 0,
+    SVGF_ERR_INVALID = -1,      /* bad argument / call order */
+    SVGF_ERR_CUDA = -2,         /* CUDA runtime error (text in svgf_last_error) */
+    SVGF_ERR_NO_DEVICE = -3,    /* no usable CUDA device: there is no CPU fallback */
+    SVGF_ERR_COMM = -4,         /* multi-GPU exchange failed */
+    SVGF_ERR_UNKNOWN_NAME = -5  /* svgf_fetch: no such buffer */
+} svgf_status;
+
+/* ---- reference-layout PODs (all alignof 4) ------------------------------------------------------------ */
+
+/* Geom, sceneStructs.h:33-47 (248 B). Matrices are column-major (glm::mat4 memory order). */
+typedef struct svgf_geom {
+    int32_t type;               /* 0 SPHERE, 1 CUBE, 2 MESH (sceneStructs.h:18-22) */
+    int32_t materialid;
+    float translation[3], rotation[3], scale[3];
+    float transform[16], inverseTransform[16], invTranspose[16];
+    int32_t T_startidx, T_endidx, BoundIdx;
+} svgf_geom;
+
+/* Material, sceneStructs.h:49-72 (56 B) */
+typedef struct svgf_material {
+    float color[3];
+    float specular_exponent;
+    float specular_color[3];
+    float hasReflective, hasRefractive, indexOfRefraction, emittance;
+    int32_t matid, texid, norid;
+} svgf_material;
+
+/* Vertex / Triangle, sceneStructs.h:24-31, 121-181 (32 B / 136 B). World space, BVH order. */
+typedef struct svgf_vertex { float pos[3], normal[3], uv[2]; } svgf_vertex;
+typedef struct svgf_triangle {
+    int32_t id;                 /* load-order id; geom ranges [T_startidx, T_endidx) refer to it */
+    svgf_vertex verts[3];
+    float normal[3];            /* unused by the hot path */
+    float bb_max[3], bb_min[3]; /* unused by the hot path */
+} svgf_triangle;
+
+/* BVH_ArrNode, bvhtree.h:48-54 (40 B). Left child = index + 1. */
+typedef struct svgf_bvh_node {
+    float bounds_min[3], bounds_max[3];
+    int32_t primitive_count;    /* > 0: leaf */
+    int32_t axis;
+    int32_t primitivesOffset;
+    int32_t rightchildoffset;
+} svgf_bvh_node;
+
+/* Camera, sceneStructs.h:74-83 (84 B). `right` is unnormalised (main.cpp:179-184). */
+typedef struct svgf_camera {
+    int32_t resolution[2];
+    float position[3], lookAt[3], view[3], up[3], right[3];
+    float fov[2];
+    float pixelLength[2];
+} svgf_camera;
+
+/* GBufferTexel, sceneStructs.h:113-119 (52 B) */
+typedef struct svgf_gbuffer_texel {
+    float normal[3], position[3], albedo[3], ialbedo[3];
+    int32_t geomId;             /* -1 = miss */
+} svgf_gbuffer_texel;
+
+/* PathSegment, sceneStructs.h:92-99 (48 B) */
+typedef struct svgf_path_segment {
+    float origin[3], direction[3], color[3];
+    int32_t pixelIndex, remainingBounces;
+    uint8_t diffuse, specular, pad_[2];
+} svgf_path_segment;
+
+/* ShadeableIntersection, sceneStructs.h:104-111 (36 B); persistent per pixel across frames */
+typedef struct svgf_intersection {
+    float t, surfaceNormal[3];
+    int32_t materialId, geomId;
+    uint8_t outside, pad_[3];
+    float uv[2];
+} svgf_intersection;
+
+/* Texture pixels, sceneStructs.h:184-222: RGB8, row-major, `components` must be 3 to be sampled. */
+typedef struct svgf_texture_desc {
+    int32_t width, height, components;
+    const unsigned char *pixels;    /* host pointer, copied at svgf_create */
+} svgf_texture_desc;
+
+/* What pathtraceInit(Scene*) reads from the Scene (pathtrace.cu:103-158). Host pointers, copied. */
+typedef struct svgf_scene_desc {
+    const svgf_geom *geoms;             int32_t n_geoms;
+    const svgf_material *materials;     int32_t n_materials;
+    const svgf_triangle *triangles;     int32_t n_triangles;
+    const svgf_bvh_node *bvh_nodes;     int32_t n_bvh_nodes;
+    const svgf_texture_desc *textures;  int32_t n_textures;
+    int32_t width, height;              /* cam.resolution at Init time */
+} svgf_scene_desc;
+
+/* The 19 `ui_*` globals the reference's hot path reads at link time (main.h:39-69), passed explicitly.
+ * Field names follow the globals (ui_tracedepth -> tracedepth ...). Booleans are int32 0/1. */
+typedef struct svgf_params {
+    int32_t tracedepth;         /* pathtrace.cu:421,425 */
+    int32_t shadowray, reducevar;
+    float sintensity, lightradius;
+    int32_t denoise_enable, sepcolor;   /* pathtrace.cu:429,436 */
+    int32_t temporal_enable;    /* denoise.cu:360-362 */
+    float color_alpha, moment_alpha;
+    int32_t right_view_option;  /* denoise.cu:373-378: 0 filter, 1 history length /100, 2 variance /0.1 */
+    int32_t atrous_nlevel, spatial_enable, history_level;   /* denoise.cu:380-391 */
+    float sigmal, sigman, sigmax;
+    int32_t blurvariance, addcolor;
+    /* Not a reference global. The reference updates variance[] in place while neighbouring threads read
+     * it (denoise.cu:111,153,161), so its a-trous output is not deterministic. 0 (default) = race-free
+     * double-buffered variance: every read of a level sees the previous level's values. */
+    int32_t reserved_variance_mode;
+} svgf_params;
+
+/* Defaults = src/main.cpp:39-62 with the GUI "All" button pressed (preview.cpp:294-299). */
+void svgf_params_default(svgf_params *p);
+
+/* Row strip owned by this process when a frame is sharded over several GPUs.
+ * rows [row_begin, row_end) of the full W x H frame; world == 1 means the whole frame. */
+typedef struct svgf_shard {
+    int32_t rank, world;
+    int32_t row_begin, row_end;
+} svgf_shard;
+
+typedef struct svgf_ctx svgf_ctx;
+
+/* ---- lifecycle: pathtraceInit + denoiseInit / pathtraceFree + denoiseFree ------------------------------ */
+int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device);
+int svgf_destroy(svgf_ctx *ctx);                 /* NULL is a no-op, like Free before the first Init */
+/* "Clear"/frame 0 (main.cpp:192-201): history_length = 0, moments = 0, variance = 0, image = 0,
+ * persistent intersections = 0. view_matrix_prev survives (denoise.cu:15). */
+int svgf_reset(svgf_ctx *ctx);
+
+/* ---- the per-frame path -------------------------------------------------------------------------------- */
+/* == pathtrace(pbo, frame), pathtrace.cu:404-452. `pbo_dev` (device, 2W x H uchar4) and `host_image`
+ * (host, W*H*3 float, = scene->state.image) may be NULL. Synchronous like the reference when host_image is
+ * given; otherwise work is left queued on the context's stream (svgf_sync to wait). */
+int svgf_render(svgf_ctx *ctx, const svgf_camera *cam, const svgf_params *params, int frame,
+                void *pbo_dev, float *host_image);
+/* == denoise(output, input, gbuffer), denoise.cu:349-402, on caller-owned DEVICE buffers in the reference's
+ * AoS layouts (vec3 colour, 52-byte texels). */
+int svgf_denoise(svgf_ctx *ctx, float *output_dev, const float *input_dev, const svgf_gbuffer_texel *gbuffer_dev,
+                 const svgf_camera *cam, const svgf_params *params);
+int svgf_sync(svgf_ctx *ctx);
+
+/* Host-buffer convenience for callers without device memory of their own (tests, benches, FFI users):
+ * copies `input`/`gbuffer` H2D, runs svgf_denoise, copies `output` back. */
+int svgf_denoise_host(svgf_ctx *ctx, float *output, const float *input, const svgf_gbuffer_texel *gbuffer,
+                      const svgf_camera *cam, const svgf_params *params);
+
+/* One edge-avoiding a-trous level (ATrousFilter, denoise.cu:77-170) on HOST planes; `level` in [1,7],
+ * step = 1 << level. colour: W*H*3, variance: W*H, gbuffer: 52-byte texels. Used by the parity tests and
+ * the roofline bench. */
+int svgf_atrous_host(svgf_ctx *ctx, float *color_out, float *variance_out, const float *color_in,
+                     const float *variance_in, const svgf_gbuffer_texel *gbuffer, int level, int is_last,
+                     const svgf_params *params);
+
+/* ---- introspection (goldens, tests) -------------------------------------------------------------------- */
+/* Copies a named intermediate to host. Names follow the reference's file-static buffers:
+ * image, denoised, gbuffer (52 B AoS, repacked), intersections, variance, color_acc, color_history,
+ * moment_acc, moment_history, history_length, pbo. `bytes` must match exactly. */
+int svgf_fetch(svgf_ctx *ctx, const char *name, void *host, size_t bytes);
+const char *svgf_last_error(const svgf_ctx *ctx);    /* ctx may be NULL: last create error */
+int svgf_abi_version(void);
+
+/* Device-side time (ms) spent in each stage of the last svgf_render/svgf_denoise call, from CUDA events on
+ * the context's stream: [0] path trace, [1] temporal, [2..8] a-trous levels 1..7, [9] pbo pack, [10] total. */
+int svgf_stage_times(svgf_ctx *ctx, float *ms11);
+/* Enable/disable per-stage event timing (off by default; it adds event records to the stream). */
+int svgf_set_profiling(svgf_ctx *ctx, int enabled);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------------------------------------------- */
+int svgf_set_shard(svgf_ctx *ctx, const svgf_shard *shard);
+
+/* ---- camera control: the host logic either side of the path (main.cpp:77-101, 154-190) ------------------ */
+typedef struct svgf_camera_rig {
+    float zoom, theta, phi;
+    float tx, ty, tz, ttheta, tphi;     /* automation phases (main.cpp:24-28) */
+    float fovy;
+} svgf_camera_rig;
+/* Fill resolution-dependent fields (scene.cpp:159-166) and derive zoom/theta/phi (resetCamera, main.cpp:77-101). */
+void svgf_camera_init(svgf_camera *cam, svgf_camera_rig *rig, const float eye[3], const float lookat[3],
+                      const float up[3], float fovy, int width, int height);
+/* Optional automation step (main.cpp:156-169) followed by the camchanged block (main.cpp:171-190). */
+void svgf_camera_step(svgf_camera *cam, svgf_camera_rig *rig, int automate, const float speeds[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVGF_B200_H */
