@@ -1,0 +1,293 @@
+"""cuda-path-tracer-denoising_b200 -- host-side binding of the B200-native SVGF + 1-spp path-trace hot path.
+
+The product is the C-ABI library `libsvgf_b200.so` (csrc/, built in-tree for sm_100a; header include/svgf_b200.h).
+This module is the thin Python mirror of that ABI used by tests/ and bench.py. It mirrors the reference's
+operator interface for the path (src/pathtrace.h:6-8, src/denoise.h:6-8):
+
+    reference                               here
+    ---------                               ----
+    pathtraceInit(scene); denoiseInit(scene)    Renderer(scene_desc, W, H)        -> svgf_create
+    pathtraceFree(); denoiseFree()              Renderer.close()                  -> svgf_destroy
+    "Clear" / frame 0 (main.cpp:192-201)        Renderer.reset()                  -> svgf_reset
+    pathtrace(pbo, frame)                       Renderer.pathtrace(cam, params, frame, host_image=...) -> svgf_render
+    denoise(out, in, gbuffer)                   Renderer.denoise(in, gbuffer, cam, params)             -> svgf_denoise_host
+    ui_* globals (main.h:39-69)                 Params (svgf_params)
+
+There is NO CPU fallback: importing works without a GPU (so the ABI can be inspected), but creating a Renderer
+without a CUDA device, or without the built library, raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvgf_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "svgf_b200.h")
+
+SVGF_OK = 0
+
+
+class SvgfError(RuntimeError):
+    pass
+
+
+class Camera(ctypes.Structure):     # svgf_camera == reference Camera (sceneStructs.h:74-83), 84 bytes
+    _fields_ = [("resolution", ctypes.c_int32 * 2), ("position", ctypes.c_float * 3), ("lookAt", ctypes.c_float * 3),
+                ("view", ctypes.c_float * 3), ("up", ctypes.c_float * 3), ("right", ctypes.c_float * 3),
+                ("fov", ctypes.c_float * 2), ("pixelLength", ctypes.c_float * 2)]
+
+    def as_array(self):
+        return np.frombuffer(bytes(self), np.float32).copy()
+
+    @classmethod
+    def from_array(cls, a):
+        return cls.from_buffer_copy(np.ascontiguousarray(a, np.float32).tobytes())
+
+
+class CameraRig(ctypes.Structure):  # svgf_camera_rig
+    _fields_ = [(n, ctypes.c_float) for n in ("zoom", "theta", "phi", "tx", "ty", "tz", "ttheta", "tphi", "fovy")]
+
+
+class Params(ctypes.Structure):     # svgf_params: the 19 ui_* globals the path reads
+    _fields_ = [("tracedepth", ctypes.c_int32), ("shadowray", ctypes.c_int32), ("reducevar", ctypes.c_int32),
+                ("sintensity", ctypes.c_float), ("lightradius", ctypes.c_float),
+                ("denoise_enable", ctypes.c_int32), ("sepcolor", ctypes.c_int32), ("temporal_enable", ctypes.c_int32),
+                ("color_alpha", ctypes.c_float), ("moment_alpha", ctypes.c_float), ("right_view_option", ctypes.c_int32),
+                ("atrous_nlevel", ctypes.c_int32), ("spatial_enable", ctypes.c_int32), ("history_level", ctypes.c_int32),
+                ("sigmal", ctypes.c_float), ("sigman", ctypes.c_float), ("sigmax", ctypes.c_float),
+                ("blurvariance", ctypes.c_int32), ("addcolor", ctypes.c_int32), ("reserved_variance_mode", ctypes.c_int32)]
+
+
+class TextureDesc(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("components", ctypes.c_int32),
+                ("pixels", ctypes.c_void_p)]
+
+
+class SceneDesc(ctypes.Structure):
+    _fields_ = [("geoms", ctypes.c_void_p), ("n_geoms", ctypes.c_int32),
+                ("materials", ctypes.c_void_p), ("n_materials", ctypes.c_int32),
+                ("triangles", ctypes.c_void_p), ("n_triangles", ctypes.c_int32),
+                ("bvh_nodes", ctypes.c_void_p), ("n_bvh_nodes", ctypes.c_int32),
+                ("textures", ctypes.c_void_p), ("n_textures", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32)]
+
+
+class Shard(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("row_begin", ctypes.c_int32), ("row_end", ctypes.c_int32)]
+
+
+# every symbol include/svgf_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
+EXPORTS = ["svgf_params_default", "svgf_create", "svgf_destroy", "svgf_reset", "svgf_render", "svgf_denoise", "svgf_sync",
+           "svgf_denoise_host", "svgf_atrous_host", "svgf_fetch", "svgf_last_error", "svgf_abi_version", "svgf_stage_times",
+           "svgf_set_profiling", "svgf_set_shard", "svgf_camera_init", "svgf_camera_step"]
+
+_lib = None
+
+
+def build():
+    """Compile csrc/ into libsvgf_b200.so (nvcc, sm_100a). Works without a GPU."""
+    subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "csrc")], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SvgfError("libsvgf_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
+        vp, cp, ci, cf = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_float
+        L.svgf_params_default.argtypes = [ctypes.POINTER(Params)]
+        L.svgf_params_default.restype = None
+        L.svgf_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(SceneDesc), ci]
+        L.svgf_destroy.argtypes = [vp]
+        L.svgf_reset.argtypes = [vp]
+        L.svgf_render.argtypes = [vp, ctypes.POINTER(Camera), ctypes.POINTER(Params), ci, vp, vp]
+        L.svgf_denoise.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Camera), ctypes.POINTER(Params)]
+        L.svgf_denoise_host.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Camera), ctypes.POINTER(Params)]
+        L.svgf_atrous_host.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ctypes.POINTER(Params)]
+        L.svgf_sync.argtypes = [vp]
+        L.svgf_fetch.argtypes = [vp, cp, vp, ctypes.c_size_t]
+        L.svgf_last_error.argtypes = [vp]
+        L.svgf_last_error.restype = cp
+        L.svgf_stage_times.argtypes = [vp, vp]
+        L.svgf_set_profiling.argtypes = [vp, ci]
+        L.svgf_set_shard.argtypes = [vp, ctypes.POINTER(Shard)]
+        L.svgf_camera_init.argtypes = [ctypes.POINTER(Camera), ctypes.POINTER(CameraRig), vp, vp, vp, cf, ci, ci]
+        L.svgf_camera_init.restype = None
+        L.svgf_camera_step.argtypes = [ctypes.POINTER(Camera), ctypes.POINTER(CameraRig), ci, vp]
+        L.svgf_camera_step.restype = None
+        _lib = L
+    return _lib
+
+
+def default_params(**over):
+    """main.cpp:39-62 defaults with the GUI "All" button (preview.cpp:294-299)."""
+    p = Params()
+    lib().svgf_params_default(ctypes.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+BUFFERS = {
+    "image": (np.float32, (3,)), "denoised": (np.float32, (3,)), "host_image": (np.float32, (3,)),
+    "gbuffer": (np.float32, (13,)), "variance": (np.float32, ()), "color_history": (np.float32, (3,)),
+    "variance_history": (np.float32, ()), "moment_acc": (np.float32, (2,)), "moment_history": (np.float32, (2,)),
+    "history_length": (np.int32, ()), "history_length_update": (np.int32, ()),
+}
+
+
+class CameraDriver:
+    """resetCamera + the camera block of runCuda (main.cpp:77-101, 154-190) through the C ABI."""
+    SPEEDS_C5 = (0.05, 0.02, 0.02, 0.02, 0.05)
+
+    def __init__(self, eye, lookat, up, fovy, W, H, automate=False, speeds=SPEEDS_C5):
+        self.cam, self.rig = Camera(), CameraRig()
+        e, l, u = (np.asarray(v, np.float32) for v in (eye, lookat, up))
+        lib().svgf_camera_init(ctypes.byref(self.cam), ctypes.byref(self.rig), e.ctypes.data, l.ctypes.data, u.ctypes.data,
+                               fovy, W, H)
+        self.automate, self.speeds, self.first = automate, np.asarray(speeds, np.float32), True
+
+    def step(self):
+        if self.automate or self.first:
+            lib().svgf_camera_step(ctypes.byref(self.cam), ctypes.byref(self.rig), int(self.automate), self.speeds.ctypes.data)
+            self.first = False
+        return self.cam
+
+
+class Renderer:
+    """One svgf_ctx: pathtraceInit+denoiseInit ... pathtrace(pbo, frame) ... pathtraceFree+denoiseFree."""
+
+    def __init__(self, scene_desc, W, H, device=0):
+        self.W, self.H = W, H
+        self._desc = scene_desc     # keeps host arrays alive during create
+        scene_desc.width, scene_desc.height = W, H
+        h = ctypes.c_void_p()
+        rc = lib().svgf_create(ctypes.byref(h), ctypes.byref(scene_desc), device)
+        if rc != SVGF_OK:
+            raise SvgfError("svgf_create -> %d: %s" % (rc, lib().svgf_last_error(None).decode()))
+        self.h = h
+
+    def _ck(self, rc, what):
+        if rc != SVGF_OK:
+            raise SvgfError("%s -> %d: %s" % (what, rc, lib().svgf_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().svgf_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self):
+        self._ck(lib().svgf_reset(self.h), "svgf_reset")
+
+    def set_shard(self, rank, world, row_begin, row_end):
+        s = Shard(rank, world, row_begin, row_end)
+        self._ck(lib().svgf_set_shard(self.h, ctypes.byref(s)), "svgf_set_shard")
+
+    def set_profiling(self, on):
+        self._ck(lib().svgf_set_profiling(self.h, int(on)), "svgf_set_profiling")
+
+    def stage_times(self):
+        a = np.zeros(11, np.float32)
+        self._ck(lib().svgf_stage_times(self.h, a.ctypes.data), "svgf_stage_times")
+        return a
+
+    def pathtrace(self, cam, params, frame, pbo_dev=None, host_image=None):
+        """== pathtrace(pbo, frame). host_image: (H, W, 3) float32 numpy array to fill (scene->state.image), or None."""
+        hp = host_image.ctypes.data if host_image is not None else None
+        self._ck(lib().svgf_render(self.h, ctypes.byref(cam), ctypes.byref(params), frame, pbo_dev, hp), "svgf_render")
+
+    def sync(self):
+        self._ck(lib().svgf_sync(self.h), "svgf_sync")
+
+    def denoise(self, color_in, gbuffer, cam, params):
+        """== denoise(output, input, gbuffer) on host arrays in the reference's AoS layouts."""
+        ci = np.ascontiguousarray(color_in, np.float32); g = np.ascontiguousarray(gbuffer, np.float32)
+        out = np.empty_like(ci)
+        self._ck(lib().svgf_denoise_host(self.h, out.ctypes.data, ci.ctypes.data, g.ctypes.data, ctypes.byref(cam),
+                                         ctypes.byref(params)), "svgf_denoise_host")
+        return out
+
+    def atrous_level(self, color_in, variance_in, gbuffer, level, is_last, params):
+        ci = np.ascontiguousarray(color_in, np.float32); vi = np.ascontiguousarray(variance_in, np.float32)
+        g = np.ascontiguousarray(gbuffer, np.float32)
+        co = np.empty_like(ci); vo = np.empty_like(vi)
+        self._ck(lib().svgf_atrous_host(self.h, co.ctypes.data, vo.ctypes.data, ci.ctypes.data, vi.ctypes.data, g.ctypes.data,
+                                        level, int(is_last), ctypes.byref(params)), "svgf_atrous_host")
+        return co, vo
+
+    def fetch(self, name):
+        if name == "pbo":
+            a = np.empty((self.H, 2 * self.W, 4), np.uint8)
+        elif name == "view_matrix_prev":
+            a = np.empty(16, np.float32)
+        else:
+            dt, tail = BUFFERS[name]
+            a = np.empty((self.H, self.W) + tail, dt)
+        self._ck(lib().svgf_fetch(self.h, name.encode(), a.ctypes.data, a.nbytes), "svgf_fetch(%s)" % name)
+        return a
+
+
+# ---- scene blobs (tests/golden/scenes/*.scene) -------------------------------------------------------
+# The arrays the reference's Scene loader produces (src/scene.cpp), in the reference's own struct layouts,
+# exported once by oracle/ref/harness.cpp:refh_export_scene. Layout: 40-byte header {"SVGFSCN1", n_geoms,
+# n_materials, n_tris, n_bvh, n_boxes, n_textures, fovy, 0}, Camera (84 B), Geom[248 B], Material[56 B],
+# Triangle[136 B], BVH_ArrNode[40 B], BoundingBox[24 B], then per texture {w, h, comp} + RGB8 bytes.
+class SceneBlob:
+    def __init__(self, path):
+        raw = np.fromfile(path, np.uint8)
+        if raw[:8].tobytes() != b"SVGFSCN1":
+            raise SvgfError("%s is not a scene blob" % path)
+        hdr = raw[8:32].view(np.int32)
+        ng, nm, nt, nb, nx, ntex = (int(v) for v in hdr)
+        self.fovy = float(raw[32:36].view(np.float32)[0])
+        off = 40
+        self.loader_camera = Camera.from_buffer_copy(raw[off:off + 84].tobytes()); off += 84
+        def take(n, sz):
+            nonlocal off
+            a = np.ascontiguousarray(raw[off:off + n * sz]).copy(); off += n * sz
+            return a
+        self.geoms, self.materials = take(ng, 248), take(nm, 56)
+        self.triangles, self.bvh = take(nt, 136), take(nb, 40)
+        take(nx, 24)
+        self.textures = []
+        for _ in range(ntex):
+            w, h, c = (int(v) for v in raw[off:off + 12].view(np.int32)); off += 12
+            self.textures.append((w, h, c, take(w * h * c, 1)))
+        self.counts = dict(geoms=ng, materials=nm, tris=nt, bvh=nb, boxes=nx, textures=ntex)
+
+    def desc(self, W, H):
+        d = SceneDesc()
+        d.geoms, d.n_geoms = self.geoms.ctypes.data, self.counts["geoms"]
+        d.materials, d.n_materials = self.materials.ctypes.data, self.counts["materials"]
+        d.triangles, d.n_triangles = self.triangles.ctypes.data, self.counts["tris"]
+        d.bvh_nodes, d.n_bvh_nodes = self.bvh.ctypes.data, self.counts["bvh"]
+        self._tex = (TextureDesc * max(1, len(self.textures)))()
+        for i, (w, h, c, px) in enumerate(self.textures):
+            self._tex[i] = TextureDesc(w, h, c, px.ctypes.data)
+        d.textures, d.n_textures = ctypes.cast(self._tex, ctypes.c_void_p), len(self.textures)
+        d.width, d.height = W, H
+        d._keepalive = self
+        return d
+
+    def camera_driver(self, W, H, automate=False, speeds=CameraDriver.SPEEDS_C5):
+        lc = self.loader_camera
+        return CameraDriver(lc.position[:], lc.lookAt[:], lc.up[:], self.fovy, W, H, automate, speeds)
+
+
+def scene_path(name):
+    if os.path.exists(name):
+        return name
+    return os.path.join(os.path.dirname(_HERE), "tests", "golden", "scenes", name + ".scene")
+
+
+def open_scene(name, W, H, device=0):
+    """Convenience: blob -> (SceneBlob, Renderer)."""
+    blob = SceneBlob(scene_path(name))
+    return blob, Renderer(blob.desc(W, H), W, H, device)

@@ -1,0 +1,468 @@
+// api.cu -- the C ABI (include/svgf_b200.h): context lifecycle, scene upload, the per-frame driver.
+//
+// Frame driver = pathtrace() (src/pathtrace.cu:404-452) + denoise() (src/denoise.cu:349-402) of the reference,
+// re-plumbed for one CUDA stream with no host synchronisation inside the frame:
+//   * the reference's 6-7 device-to-device copies per frame (176 B/pixel) are replaced by rotating which buffer
+//     plays "history" / "accumulated" / "ping" / "pong";
+//   * its 4 cudaDeviceSynchronize + pageable D2H are replaced by one async copy into pinned memory and a single
+//     stream synchronise, only when the caller asked for the host image.
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include "svgf_internal.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+static thread_local std::string g_create_err;
+
+static_assert(sizeof(svgf_geom) == 248 && sizeof(svgf_material) == 56 && sizeof(svgf_triangle) == 136 &&
+              sizeof(svgf_bvh_node) == 40 && sizeof(svgf_camera) == 84 && sizeof(svgf_gbuffer_texel) == 52 &&
+              sizeof(svgf_path_segment) == 48 && sizeof(svgf_intersection) == 36,
+              "reference ABI sizes (SURVEY.md 8(a) T1-T10)");
+static_assert(offsetof(svgf_geom, transform) == 44 && offsetof(svgf_geom, inverseTransform) == 108 &&
+              offsetof(svgf_geom, invTranspose) == 172 && offsetof(svgf_geom, T_startidx) == 236, "Geom offsets");
+static_assert(offsetof(svgf_material, specular_color) == 16 && offsetof(svgf_material, hasReflective) == 28 &&
+              offsetof(svgf_material, emittance) == 40 && offsetof(svgf_material, texid) == 48, "Material offsets");
+static_assert(offsetof(svgf_triangle, verts) == 4 && offsetof(svgf_triangle, normal) == 100, "Triangle offsets");
+static_assert(offsetof(svgf_bvh_node, primitive_count) == 24 && offsetof(svgf_bvh_node, rightchildoffset) == 36, "BVH_ArrNode offsets");
+static_assert(offsetof(svgf_camera, position) == 8 && offsetof(svgf_camera, right) == 56 && offsetof(svgf_camera, pixelLength) == 76, "Camera offsets");
+static_assert(offsetof(svgf_gbuffer_texel, position) == 12 && offsetof(svgf_gbuffer_texel, geomId) == 48, "GBufferTexel offsets");
+static_assert(offsetof(svgf_intersection, materialId) == 16 && offsetof(svgf_intersection, uv) == 28, "ShadeableIntersection offsets");
+static_assert(offsetof(svgf_path_segment, pixelIndex) == 36 && offsetof(svgf_path_segment, diffuse) == 44, "PathSegment offsets");
+
+#define CK(call)                                                                    \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);            \
+            return SVGF_ERR_CUDA;                                                   \
+        }                                                                           \
+    } while (0)
+
+template <typename T> static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n ? n * sizeof(T) : sizeof(T)); }
+
+static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
+    DeviceScene &s = c->scene;
+    // geoms -> GeomD
+    std::vector<GeomD> gd(d->n_geoms);
+    for (int i = 0; i < d->n_geoms; i++) {
+        const svgf_geom &g = d->geoms[i];
+        GeomD &o = gd[i];
+        memset(&o, 0, sizeof(o));
+        o.type = g.type; o.materialid = g.materialid;
+        o.tri_begin = g.type == 2 ? g.T_startidx : 0; o.tri_end = g.type == 2 ? g.T_endidx : 0;
+        memcpy(o.translation, g.translation, 12);
+        memcpy(o.inverseTransform, g.inverseTransform, 64); memcpy(o.transform, g.transform, 64); memcpy(o.invTranspose, g.invTranspose, 64);
+        if (g.materialid < 0 || g.materialid >= d->n_materials) { c->err = "geom references a material out of range"; return SVGF_ERR_INVALID; }
+    }
+    s.n_geoms = d->n_geoms; s.n_materials = d->n_materials; s.n_nodes = d->n_bvh_nodes; s.n_tris = d->n_triangles; s.n_textures = d->n_textures;
+    CK(dalloc(&s.geoms, gd.size()));
+    CK(cudaMemcpy(s.geoms, gd.data(), gd.size() * sizeof(GeomD), cudaMemcpyHostToDevice));
+    for (int i = 0; i < d->n_materials; i++)
+        if (d->materials[i].texid != -1 && (d->materials[i].texid < 0 || d->materials[i].texid >= d->n_textures)) {
+            c->err = "material references a texture out of range"; return SVGF_ERR_INVALID;
+        }
+    CK(dalloc(&s.materials, (size_t)d->n_materials));
+    CK(cudaMemcpy(s.materials, d->materials, (size_t)d->n_materials * sizeof(svgf_material), cudaMemcpyHostToDevice));
+    // BVH nodes 40 B -> 2 x float4
+    std::vector<float4> bv(2 * (size_t)d->n_bvh_nodes);
+    for (int i = 0; i < d->n_bvh_nodes; i++) {
+        const svgf_bvh_node &n = d->bvh_nodes[i];
+        const bool leaf = n.primitive_count > 0;
+        if (leaf && (n.primitive_count > 0xffff || n.primitivesOffset < 0 || n.primitivesOffset + n.primitive_count > d->n_triangles)) {
+            c->err = "BVH leaf out of range"; return SVGF_ERR_INVALID;
+        }
+        if (!leaf && (n.axis < 0 || n.axis > 2 || n.rightchildoffset <= i || n.rightchildoffset >= d->n_bvh_nodes || i + 1 >= d->n_bvh_nodes)) {
+            c->err = "BVH interior node malformed"; return SVGF_ERR_INVALID;
+        }
+        int meta = leaf ? n.primitive_count : (n.axis << 16);
+        int off = leaf ? n.primitivesOffset : n.rightchildoffset;
+        float fm, fo; memcpy(&fm, &meta, 4); memcpy(&fo, &off, 4);
+        bv[2 * i] = make_float4(n.bounds_min[0], n.bounds_min[1], n.bounds_min[2], fm);
+        bv[2 * i + 1] = make_float4(n.bounds_max[0], n.bounds_max[1], n.bounds_max[2], fo);
+    }
+    CK(dalloc(&s.bvh, bv.size()));
+    if (!bv.empty()) CK(cudaMemcpy(s.bvh, bv.data(), bv.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    // triangles 136 B -> hot {v0,id} {e1} {e2} + cold {n0,u0} {n1,v0} {n2,u1} {v1,u2,v2}
+    std::vector<float4> hot(3 * (size_t)d->n_triangles), cold(4 * (size_t)d->n_triangles);
+    for (int i = 0; i < d->n_triangles; i++) {
+        const svgf_triangle &t = d->triangles[i];
+        const float *v0 = t.verts[0].pos, *v1 = t.verts[1].pos, *v2 = t.verts[2].pos;
+        float fid; memcpy(&fid, &t.id, 4);
+        // e1 = v1 - v0, e2 = v2 - v0 exactly as glm::intersectRayTriangle forms them (gtx/intersect.inl:44-45);
+        // an fp32 subtraction gives the same bits on the host as on the device
+        hot[3 * i] = make_float4(v0[0], v0[1], v0[2], fid);
+        hot[3 * i + 1] = make_float4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], 0.f);
+        hot[3 * i + 2] = make_float4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0.f);
+        const float *n0 = t.verts[0].normal, *n1 = t.verts[1].normal, *n2 = t.verts[2].normal;
+        cold[4 * i] = make_float4(n0[0], n0[1], n0[2], t.verts[0].uv[0]);
+        cold[4 * i + 1] = make_float4(n1[0], n1[1], n1[2], t.verts[0].uv[1]);
+        cold[4 * i + 2] = make_float4(n2[0], n2[1], n2[2], t.verts[1].uv[0]);
+        cold[4 * i + 3] = make_float4(t.verts[1].uv[1], t.verts[2].uv[0], t.verts[2].uv[1], 0.f);
+    }
+    CK(dalloc(&s.tri_hot, hot.size())); CK(dalloc(&s.tri_cold, cold.size()));
+    if (!hot.empty()) {
+        CK(cudaMemcpy(s.tri_hot, hot.data(), hot.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.tri_cold, cold.data(), cold.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    // textures
+    std::vector<TexD> td(d->n_textures);
+    for (int i = 0; i < d->n_textures; i++) {
+        const svgf_texture_desc &t = d->textures[i];
+        const size_t n = (size_t)t.width * t.height * t.components;
+        unsigned char *dp = nullptr;
+        CK(cudaMalloc((void **)&dp, n ? n : 1));
+        s.tex_pixels.push_back(dp);
+        if (n) CK(cudaMemcpy(dp, t.pixels, n, cudaMemcpyHostToDevice));
+        td[i].w = t.width; td[i].h = t.height; td[i].comp = t.components; td[i].pad = 0; td[i].px = dp;
+    }
+    CK(dalloc(&s.textures, td.size()));
+    if (!td.empty()) CK(cudaMemcpy(s.textures, td.data(), td.size() * sizeof(TexD), cudaMemcpyHostToDevice));
+    return SVGF_OK;
+}
+
+static int alloc_frame_buffers(svgf_ctx *c) {
+    const size_t px = c->px;
+    for (int i = 0; i < 3; i++) CK(dalloc(&c->cv[i], px));
+    for (int i = 0; i < 2; i++) { CK(dalloc(&c->nrm[i], px)); CK(dalloc(&c->mom[i], px)); CK(dalloc(&c->hlen[i], px)); }
+    CK(dalloc(&c->pos, px)); CK(dalloc(&c->alb, px));
+    CK(dalloc(&c->image, 3 * px)); CK(dalloc(&c->denoised, 3 * px)); CK(dalloc(&c->var_out, px));
+    CK(dalloc(&c->stale_nm, px)); CK(dalloc(&c->stale_uv, px));
+    CK(cudaMalloc((void **)&c->pbo_own, px * 8));
+    CK(cudaMallocHost((void **)&c->pinned_image, px * 12));
+    for (int i = 0; i < 16; i++) CK(cudaEventCreate(&c->ev[i]));
+    return SVGF_OK;
+}
+
+extern "C" {
+
+int svgf_abi_version(void) { return SVGF_ABI_VERSION; }
+
+void svgf_params_default(svgf_params *p) {
+    memset(p, 0, sizeof(*p));
+    p->tracedepth = 4; p->shadowray = 1; p->reducevar = 1; p->sintensity = 2.7f; p->lightradius = 1.4f;
+    p->denoise_enable = 1; p->sepcolor = 1; p->temporal_enable = 1; p->color_alpha = 0.2f; p->moment_alpha = 0.2f;
+    p->right_view_option = 0; p->atrous_nlevel = 5; p->spatial_enable = 1; p->history_level = 1;
+    p->sigmal = 0.45f; p->sigman = 0.2f; p->sigmax = 0.35f; p->blurvariance = 1; p->addcolor = 1;
+}
+
+const char *svgf_last_error(const svgf_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
+    if (!out || !scene || scene->width <= 0 || scene->height <= 0 || scene->n_geoms <= 0 || scene->n_materials <= 0) {
+        g_create_err = "svgf_create: invalid scene description";
+        return SVGF_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_err = "svgf_create: no usable CUDA device (this library has no CPU path)";
+        (void)cudaGetLastError();
+        return SVGF_ERR_NO_DEVICE;
+    }
+    svgf_ctx *c = new (std::nothrow) svgf_ctx();
+    if (!c) return SVGF_ERR_INVALID;
+    c->device = device; c->W = scene->width; c->H = scene->height; c->px = (size_t)c->W * c->H;
+    c->shard = svgf_shard{0, 1, 0, c->H};
+    memset(c->view_matrix_prev, 0, sizeof(c->view_matrix_prev));
+    c->view_matrix_prev[0] = c->view_matrix_prev[5] = c->view_matrix_prev[10] = c->view_matrix_prev[15] = 1.0f;   // glm::mat4()
+    int rc = SVGF_OK;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_err = std::string("svgf_create: ") + cudaGetErrorString(e); delete c; return SVGF_ERR_CUDA; }
+    rc = upload_scene(c, scene);
+    if (rc == SVGF_OK) rc = alloc_frame_buffers(c);
+    if (rc == SVGF_OK) rc = svgf_reset(c);
+    if (rc != SVGF_OK) { g_create_err = c->err; svgf_destroy(c); return rc; }
+    *out = c;
+    return SVGF_OK;
+}
+
+int svgf_destroy(svgf_ctx *c) {
+    if (!c) return SVGF_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DeviceScene &s = c->scene;
+    cudaFree(s.geoms); cudaFree(s.materials); cudaFree(s.bvh); cudaFree(s.tri_hot); cudaFree(s.tri_cold); cudaFree(s.textures);
+    for (unsigned char *p : s.tex_pixels) cudaFree(p);      // the reference leaks these (pathtrace.cu:136 vs 160-183)
+    for (int i = 0; i < 3; i++) cudaFree(c->cv[i]);
+    for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }
+    cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
+    cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own);
+    cudaFree(c->aos_in); cudaFree(c->aos_out); cudaFree(c->aos_g);
+    if (c->pinned_image) cudaFreeHost(c->pinned_image);
+    for (int i = 0; i < 16; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SVGF_OK;
+}
+
+// pathtraceInit (pathtrace.cu:108-128) + denoiseInit (denoise.cu:41-60): zero what the reference zeroes. Buffers it
+// leaves uninitialised (colour history, previous G-buffer, ping-pong) are zeroed too; they are never read before
+// being written because history_length == 0 gates every history read (denoise.cu:198).
+int svgf_reset(svgf_ctx *c) {
+    if (!c) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const size_t px = c->px;
+    cudaStream_t st = c->stream;
+    for (int i = 0; i < 3; i++) CK(cudaMemsetAsync(c->cv[i], 0, px * sizeof(float4), st));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMemsetAsync(c->nrm[i], 0, px * sizeof(float4), st));
+        CK(cudaMemsetAsync(c->mom[i], 0, px * sizeof(float2), st));
+        CK(cudaMemsetAsync(c->hlen[i], 0, px * sizeof(int), st));
+    }
+    CK(cudaMemsetAsync(c->pos, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->alb, 0, px * sizeof(float4), st));
+    CK(cudaMemsetAsync(c->image, 0, px * 12, st)); CK(cudaMemsetAsync(c->denoised, 0, px * 12, st));
+    CK(cudaMemsetAsync(c->var_out, 0, px * 4, st));
+    CK(cudaMemsetAsync(c->stale_nm, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->stale_uv, 0, px * sizeof(float2), st));
+    CK(cudaMemsetAsync(c->pbo_own, 0, px * 8, st));
+    c->hist_cv = 0; c->cur_nrm = 0; c->cur_mom = 0; c->cur_hlen = 0;
+    CK(cudaStreamSynchronize(st));
+    return SVGF_OK;
+}
+
+int svgf_set_shard(svgf_ctx *c, const svgf_shard *s) {
+    if (!c || !s || s->world < 1 || s->rank < 0 || s->rank >= s->world || s->row_begin < 0 || s->row_end > c->H || s->row_begin > s->row_end) {
+        if (c) c->err = "svgf_set_shard: invalid shard";
+        return SVGF_ERR_INVALID;
+    }
+    c->shard = *s;
+    return SVGF_OK;
+}
+
+int svgf_set_profiling(svgf_ctx *c, int enabled) { if (!c) return SVGF_ERR_INVALID; c->profiling = enabled != 0; return SVGF_OK; }
+
+int svgf_stage_times(svgf_ctx *c, float *ms11) {
+    if (!c || !ms11) return SVGF_ERR_INVALID;
+    memcpy(ms11, c->stage_ms, sizeof(c->stage_ms));
+    return SVGF_OK;
+}
+
+int svgf_sync(svgf_ctx *c) {
+    if (!c) return SVGF_ERR_INVALID;
+    CK(cudaStreamSynchronize(c->stream));
+    return SVGF_OK;
+}
+
+}  // extern "C"
+
+// ---- the denoise driver on SoA planes (denoise.cu:349-402) -------------------------------------------
+// Inputs: c->image (1-spp colour), c->nrm[cur_nrm], c->pos, c->alb. Output: c->denoised, c->var_out.
+static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, const svgf_params *P, cudaEvent_t *ev) {
+    const int acc_slot = (c->hist_cv + 1) % 3;          // any buffer that is not the current history
+    const float4 *hist = c->cv[c->hist_cv];
+    float4 *acc = c->cv[acc_slot];
+    const float color_alpha = P->temporal_enable ? P->color_alpha : 1.0f;
+    const float moment_alpha = P->temporal_enable ? P->moment_alpha : 1.0f;
+    if (P->temporal_enable) {
+        CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->nrm[c->cur_nrm ^ 1], c->pos, hist, c->mom[c->cur_mom],
+                           c->hlen[c->cur_hlen], acc, c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1], c->view_matrix_prev,
+                           color_alpha, moment_alpha, 1));
+    } else {
+        CK(launch_no_temporal(c, image, acc));
+    }
+    if (ev) CK(cudaEventRecord(ev[2], c->stream));
+    int new_hist = acc_slot;        // denoise.cu:366/370: colour history := accumulated (or input) colour
+    if (P->right_view_option == 1) {
+        // DebugView shows dev_history_length, i.e. the length BEFORE this frame's update (denoise.cu:374)
+        CK(launch_cv_to_outputs(c, acc, c->denoised, c->var_out));
+        CK(launch_debug_view(c, 1, c->hlen[c->cur_hlen], acc, c->denoised));
+    } else if (P->right_view_option == 2) {
+        CK(launch_cv_to_outputs(c, acc, c->denoised, c->var_out));
+        CK(launch_debug_view(c, 2, c->hlen[c->cur_hlen], acc, c->denoised));
+    } else if (P->atrous_nlevel == 0 || !P->spatial_enable) {
+        CK(launch_cv_to_outputs(c, acc, c->denoised, c->var_out));
+    } else {
+        int src = acc_slot;
+        for (int level = 1; level <= P->atrous_nlevel; level++) {
+            const bool last = level == P->atrous_nlevel;
+            const bool is_hist = level == P->history_level;
+            // destination: any slot that is neither the source nor the (new) history
+            int dst = -1;
+            for (int s = 0; s < 3; s++) if (s != src && s != new_hist) { dst = s; break; }
+            AtrousArgs a;
+            a.cv_in = c->cv[src];
+            a.cv_out = (!last || is_hist) ? c->cv[dst] : nullptr;
+            a.nrm = c->nrm[c->cur_nrm]; a.pos = c->pos; a.alb = c->alb;
+            a.denoised_out = last ? c->denoised : nullptr; a.var_out = last ? c->var_out : nullptr;
+            a.level = level; a.is_last = last; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
+            a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;
+            CK(launch_atrous(c, a));
+            if (ev && level <= SVGF_MAX_LEVELS) CK(cudaEventRecord(ev[2 + level], c->stream));
+            if (is_hist) new_hist = dst;     // denoise.cu:391: colour history := this level's output
+            src = dst;
+        }
+    }
+    // denoise.cu:396-399 by rotation
+    c->hist_cv = new_hist;
+    c->cur_nrm ^= 1;            // this frame's normals/geomIds become "previous"
+    if (P->temporal_enable) { c->cur_mom ^= 1; c->cur_hlen ^= 1; }
+    svgf_view_matrix(cam, c->view_matrix_prev);
+    return SVGF_OK;
+}
+// NOTE on the temporal-off path: the reference still copies moment_acc/history_length_update (never written in that
+// frame, denoise.cu:397-398) over the histories, i.e. leaves them undefined; here they simply stay as they were.
+
+static void collect_times(svgf_ctx *c, int nlevel, bool denoise) {
+    // ev[0] start, ev[1] after rt, ev[2] after temporal, ev[3..9] after a-trous level 1..7, ev[10] after pack, ev[11] end
+    memset(c->stage_ms, 0, sizeof(c->stage_ms));
+    cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
+    cudaEvent_t prev = c->ev[1];
+    if (denoise) {
+        cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
+        prev = c->ev[2];
+        for (int l = 1; l <= nlevel && l <= SVGF_MAX_LEVELS; l++) {
+            cudaEventElapsedTime(&c->stage_ms[1 + l], prev, c->ev[2 + l]);
+            prev = c->ev[2 + l];
+        }
+    }
+    cudaEventElapsedTime(&c->stage_ms[9], prev, c->ev[10]);
+    cudaEventElapsedTime(&c->stage_ms[10], c->ev[0], c->ev[11]);
+}
+
+extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, float *host_image) {
+    if (!c || !cam || !P) return SVGF_ERR_INVALID;
+    if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_render: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
+    if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS || P->tracedepth < 0) { c->err = "svgf_render: parameter out of range"; return SVGF_ERR_INVALID; }
+    CK(cudaSetDevice(c->device));
+    cudaEvent_t *ev = c->profiling ? c->ev : nullptr;
+    if (ev) CK(cudaEventRecord(ev[0], c->stream));
+    RtParams rp;
+    rp.W = c->W; rp.H = c->H; rp.row_begin = c->shard.row_begin; rp.row_end = c->shard.row_end;
+    rp.frame = frame; rp.max_depth = P->tracedepth; rp.trace_shadowray = P->shadowray; rp.reduce_var = P->reducevar;
+    rp.denoise = P->denoise_enable; rp.sepcolor = P->sepcolor; rp.sintensity = P->sintensity; rp.lightradius = P->lightradius;
+    rp.cam = *cam;
+    CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm]));
+    if (ev) CK(cudaEventRecord(ev[1], c->stream));
+    if (P->denoise_enable) {
+        int rc = denoise_soa(c, c->image, cam, P, ev);
+        if (rc != SVGF_OK) return rc;
+    } else {
+        CK(launch_copy_f3(c, c->denoised, c->image));        // pathtrace.cu:440
+    }
+    unsigned char *pbo = pbo_dev ? static_cast<unsigned char *>(pbo_dev) : c->pbo_own;
+    CK(launch_pack_pbo(c, pbo, c->image, c->denoised));
+    if (ev) CK(cudaEventRecord(ev[10], c->stream));
+    if (host_image) {   // pathtrace.cu:450, through pinned staging so the copy is a real async DMA
+        const size_t off = (size_t)c->shard.row_begin * c->W * 3, n = (size_t)(c->shard.row_end - c->shard.row_begin) * c->W * 3;
+        CK(cudaMemcpyAsync(c->pinned_image + off, c->denoised + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (ev) CK(cudaEventRecord(ev[11], c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        memcpy(host_image + off, c->pinned_image + off, n * sizeof(float));
+    } else if (ev) {
+        CK(cudaEventRecord(ev[11], c->stream));
+    }
+    if (ev) { CK(cudaStreamSynchronize(c->stream)); collect_times(c, P->atrous_nlevel, P->denoise_enable && P->spatial_enable && P->right_view_option == 0); }
+    return SVGF_OK;
+}
+
+extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_dev, const svgf_gbuffer_texel *gbuffer_dev,
+                            const svgf_camera *cam, const svgf_params *P) {
+    if (!c || !output_dev || !input_dev || !gbuffer_dev || !cam || !P) return SVGF_ERR_INVALID;
+    if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_denoise: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
+    if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS) { c->err = "svgf_denoise: atrous_nlevel out of range"; return SVGF_ERR_INVALID; }
+    CK(cudaSetDevice(c->device));
+    cudaEvent_t *ev = c->profiling ? c->ev : nullptr;
+    if (ev) { CK(cudaEventRecord(ev[0], c->stream)); CK(cudaEventRecord(ev[1], c->stream)); }
+    CK(launch_aos_to_soa(c, gbuffer_dev, c->nrm[c->cur_nrm], c->pos, c->alb));
+    int rc = denoise_soa(c, input_dev, cam, P, ev);
+    if (rc != SVGF_OK) return rc;
+    CK(cudaMemcpyAsync(output_dev, c->denoised, c->px * 12, cudaMemcpyDeviceToDevice, c->stream));
+    if (ev) { CK(cudaEventRecord(ev[10], c->stream)); CK(cudaEventRecord(ev[11], c->stream)); }
+    CK(cudaStreamSynchronize(c->stream));       // denoise.cu:401
+    if (ev) collect_times(c, P->atrous_nlevel, P->spatial_enable && P->right_view_option == 0);
+    return SVGF_OK;
+}
+
+static int ensure_aos(svgf_ctx *c) {
+    if (!c->aos_in) { CK(dalloc(&c->aos_in, 3 * c->px)); CK(dalloc(&c->aos_out, 3 * c->px)); CK(dalloc(&c->aos_g, c->px)); }
+    return SVGF_OK;
+}
+
+extern "C" int svgf_denoise_host(svgf_ctx *c, float *output, const float *input, const svgf_gbuffer_texel *gbuffer,
+                                 const svgf_camera *cam, const svgf_params *P) {
+    if (!c || !output || !input || !gbuffer) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_aos(c);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->aos_in, input, c->px * 12, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->aos_g, gbuffer, c->px * sizeof(svgf_gbuffer_texel), cudaMemcpyHostToDevice, c->stream));
+    rc = svgf_denoise(c, c->aos_out, c->aos_in, c->aos_g, cam, P);
+    if (rc) return rc;
+    CK(cudaMemcpy(output, c->aos_out, c->px * 12, cudaMemcpyDeviceToHost));
+    return SVGF_OK;
+}
+
+extern "C" int svgf_atrous_host(svgf_ctx *c, float *color_out, float *variance_out, const float *color_in,
+                                const float *variance_in, const svgf_gbuffer_texel *gbuffer, int level, int is_last,
+                                const svgf_params *P) {
+    if (!c || !color_out || !variance_out || !color_in || !variance_in || !gbuffer || !P || level < 1 || level > SVGF_MAX_LEVELS) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_aos(c);
+    if (rc) return rc;
+    const size_t px = c->px;
+    std::vector<float4> cv(px);
+    for (size_t i = 0; i < px; i++) cv[i] = make_float4(color_in[3 * i], color_in[3 * i + 1], color_in[3 * i + 2], variance_in[i]);
+    CK(cudaMemcpyAsync(c->cv[0], cv.data(), px * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->aos_g, gbuffer, px * sizeof(svgf_gbuffer_texel), cudaMemcpyHostToDevice, c->stream));
+    CK(launch_aos_to_soa(c, c->aos_g, c->nrm[0], c->pos, c->alb));
+    AtrousArgs a;
+    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb;
+    a.denoised_out = is_last ? c->denoised : nullptr; a.var_out = is_last ? c->var_out : nullptr;
+    a.level = level; a.is_last = is_last != 0; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
+    a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;
+    CK(launch_atrous(c, a));
+    CK(cudaMemcpyAsync(cv.data(), c->cv[1], px * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < px; i++) { color_out[3 * i] = cv[i].x; color_out[3 * i + 1] = cv[i].y; color_out[3 * i + 2] = cv[i].z; variance_out[i] = cv[i].w; }
+    c->hist_cv = 0; c->cur_nrm = 0;     // scratch use of the frame buffers: caller should svgf_reset before rendering again
+    return SVGF_OK;
+}
+
+namespace {
+__global__ void split_cv_kernel(size_t n, const float4 *__restrict__ cv, float *__restrict__ rgb, float *__restrict__ w) {
+    const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float4 c = cv[p];
+    if (rgb) { rgb[3 * p] = c.x; rgb[3 * p + 1] = c.y; rgb[3 * p + 2] = c.z; }
+    if (w) w[p] = c.w;
+}
+}  // namespace
+
+extern "C" int svgf_fetch(svgf_ctx *c, const char *name, void *host, size_t bytes) {
+    if (!c || !name || !host) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t px = c->px;
+    auto d2h = [&](const void *src, size_t need) -> int {
+        if (bytes != need) { c->err = std::string("svgf_fetch(") + name + "): size mismatch"; return SVGF_ERR_INVALID; }
+        CK(cudaMemcpy(host, src, need, cudaMemcpyDeviceToHost));
+        return SVGF_OK;
+    };
+    if (!strcmp(name, "image")) return d2h(c->image, px * 12);
+    if (!strcmp(name, "denoised") || !strcmp(name, "host_image")) return d2h(c->denoised, px * 12);
+    if (!strcmp(name, "variance")) return d2h(c->var_out, px * 4);
+    if (!strcmp(name, "pbo")) return d2h(c->pbo_own, px * 8);
+    // after a frame the rotation has already happened: "accumulated"/"update" buffers are the new histories
+    if (!strcmp(name, "moment_acc") || !strcmp(name, "moment_history")) return d2h(c->mom[c->cur_mom], px * 8);
+    if (!strcmp(name, "history_length") || !strcmp(name, "history_length_update")) return d2h(c->hlen[c->cur_hlen], px * 4);
+    int rc = ensure_aos(c);
+    if (rc) return rc;
+    if (!strcmp(name, "color_history") || !strcmp(name, "variance_history")) {
+        split_cv_kernel<<<(unsigned)((px + 255) / 256), 256, 0, c->stream>>>(px, c->cv[c->hist_cv], c->aos_out, (float *)c->aos_g);
+        CK(cudaGetLastError()); CK(cudaStreamSynchronize(c->stream));
+        return !strcmp(name, "color_history") ? d2h(c->aos_out, px * 12) : d2h(c->aos_g, px * 4);
+    }
+    if (!strcmp(name, "gbuffer") || !strcmp(name, "gbuffer_prev")) {
+        // the frame's G-buffer; after the rotation its normals sit in the "previous" slot
+        CK(launch_soa_to_aos(c, c->nrm[c->cur_nrm ^ 1], c->pos, c->alb, c->aos_g));
+        CK(cudaStreamSynchronize(c->stream));
+        return d2h(c->aos_g, px * sizeof(svgf_gbuffer_texel));
+    }
+    if (!strcmp(name, "view_matrix_prev")) {
+        if (bytes != 64) return SVGF_ERR_INVALID;
+        memcpy(host, c->view_matrix_prev, 64);
+        return SVGF_OK;
+    }
+    c->err = std::string("svgf_fetch: unknown buffer '") + name + "'";
+    return SVGF_ERR_UNKNOWN_NAME;
+}

@@ -1,0 +1,282 @@
+// denoise.cu -- SVGF temporal pass, PBO pack and layout conversion kernels, sm_100a.
+//
+//   temporal_kernel     <- BackProjection + isReprjValid (src/denoise.cu:172-317), fused with the variance
+//                          estimate and writing {colour, variance} as one float4; history is read from whichever
+//                          buffers the previous frame left (pointer rotation instead of denoise.cu:366,396-398)
+//   no_temporal_kernel  <- EstimateVariance + the input->history copy (denoise.cu:320-329, 369-370)
+//   pack_pbo_kernel     <- sendTwoImagesToPBO (src/pathtrace.cu:46-78)
+//   debug_view_kernel   <- DebugView<int|float> (denoise.cu:331-340, 373-378)
+//   aos<->soa           layout conversion for the reference-layout entry point svgf_denoise() and svgf_fetch
+// The a-trous filter itself lives in atrous.cu.
+#include "svgf_internal.h"
+
+namespace {
+
+__device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, float by, float bz) {
+    // glm::distance(a, b) = length(b - a), detail/func_geometric.inl:108-111
+    const float dx = bx - ax, dy = by - ay, dz = bz - az;
+    return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+// isReprjValid, denoise.cu:172-182, for a tap at float coordinates (px, py) of the previous frame.
+// Returns the linear index of the tap through `q`.
+__device__ __forceinline__ bool reprj_valid(int W, int H, float px, float py, const float4 &ncur,
+                                            const float4 *__restrict__ nrm_prev, int &q) {
+    // NaN coordinates pass the reference's bounds test and index garbage (undefined); rejected here.
+    if (!(px >= 0.f) || !(px < (float)W) || !(py >= 0.f) || !(py < (float)H)) return false;
+    q = (int)(px + py * (float)W);
+    const float4 np = __ldg(&nrm_prev[q]);
+    const int gprev = __float_as_int(np.w), gcur = __float_as_int(ncur.w);
+    if (gprev == -1 || gprev != gcur) return false;
+    if (dist3(np.x, np.y, np.z, ncur.x, ncur.y, ncur.z) > 1e-1f) return false;
+    return true;
+}
+
+struct Mat4 { float m[16]; };
+
+// 108 algorithmic bytes per pixel: reads image 12 + normal/geomId 16 + position 12 + own history
+// length 4 + (reprojected, cache-shared) prev normal/geomId 16, colour history 12(16), moments 8, history length 4;
+// writes {colour,variance} 16 + moments 8 + history length 4.
+__global__ void __launch_bounds__(256)
+temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
+                const float4 *__restrict__ nrm_cur, const float4 *__restrict__ nrm_prev, const float4 *__restrict__ pos,
+                const float4 *__restrict__ hist_cv, const float2 *__restrict__ mom_hist, const int *__restrict__ hlen_in,
+                float4 *__restrict__ acc_cv, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
+                float color_alpha_min, float moment_alpha_min) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= row_end) return;
+    const int p = x + y * W;
+    const int N = hlen_in[p];
+    const float sr = image[3 * (size_t)p], sg = image[3 * (size_t)p + 1], sb = image[3 * (size_t)p + 2];
+    const float luminance = 0.2126 * sr + 0.7152 * sg + 0.0722 * sb;    // double, as denoise.cu:196
+    const float4 ncur = nrm_cur[p];
+    if (N > 0 && __float_as_int(ncur.w) != -1) {
+        const float4 pp = pos[p];
+        // prev_viewmat * vec4(position, 1): (m0 v0 + m1 v1) + (m2 v2 + m3 v3), glm type_mat4x4.inl:617-628
+        const float vx = (vm.m[0] * pp.x + vm.m[4] * pp.y) + (vm.m[8] * pp.z + vm.m[12] * 1.0f);
+        const float vy = (vm.m[1] * pp.x + vm.m[5] * pp.y) + (vm.m[9] * pp.z + vm.m[13] * 1.0f);
+        const float vz = (vm.m[2] * pp.x + vm.m[6] * pp.y) + (vm.m[10] * pp.z + vm.m[14] * 1.0f);
+        const float clipx = vx / vz, clipy = vy / vz;
+        const float ndcx = -clipx * 0.5f + 0.5f, ndcy = -clipy * 0.5f + 0.5f;
+        const float prevx = ndcx * W - 0.5f, prevy = ndcy * H - 0.5f;
+        const float floorx = floorf(prevx), floory = floorf(prevy);
+        const float fracx = prevx - floorx, fracy = prevy - floory;
+        bool valid = (floorx >= 0 && floory >= 0 && floorx < W && floory < H);
+        // glm::ivec2(floorx, floory) + offset: saturating cvt, wrapping integer add (as the reference's SASS)
+        const int ifx = __float2int_rz(floorx), ify = __float2int_rz(floory);
+        bool v[4]; int qi[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int lx = (int)((unsigned)ifx + (unsigned)(s & 1)), ly = (int)((unsigned)ify + (unsigned)(s >> 1));
+            qi[s] = 0;
+            v[s] = reprj_valid(W, H, (float)lx, (float)ly, ncur, nrm_prev, qi[s]);
+            qi[s] = lx + ly * W;
+            valid = valid && v[s];
+        }
+        float pr = 0.f, pg = 0.f, pb = 0.f, pm1 = 0.f, pm2 = 0.f, phl = 0.f;
+        if (valid) {
+            float sumw = 0.0f;
+            const float w[4] = {(1 - fracx) * (1 - fracy), fracx * (1 - fracy), (1 - fracx) * fracy, fracx * fracy};
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                if (v[s]) {
+                    const float4 hc = __ldg(&hist_cv[qi[s]]); const float2 hm = __ldg(&mom_hist[qi[s]]);
+                    pr += w[s] * hc.x; pg += w[s] * hc.y; pb += w[s] * hc.z;
+                    pm1 += w[s] * hm.x; pm2 += w[s] * hm.y;
+                    phl += w[s] * (float)__ldg(&hlen_in[qi[s]]);
+                    sumw += w[s];
+                }
+            }
+            if (sumw >= 0.01) {
+                pr /= sumw; pg /= sumw; pb /= sumw; pm1 /= sumw; pm2 /= sumw; phl /= sumw;
+                valid = true;
+            }
+        }
+        if (!valid) {
+            float cnt = 0.0f;
+            for (int yy = -1; yy <= 1; yy++) {
+                for (int xx = -1; xx <= 1; xx++) {
+                    const float lx = floorx + (float)xx, ly = floory + (float)yy;
+                    int q = 0;
+                    if (reprj_valid(W, H, lx, ly, ncur, nrm_prev, q)) {
+                        q = (int)(lx + (float)W * ly);
+                        const float4 hc = __ldg(&hist_cv[q]); const float2 hm = __ldg(&mom_hist[q]);
+                        pr += hc.x; pg += hc.y; pb += hc.z; pm1 += hm.x; pm2 += hm.y;
+                        phl += (float)__ldg(&hlen_in[q]);
+                        cnt += 1.0f;
+                    }
+                }
+            }
+            if (cnt > 0.0f) {
+                pr /= cnt; pg /= cnt; pb /= cnt; pm1 /= cnt; pm2 /= cnt; phl /= cnt;
+                valid = true;
+            }
+        }
+        if (valid) {
+            const float color_alpha = fmaxf(1.0f / (float)(N + 1), color_alpha_min);
+            const float moment_alpha = fmaxf(1.0f / (float)(N + 1), moment_alpha_min);
+            hlen_out[p] = (int)phl + 1;
+            const float first = moment_alpha * pm1 + (1.0f - moment_alpha) * luminance;
+            const float second = moment_alpha * pm2 + (1.0f - moment_alpha) * luminance * luminance;
+            mom_acc[p] = make_float2(first, second);
+            const float variance = second - first * first;
+            acc_cv[p] = make_float4(sr * color_alpha + pr * (1.0f - color_alpha), sg * color_alpha + pg * (1.0f - color_alpha),
+                                    sb * color_alpha + pb * (1.0f - color_alpha), variance > 0.0f ? variance : 0.0f);
+            return;
+        }
+    }
+    hlen_out[p] = 1;
+    mom_acc[p] = make_float2(luminance, luminance * luminance);
+    acc_cv[p] = make_float4(sr, sg, sb, 100.0f);
+}
+
+__global__ void __launch_bounds__(256)
+no_temporal_kernel(int W, int row_begin, int row_end, const float *__restrict__ image, float4 *__restrict__ acc_cv) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= row_end) return;
+    const size_t p = x + (size_t)y * W;
+    acc_cv[p] = make_float4(image[3 * p], image[3 * p + 1], image[3 * p + 2], 10.0f);
+}
+
+// clamp((int)(v * 255.0), 0, 255) with the reference's DOUBLE product (pathtrace.cu:60-62), evaluated in fp32:
+// the float product can only truncate differently from the exact one when it rounded up onto an integer, which the
+// FMA residual detects.
+__device__ __forceinline__ unsigned int to_u8(float v) {
+    const float p = v * 255.0f;
+    int i = __float2int_rz(p);
+    if ((float)i == p && fmaf(v, 255.0f, -p) < 0.0f) i -= 1;
+    return (unsigned int)min(max(i, 0), 255);
+}
+
+__global__ void __launch_bounds__(256)
+pack_pbo_kernel(int W, int row_begin, int row_end, uchar4 *__restrict__ pbo, const float *__restrict__ left,
+                const float *__restrict__ right) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= row_end) return;
+    const size_t idx = x + (size_t)y * W;
+    const size_t li = x + (size_t)y * W * 2;
+    pbo[li] = make_uchar4(to_u8(left[3 * idx]), to_u8(left[3 * idx + 1]), to_u8(left[3 * idx + 2]), 0);
+    pbo[li + W] = make_uchar4(to_u8(right[3 * idx]), to_u8(right[3 * idx + 1]), to_u8(right[3 * idx + 2]), 0);
+}
+
+__global__ void __launch_bounds__(256)
+debug_view_kernel(size_t begin, size_t end, int option, const int *__restrict__ hlen, const float4 *__restrict__ cv,
+                  float *__restrict__ out) {
+    const size_t p = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= end) return;
+    const float v = option == 1 ? (float)hlen[p] / 100.0f : cv[p].w / 0.1f;
+    out[3 * p] = v; out[3 * p + 1] = v; out[3 * p + 2] = v;
+}
+
+__global__ void __launch_bounds__(256)
+cv_to_outputs_kernel(size_t begin, size_t end, const float4 *__restrict__ cv, float *__restrict__ denoised,
+                     float *__restrict__ var_out) {
+    const size_t p = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= end) return;
+    const float4 c = cv[p];
+    denoised[3 * p] = c.x; denoised[3 * p + 1] = c.y; denoised[3 * p + 2] = c.z;
+    var_out[p] = c.w;
+}
+
+__global__ void __launch_bounds__(256)
+aos_to_soa_kernel(size_t n, const svgf_gbuffer_texel *__restrict__ g, float4 *__restrict__ nrm, float4 *__restrict__ pos,
+                  float4 *__restrict__ alb) {
+    const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float *t = reinterpret_cast<const float *>(g + p);
+    nrm[p] = make_float4(t[0], t[1], t[2], t[12]);
+    pos[p] = make_float4(t[3], t[4], t[5], 0.f);
+    // the last a-trous level multiplies by albedo * ialbedo (denoise.cu:167); fold ialbedo in here
+    alb[p] = make_float4(t[6] * t[9], t[7] * t[10], t[8] * t[11], 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+soa_to_aos_kernel(size_t n, const float4 *__restrict__ nrm, const float4 *__restrict__ pos, const float4 *__restrict__ alb,
+                  svgf_gbuffer_texel *__restrict__ g) {
+    const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float4 a = nrm[p], b = pos[p], c = alb[p];
+    float *t = reinterpret_cast<float *>(g + p);
+    t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = b.x; t[4] = b.y; t[5] = b.z; t[6] = c.x; t[7] = c.y; t[8] = c.z;
+    t[9] = 1.0f; t[10] = 1.0f; t[11] = 1.0f;        // ialbedo == 1, pathtrace.cu:323
+    t[12] = a.w;
+}
+
+__global__ void __launch_bounds__(256)
+copy_f3_kernel(size_t begin, size_t end, float *__restrict__ dst, const float *__restrict__ src) {
+    const size_t i = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < end) dst[i] = src[i];
+}
+
+inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (rows + b.y - 1) / b.y); }
+
+}  // namespace
+
+cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const float4 *nrm_prev,
+                            const float4 *pos, const float4 *hist_cv, const float2 *mom_hist, const int *hlen_in,
+                            float4 *acc_cv, float2 *mom_acc, int *hlen_out, const float *prev_viewmat,
+                            float color_alpha, float moment_alpha, int) {
+    const int rows = c->shard.row_end - c->shard.row_begin;
+    if (rows <= 0) return cudaSuccess;
+    Mat4 vm; for (int i = 0; i < 16; i++) vm.m[i] = prev_viewmat[i];
+    dim3 b(32, 8);
+    temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
+                                                                 nrm_prev, pos, hist_cv, mom_hist, hlen_in, acc_cv, mom_acc,
+                                                                 hlen_out, vm, color_alpha, moment_alpha);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv) {
+    const int rows = c->shard.row_end - c->shard.row_begin;
+    if (rows <= 0) return cudaSuccess;
+    dim3 b(32, 8);
+    no_temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->shard.row_begin, c->shard.row_end, image, acc_cv);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_pbo(svgf_ctx *c, unsigned char *pbo, const float *left, const float *right) {
+    const int rows = c->shard.row_end - c->shard.row_begin;
+    if (rows <= 0) return cudaSuccess;
+    dim3 b(32, 8);
+    pack_pbo_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->shard.row_begin, c->shard.row_end,
+                                                                 reinterpret_cast<uchar4 *>(pbo), left, right);
+    return cudaGetLastError();
+}
+
+static inline void strip_range(const svgf_ctx *c, size_t &b, size_t &e) {
+    b = (size_t)c->shard.row_begin * c->W; e = (size_t)c->shard.row_end * c->W;
+}
+
+cudaError_t launch_debug_view(svgf_ctx *c, int option, const int *hlen, const float4 *cv, float *denoised) {
+    size_t b, e; strip_range(c, b, e);
+    if (e <= b) return cudaSuccess;
+    debug_view_kernel<<<(unsigned)((e - b + 255) / 256), 256, 0, c->stream>>>(b, e, option, hlen, cv, denoised);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cv_to_outputs(svgf_ctx *c, const float4 *cv, float *denoised, float *var_out) {
+    size_t b, e; strip_range(c, b, e);
+    if (e <= b) return cudaSuccess;
+    cv_to_outputs_kernel<<<(unsigned)((e - b + 255) / 256), 256, 0, c->stream>>>(b, e, cv, denoised, var_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aos_to_soa(svgf_ctx *c, const svgf_gbuffer_texel *g, float4 *nrm, float4 *pos, float4 *alb) {
+    aos_to_soa_kernel<<<(unsigned)((c->px + 255) / 256), 256, 0, c->stream>>>(c->px, g, nrm, pos, alb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_soa_to_aos(svgf_ctx *c, const float4 *nrm, const float4 *pos, const float4 *alb, svgf_gbuffer_texel *g) {
+    soa_to_aos_kernel<<<(unsigned)((c->px + 255) / 256), 256, 0, c->stream>>>(c->px, nrm, pos, alb, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_copy_f3(svgf_ctx *c, float *dst, const float *src) {
+    size_t b, e; strip_range(c, b, e);
+    if (e <= b) return cudaSuccess;
+    copy_f3_kernel<<<(unsigned)((3 * (e - b) + 255) / 256), 256, 0, c->stream>>>(3 * b, 3 * e, dst, src);
+    return cudaGetLastError();
+}

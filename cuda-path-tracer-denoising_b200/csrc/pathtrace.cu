@@ -1,0 +1,465 @@
+// pathtrace.cu -- 1-spp path-trace feeder, sm_100a.
+//
+// Replaces generateRayFromCamera + rt of the reference (src/pathtrace.cu:187-208, 300-401) and the
+// device libraries they call (src/intersections.h, src/interactions.h, sceneStructs.h:157-221,
+// boundingbox.h:62-79). Per-pixel results are a pure function of (pixel index, frame, depth) because the
+// reference re-seeds its RNG as initRand(idx, frame + depth, 16) at every bounce (pathtrace.cu:328), so any
+// execution order reproduces the reference. The arithmetic follows the reference's (and glm 0.9.6.3's)
+// expression order so results agree to rounding; what is re-designed is everything around it:
+//   * scene tables live in shared memory (geoms, materials) or compact 16-byte records (BVH nodes 32 B instead
+//     of 40 B AoS, triangles as {v0,e1,e2} + a cold shading record instead of one 136 B struct);
+//   * the global BVH is traversed ONCE per query instead of once per MESH geom (pathtrace.cu:244-255): every
+//     mesh geom receives the same closest triangle and only the owner of its id accepts it, so one traversal
+//     and a range test per geom give the same answer;
+//   * normal/uv interpolation is deferred to the winning triangle;
+//   * the G-buffer is written as float4 SoA planes, the persistent per-pixel intersection record is reduced to
+//     the 24 bytes that can be observed (stale normal/material/uv on a primary miss, pathtrace.cu:316-322).
+#include "svgf_internal.h"
+#include <cfloat>
+
+namespace {
+
+#define PI_F 3.1415926535897932384626422832795028841971f
+#define TWO_PI_F 6.2831853071795864769252867665590057683943f
+#define SQRT_OF_ONE_THIRD_F 0.5773502691896257645091487805019574556476f
+#define COLORDIVIDOR_F 0.003921568627f
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 mk(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ F3 operator-(F3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ F3 operator*(F3 a, F3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ F3 operator*(float s, F3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ F3 operator/(F3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float dot(F3 a, F3 b) { F3 t = a * b; return t.x + t.y + t.z; }
+__device__ __forceinline__ F3 cross(F3 x, F3 y) { return mk(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }
+__device__ __forceinline__ float length(F3 v) { return sqrtf(dot(v, v)); }
+__device__ __forceinline__ F3 normalize(F3 v) { return v * (1.0f / sqrtf(dot(v, v))); }
+__device__ __forceinline__ float gmin(float x, float y) { return x < y ? x : y; }
+__device__ __forceinline__ float gmax(float x, float y) { return x > y ? x : y; }
+__device__ __forceinline__ float gabs(float x) { return x >= 0.0f ? x : -x; }
+
+// glm mat4 * vec4 -> xyz, (m0 v0 + m1 v1) + (m2 v2 + m3 v3)   (intersections.h:36-38)
+__device__ __forceinline__ F3 multiplyMV(const float *m, F3 v, float w) {
+    float o[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float add0 = m[0 + r] * v.x + m[4 + r] * v.y;
+        float add1 = m[8 + r] * v.z + m[12 + r] * w;
+        o[r] = add0 + add1;
+    }
+    return mk(o[0], o[1], o[2]);
+}
+
+struct Ray { F3 origin, direction; };
+
+// interactions.h:10-30
+__device__ __forceinline__ unsigned int initRand(unsigned int val0, unsigned int val1) {
+    unsigned int v0 = val0, v1 = val1, s0 = 0;
+#pragma unroll
+    for (unsigned int n = 0; n < 16; n++) {
+        s0 += 0x9e3779b9;
+        v0 += ((v1 << 4) + 0xa341316c) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4);
+        v1 += ((v0 << 4) + 0xad90777d) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761e);
+    }
+    return v0;
+}
+__device__ __forceinline__ float nextRand(unsigned int &s) {
+    s = (1664525u * s + 1013904223u);
+    return float(s & 0x00FFFFFF) / float(0x01000000);
+}
+
+__device__ __forceinline__ F3 getPointOnRay(const Ray &r, float t) {   // intersections.h:29-31
+    return r.origin + (t - .0001f) * normalize(r.direction);
+}
+
+// intersections.h:50-92
+__device__ float boxIntersectionTest(const GeomD &box, const Ray &r, F3 &normal) {
+    Ray q;
+    q.origin = multiplyMV(box.inverseTransform, r.origin, 1.0f);
+    q.direction = normalize(multiplyMV(box.inverseTransform, r.direction, 0.0f));
+    float tmin = -1e38f, tmax = 1e38f;
+    int tmin_axis = -1, tmax_axis = -1; float tmin_s = 0.f, tmax_s = 0.f;   // normal = sign on one axis, zero elsewhere
+    const float qo[3] = {q.origin.x, q.origin.y, q.origin.z}, qd[3] = {q.direction.x, q.direction.y, q.direction.z};
+#pragma unroll
+    for (int xyz = 0; xyz < 3; ++xyz) {
+        float qdxyz = qd[xyz];
+        float t1 = (-0.5f - qo[xyz]) / qdxyz;
+        float t2 = (+0.5f - qo[xyz]) / qdxyz;
+        float ta = gmin(t1, t2);
+        float tb = gmax(t1, t2);
+        float s = t2 < t1 ? +1.f : -1.f;
+        if (ta > 0 && ta > tmin) { tmin = ta; tmin_axis = xyz; tmin_s = s; }
+        if (tb < tmax) { tmax = tb; tmax_axis = xyz; tmax_s = s; }
+    }
+    if (tmax >= tmin && tmax > 0) {
+        if (tmin <= 0) { tmin = tmax; tmin_axis = tmax_axis; tmin_s = tmax_s; }
+        F3 ip = multiplyMV(box.transform, getPointOnRay(q, tmin), 1.0f);
+        F3 n = mk(tmin_axis == 0 ? tmin_s : 0.f, tmin_axis == 1 ? tmin_s : 0.f, tmin_axis == 2 ? tmin_s : 0.f);
+        normal = normalize(multiplyMV(box.transform, n, 0.0f));
+        return length(r.origin - ip);
+    }
+    return -1;
+}
+
+// intersections.h:104-146
+__device__ float sphereIntersectionTest(const GeomD &sphere, const Ray &r, F3 &normal) {
+    Ray rt;
+    rt.origin = multiplyMV(sphere.inverseTransform, r.origin, 1.0f);
+    rt.direction = normalize(multiplyMV(sphere.inverseTransform, r.direction, 0.0f));
+    float vDotDirection = dot(rt.origin, rt.direction);
+    float radicand = vDotDirection * vDotDirection - (dot(rt.origin, rt.origin) - 0.25f);
+    if (radicand < 0) return -1;
+    float squareRoot = sqrtf(radicand);
+    float firstTerm = -vDotDirection;
+    float t1 = firstTerm + squareRoot;
+    float t2 = firstTerm - squareRoot;
+    float t = 0;
+    bool outside;
+    if (t1 < 0 && t2 < 0) return -1;
+    else if (t1 > 0 && t2 > 0) { t = fminf(t1, t2); outside = true; }
+    else { t = fmaxf(t1, t2); outside = false; }
+    F3 osi = getPointOnRay(rt, t);
+    F3 ip = multiplyMV(sphere.transform, osi, 1.f);
+    normal = normalize(multiplyMV(sphere.invTranspose, osi, 0.f));
+    if (!outside) normal = -normal;
+    return length(r.origin - ip);
+}
+
+struct SceneView {
+    const GeomD *geoms; int n_geoms;            // shared memory
+    const svgf_material *materials;             // shared memory
+    const float4 *bvh; int n_nodes;
+    const float4 *tri_hot, *tri_cold;
+    const TexD *textures;
+};
+
+// IntersectBVH (intersections.h:265-329) with Triangle::Intersect (sceneStructs.h:157-180) over
+// glm::intersectRayTriangle (gtx/intersect.inl:37-74); same near-first order, same 64-entry stack
+// (overflow drops the subtree), same "first strictly smaller t wins".
+struct TriBest { float t, bx, by; int slot; };
+__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, TriBest &best) {
+    if (sc.n_nodes == 0) return false;
+    bool hit = false;
+    const int neg[3] = {ray.direction.x < 0.f, ray.direction.y < 0.f, ray.direction.z < 0.f};
+    const F3 invdir = mk(1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z);
+    int top = 0, cur = 0;
+    int stack[64];
+    best.t = FLT_MAX; best.slot = -1; best.bx = best.by = 0.f;
+    while (true) {
+        const float4 a = __ldg(&sc.bvh[2 * cur]), b = __ldg(&sc.bvh[2 * cur + 1]);
+        // boundingbox.h:62-79 (no t-culling in the reference)
+        float txMin = (a.x - ray.origin.x) * invdir.x, txMax = (b.x - ray.origin.x) * invdir.x;
+        float tyMin = (a.y - ray.origin.y) * invdir.y, tyMax = (b.y - ray.origin.y) * invdir.y;
+        float tzMin = (a.z - ray.origin.z) * invdir.z, tzMax = (b.z - ray.origin.z) * invdir.z;
+        float tmin = gmax(gmax(gmin(txMin, txMax), gmin(tyMin, tyMax)), gmin(tzMin, tzMax));
+        float tmax = gmin(gmin(gmax(txMin, txMax), gmax(tyMin, tyMax)), gmax(tzMin, tzMax));
+        const bool box_hit = !(tmax < 0) && !(tmin > tmax);
+        if (box_hit) {
+            const int meta = __float_as_int(a.w), off = __float_as_int(b.w);
+            const int count = meta & 0xffff;
+            if (count > 0) {
+                for (int i = 0; i < count; i++) {
+                    const int slot = off + i;
+                    const float4 h0 = __ldg(&sc.tri_hot[3 * slot]), h1 = __ldg(&sc.tri_hot[3 * slot + 1]), h2 = __ldg(&sc.tri_hot[3 * slot + 2]);
+                    const F3 v0 = mk(h0.x, h0.y, h0.z), e1 = mk(h1.x, h1.y, h1.z), e2 = mk(h2.x, h2.y, h2.z);
+                    const F3 p = cross(ray.direction, e2);
+                    const float det = dot(e1, p);
+                    if (det < FLT_EPSILON) continue;
+                    const float f = 1.0f / det;
+                    const F3 s = ray.origin - v0;
+                    const float bx = f * dot(s, p);
+                    if (bx < 0.0f) continue;
+                    if (bx > 1.0f) continue;
+                    const F3 q = cross(s, e1);
+                    const float by = f * dot(ray.direction, q);
+                    if (by < 0.0f) continue;
+                    if (by + bx > 1.0f) continue;
+                    const float bz = f * dot(e2, q);
+                    if (!(bz >= 0.0f)) continue;
+                    hit = true;
+                    if (bz < best.t) { best.t = bz; best.bx = bx; best.by = by; best.slot = slot; }
+                }
+                if (top == 0) break;
+                cur = stack[--top];
+            } else {
+                if (top == 64) { cur = stack[--top]; continue; }
+                const int axis = meta >> 16;
+                if (neg[axis]) { stack[top++] = cur + 1; cur = off; }
+                else { stack[top++] = off; cur = cur + 1; }
+            }
+        } else {
+            if (top == 0) break;
+            cur = stack[--top];
+        }
+    }
+    return hit;
+}
+
+struct Isect {      // the live part of ShadeableIntersection (sceneStructs.h:104-111)
+    float t; F3 n; int materialId, geomId; float u, v;
+};
+
+// computeIntersection, pathtrace.cu:210-281. On a miss only t and geomId change (267-271).
+__device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &is) {
+    float t_min = FLT_MAX;
+    int hit_geom = -1;
+    F3 normal = mk(0, 0, 0);
+    float uu = 0.f, vv = 0.f;
+    // tmp_uv is only ever written by mesh hits and carried across loop iterations (pathtrace.cu:226,251,263)
+    float tmp_u = 0.f, tmp_v = 0.f;
+    bool mesh_done = false, mesh_hit = false;
+    TriBest tb; tb.t = FLT_MAX; tb.slot = -1; tb.bx = tb.by = 0.f;
+    int tri_id = -1;
+    for (int i = 0; i < sc.n_geoms; i++) {
+        const GeomD &g = sc.geoms[i];
+        float t;
+        F3 tmp_n = mk(0, 0, 0);
+        if (g.type == 1) t = boxIntersectionTest(g, ray, tmp_n);
+        else if (g.type == 0) t = sphereIntersectionTest(g, ray, tmp_n);
+        else {
+            if (!mesh_done) {
+                mesh_done = true;
+                mesh_hit = intersectBVH(sc, ray, tb);
+                if (mesh_hit) tri_id = __float_as_int(__ldg(&sc.tri_hot[3 * tb.slot]).w);
+            }
+            t = -1.0f;
+            if (mesh_hit && tri_id >= g.tri_begin && tri_id < g.tri_end) {
+                t = tb.t;
+                // deferred Triangle::Intersect shading (sceneStructs.h:160-172): uv in the correct barycentric
+                // order, normal in the reference's permuted order -- both kept
+                const float4 c0 = __ldg(&sc.tri_cold[4 * tb.slot]), c1 = __ldg(&sc.tri_cold[4 * tb.slot + 1]);
+                const float4 c2 = __ldg(&sc.tri_cold[4 * tb.slot + 2]), c3 = __ldg(&sc.tri_cold[4 * tb.slot + 3]);
+                const float w0 = 1.0f - tb.bx - tb.by;
+                tmp_u = (c0.w * w0 + c2.w * tb.bx) + c3.y * tb.by;
+                tmp_v = (c1.w * w0 + c3.x * tb.bx) + c3.z * tb.by;
+                const float wn = 1.f - tb.bx - tb.by;
+                F3 n = (mk(c0.x, c0.y, c0.z) * tb.bx + mk(c1.x, c1.y, c1.z) * tb.by) + mk(c2.x, c2.y, c2.z) * wn;
+                tmp_n = normalize(n);
+            }
+        }
+        if (t > 0.0f && t < t_min) { t_min = t; hit_geom = i; normal = tmp_n; uu = tmp_u; vv = tmp_v; }
+    }
+    if (hit_geom == -1) { is.t = -1.0f; is.geomId = -1; return false; }
+    is.t = t_min; is.materialId = sc.geoms[hit_geom].materialid; is.n = normal; is.u = uu; is.v = vv; is.geomId = hit_geom;
+    return true;
+}
+
+// Texture::getColor, sceneStructs.h:208-221 (nearest texel, RGB8)
+__device__ F3 textureColor(const TexD &tx, float u, float v) {
+    int X = (int)gmin(1.f * tx.w * u, 1.f * tx.w - 1.0f);
+    int Y = (int)gmin(1.f * tx.h * (1.0f - v), 1.f * tx.h - 1.0f);
+    int texel = Y * tx.w + X;
+    if (tx.comp != 3) return mk(0, 0, 0);
+    // uv < 0 reads out of bounds in the reference (undefined); clamp so the kernel cannot fault
+    const int n = tx.w * tx.h;
+    texel = texel < 0 ? 0 : (texel >= n ? n - 1 : texel);
+    const unsigned char *p = tx.px + 3 * (size_t)texel;
+    F3 col = mk((float)p[0], (float)p[1], (float)p[2]);
+    return COLORDIVIDOR_F * col;
+}
+__device__ __forceinline__ F3 materialAlbedo(const SceneView &sc, const svgf_material &m, float u, float v) {
+    return m.texid == -1 ? mk(m.color[0], m.color[1], m.color[2]) : textureColor(sc.textures[m.texid], u, v);
+}
+
+// computeShadowRay, pathtrace.cu:284-297; glm::rotation (gtx/quaternion.inl:248-283), quat*vec3 (gtc/quaternion.inl:319-326)
+__device__ void computeShadowRay(Ray &sr, F3 originPos, F3 lightPos, float lightRadius, float &expectDist, unsigned int &seed) {
+    F3 dirToCenter = normalize(lightPos - originPos);
+    const F3 orig = mk(0.0f, 0.0f, 1.0f);
+    float qw; F3 qv;
+    float cosTheta = dot(orig, dirToCenter);
+    if (cosTheta < -1.0f + FLT_EPSILON) {
+        F3 axis = cross(mk(0, 0, 1), orig);
+        if (dot(axis, axis) < FLT_EPSILON) axis = cross(mk(1, 0, 0), orig);
+        axis = normalize(axis);
+        const float a = 3.14159265358979323846264338327950288f;
+        const float s = sinf(a * 0.5f);
+        qw = cosf(a * 0.5f); qv = mk(axis.x * s, axis.y * s, axis.z * s);
+    } else {
+        F3 axis = cross(orig, dirToCenter);
+        float s = sqrtf((1.0f + cosTheta) * 2.0f);
+        float invs = 1.0f / s;
+        qw = s * 0.5f; qv = mk(axis.x * invs, axis.y * invs, axis.z * invs);
+    }
+    float theta = 2 * PI_F * nextRand(seed);
+    F3 v = mk(cosf(theta), sinf(theta), 0.0f);
+    F3 uv = cross(qv, v);
+    F3 uuv = cross(qv, uv);
+    F3 sampleDirection = v + ((uv * qw) + uuv) * 2.0f;
+    float sampleRadius = nextRand(seed) * lightRadius;
+    F3 samplePoint = lightPos + sampleDirection * sampleRadius;
+    expectDist = length(samplePoint - originPos);
+    sr.origin = originPos;
+    sr.direction = normalize(samplePoint - originPos);
+}
+
+// interactions.h:37-67
+__device__ F3 calculateRandomDirectionInHemisphere(F3 normal, unsigned int &seed) {
+    float up = sqrtf(nextRand(seed));
+    float over = sqrtf(1 - up * up);
+    float around = nextRand(seed) * TWO_PI_F;
+    F3 notNormal;
+    if (fabsf(normal.x) < SQRT_OF_ONE_THIRD_F) notNormal = mk(1, 0, 0);
+    else if (fabsf(normal.y) < SQRT_OF_ONE_THIRD_F) notNormal = mk(0, 1, 0);
+    else notNormal = mk(0, 0, 1);
+    F3 p1 = normalize(cross(normal, notNormal));
+    F3 p2 = normalize(cross(normal, p1));
+    return (up * normal + cosf(around) * over * p1) + sinf(around) * over * p2;
+}
+
+struct PathState { Ray ray; F3 color; bool diffuse; };
+
+// scatterRay, interactions.h:94-136
+__device__ void scatterRay(PathState &ps, F3 intersect, F3 normal, const svgf_material &m, unsigned int &seed) {
+    ps.ray.origin = intersect + 1e-4f * normal;
+    const F3 spec = mk(m.specular_color[0], m.specular_color[1], m.specular_color[2]);
+    if (m.hasRefractive) {
+        float eta = 1.0f / m.indexOfRefraction;
+        float unit_projection = dot(ps.ray.direction, normal);
+        if (unit_projection > 0) eta = 1.0f / eta;
+        float R0 = powf((1.0f - eta) / (1.0f + eta), 2.0f);
+        float R = R0 + (1 - R0) * powf(1 - gabs(unit_projection), 5.0f);
+        if (R < nextRand(seed)) {
+            F3 I = ps.ray.direction, N = normal;        // glm::refract, detail/func_geometric.inl:189-198
+            float dotValue = dot(N, I);
+            float k = 1.0f - eta * eta * (1.0f - dotValue * dotValue);
+            ps.ray.direction = (eta * I - (eta * dotValue + sqrtf(k)) * N) * (float)(k >= 0.0f);
+        } else {
+            F3 I = ps.ray.direction, N = normal;        // glm::reflect
+            ps.ray.direction = I - N * dot(N, I) * 2.0f;
+            ps.color = ps.color * spec;
+        }
+    } else if (nextRand(seed) < m.hasReflective) {
+        F3 I = ps.ray.direction, N = normal;
+        ps.ray.direction = I - N * dot(N, I) * 2.0f;
+        ps.color = ps.color * spec;
+    } else {
+        ps.ray.direction = calculateRandomDirectionInHemisphere(normal, seed);
+        ps.diffuse = true;
+    }
+}
+
+// One thread per pixel. Block = 8x16 pixel tile so a warp covers an 8x4 patch (coherent primary rays).
+constexpr int RT_BX = 8, RT_BY = 16;
+
+__global__ void __launch_bounds__(RT_BX *RT_BY)
+rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf_material *__restrict__ g_materials,
+          int n_materials, const float4 *__restrict__ bvh, int n_nodes, const float4 *__restrict__ tri_hot,
+          const float4 *__restrict__ tri_cold, const TexD *__restrict__ textures,
+          float4 *__restrict__ nrm_out, float4 *__restrict__ pos_out, float4 *__restrict__ alb_out,
+          float *__restrict__ image, float4 *__restrict__ stale_nm, float2 *__restrict__ stale_uv) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    GeomD *s_geoms = reinterpret_cast<GeomD *>(smem);
+    svgf_material *s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomD) * n_geoms);
+    {
+        const int tid = threadIdx.y * RT_BX + threadIdx.x, nt = RT_BX * RT_BY;
+        const int gw = sizeof(GeomD) / 4 * n_geoms, mw = sizeof(svgf_material) / 4 * n_materials;
+        const int *src = reinterpret_cast<const int *>(g_geoms); int *dst = reinterpret_cast<int *>(s_geoms);
+        for (int i = tid; i < gw; i += nt) dst[i] = src[i];
+        src = reinterpret_cast<const int *>(g_materials); dst = reinterpret_cast<int *>(s_mats);
+        for (int i = tid; i < mw; i += nt) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int x = blockIdx.x * RT_BX + threadIdx.x;
+    const int y = P.row_begin + blockIdx.y * RT_BY + threadIdx.y;
+    if (x >= P.W || y >= P.row_end) return;
+    const int idx = x + y * P.W;
+
+    SceneView sc;
+    sc.geoms = s_geoms; sc.n_geoms = n_geoms; sc.materials = s_mats; sc.bvh = bvh; sc.n_nodes = n_nodes;
+    sc.tri_hot = tri_hot; sc.tri_cold = tri_cold; sc.textures = textures;
+
+    // generateRayFromCamera, pathtrace.cu:187-208
+    const svgf_camera &cam = P.cam;
+    PathState seg;
+    seg.ray.origin = mk(cam.position[0], cam.position[1], cam.position[2]);
+    seg.color = mk(1.0f, 1.0f, 1.0f);
+    seg.ray.direction = normalize(mk(cam.view[0], cam.view[1], cam.view[2])
+        - mk(cam.right[0], cam.right[1], cam.right[2]) * cam.pixelLength[0] * ((float)x - (float)(P.W * 0.5f - 0.5f))
+        - mk(cam.up[0], cam.up[1], cam.up[2]) * cam.pixelLength[1] * ((float)y - (float)(P.H * 0.5f - 0.5f)));
+    seg.diffuse = false;
+
+    Isect is;
+    bool any_hit = false;
+    bool hit = computeIntersection(sc, seg.ray, is);
+    if (!hit) {     // stale record from earlier frames (pathtrace.cu:85,119-120,316-322)
+        const float4 s = stale_nm[idx]; const float2 suv = stale_uv[idx];
+        is.n = mk(s.x, s.y, s.z); is.materialId = __float_as_int(s.w); is.u = suv.x; is.v = suv.y;
+    } else any_hit = true;
+    {
+        const svgf_material &material = sc.materials[is.materialId];
+        const F3 p = seg.ray.origin + is.t * seg.ray.direction;
+        const F3 a = materialAlbedo(sc, material, is.u, is.v);
+        nrm_out[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.geomId));
+        pos_out[idx] = make_float4(p.x, p.y, p.z, 0.f);
+        alb_out[idx] = make_float4(a.x, a.y, a.z, 0.f);
+    }
+    F3 acc = mk(0, 0, 0);
+    for (int depth = 1; depth <= P.max_depth; depth++) {
+        if (!hit) break;
+        unsigned int seed = initRand(idx, P.frame + depth);
+        const svgf_material &material = sc.materials[is.materialId];
+        if (material.emittance > 0.0f) {
+            if (!P.trace_shadowray || !P.reduce_var || !seg.diffuse)
+                acc = acc + seg.color * mk(material.color[0], material.color[1], material.color[2]) * material.emittance;
+            break;
+        }
+        const F3 ipos = seg.ray.origin + is.t * seg.ray.direction;
+        const F3 inrm = is.n;
+        const bool materialIsDiffuse = material.hasReflective < 1e-6 && material.hasRefractive < 1e-6;
+        if (!(P.denoise && P.sepcolor) || depth > 1) seg.color = seg.color * materialAlbedo(sc, material, is.u, is.v);
+        if (P.trace_shadowray && materialIsDiffuse) {
+            const GeomD &light = sc.geoms[0];
+            const F3 lpos = mk(light.translation[0], light.translation[1], light.translation[2]);
+            Ray sr; float expectDist = 0.0f;
+            computeShadowRay(sr, ipos + 1e-4f * inrm, lpos, P.lightradius, expectDist, seed);
+            Isect sh; sh.geomId = -2; sh.materialId = 0;
+            computeIntersection(sc, sr, sh);
+            if (sh.geomId == 0) {
+                const svgf_material &sm = sc.materials[sh.materialId];
+                if (sm.emittance > 0.0f) {
+                    float diffuse = gmax(0.0f, dot(sr.direction, inrm));
+                    float shadowIntensity = P.sintensity / powf(expectDist, 2.0f);
+                    acc = acc + seg.color * sm.emittance * mk(sm.color[0], sm.color[1], sm.color[2]) * shadowIntensity * diffuse;
+                }
+            }
+        }
+        if (depth < P.max_depth) {
+            scatterRay(seg, ipos, inrm, material, seed);
+            hit = computeIntersection(sc, seg.ray, is);
+            any_hit |= hit;
+        }
+    }
+    float *img = image + 3 * (size_t)idx;
+    if (P.denoise) { img[0] = acc.x; img[1] = acc.y; img[2] = acc.z; }
+    else {          // running mean, pathtrace.cu:398
+        const float f = (float)P.frame, f1 = (float)(P.frame + 1);
+        F3 old = mk(img[0], img[1], img[2]);
+        F3 nw = old * f / f1 + acc / f1;
+        img[0] = nw.x; img[1] = nw.y; img[2] = nw.z;
+    }
+    if (any_hit) {
+        stale_nm[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.materialId));
+        stale_uv[idx] = make_float2(is.u, is.v);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
+    const DeviceScene &s = c->scene;
+    const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int rows = p.row_end - p.row_begin;
+    if (rows <= 0) return cudaSuccess;
+    dim3 block(RT_BX, RT_BY), grid((p.W + RT_BX - 1) / RT_BX, (rows + RT_BY - 1) / RT_BY);
+    rt_kernel<<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes,
+                                                s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, c->alb, c->image,
+                                                c->stale_nm, c->stale_uv);
+    return cudaGetLastError();
+}

@@ -1,0 +1,127 @@
+// svgf_internal.h -- device data layout and context of the B200-native SVGF + path-trace hot path.
+// (internal; the public boundary is include/svgf_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/svgf_b200.h"
+
+// ---------------------------------------------------------------------------------------------------
+// HBM layout. Everything per-pixel is a 16-byte-element plane (float4), row-major, so that one thread
+// moves one pixel with one LDG.128/STG.128 and TMA can tile it with 16 B elements.
+//
+//   cv[3]        {r, g, b, variance}      colour+variance; rotates between "accumulated", "a-trous ping/pong"
+//                                         and "history" by pointer (no D2D copies, cf. denoise.cu:366,391,396-398)
+//   nrm[2]       {nx, ny, nz, geomId}     current / previous frame (swap), geomId as int bits
+//   pos          {px, py, pz, 0}
+//   alb          {ar, ag, ab, 0}          first-hit albedo (re-modulated by the last a-trous level)
+//   mom[2]       {m1, m2}                 luminance moments history / accumulated (swap)
+//   hlen[2]      int32                    history length before / after back-projection (swap)
+//   image        vec3 AoS (12 B)          1-spp radiance, the reference's dev_image layout (read by pbo pack)
+//   denoised     vec3 AoS (12 B)          final colour, the reference's dev_denoised_image layout (D2H'd as is)
+//   var_out      float                    final variance (what the reference leaves in dev_variance)
+//   stale        {nx, ny, nz, matId}, {u, v}   the part of the reference's persistent per-pixel
+//                                         ShadeableIntersection that survives a miss (pathtrace.cu:267-271,316-322)
+// ---------------------------------------------------------------------------------------------------
+
+struct GeomD {              // what the closest-hit loop needs of a Geom (sceneStructs.h:33-47), 224 B
+    int type, materialid, tri_begin, tri_end;
+    float translation[3], pad_;
+    float inverseTransform[16], transform[16], invTranspose[16];
+};
+static_assert(sizeof(GeomD) == 224, "GeomD");
+
+struct TexD { int w, h, comp, pad; const unsigned char *px; };
+
+struct DeviceScene {
+    GeomD *geoms = nullptr;             int n_geoms = 0;
+    svgf_material *materials = nullptr; int n_materials = 0;
+    float4 *bvh = nullptr;              int n_nodes = 0;    // 2 x float4 per node: {min, count|axis<<16 as int}, {max, offset}
+    float4 *tri_hot = nullptr;          int n_tris = 0;     // 3 x float4 per tri: {v0, id}, {e1, owner geom}, {e2, 0}
+    float4 *tri_cold = nullptr;                             // 4 x float4 per tri: {n0,u0} {n1,v0} {n2,u1} {v1,u2,v2,0}
+    TexD *textures = nullptr;           int n_textures = 0;
+    std::vector<unsigned char *> tex_pixels;
+};
+
+enum { SVGF_MAX_LEVELS = 7 };
+
+struct svgf_ctx {
+    int device = 0;
+    int W = 0, H = 0;
+    size_t px = 0;
+    cudaStream_t stream = nullptr;
+    DeviceScene scene;
+
+    // shard (rows [row_begin,row_end) of the frame); world==1: whole frame
+    svgf_shard shard{0, 1, 0, 0};
+
+    float4 *cv[3] = {nullptr, nullptr, nullptr};
+    int hist_cv = -1;                   // which cv[] holds the colour history for the next frame (-1: none yet)
+    float4 *nrm[2] = {nullptr, nullptr};
+    int cur_nrm = 0;
+    float4 *pos = nullptr, *alb = nullptr;
+    float2 *mom[2] = {nullptr, nullptr};
+    int cur_mom = 0;                    // mom[cur_mom] = history, the other = accumulated
+    int *hlen[2] = {nullptr, nullptr};
+    int cur_hlen = 0;
+    float *image = nullptr, *denoised = nullptr, *var_out = nullptr;
+    float4 *stale_nm = nullptr; float2 *stale_uv = nullptr;
+    unsigned char *pbo_own = nullptr;   // used when the caller passes no PBO
+
+    // scratch for the AoS entry point svgf_denoise() and the host conveniences
+    float *aos_in = nullptr, *aos_out = nullptr; svgf_gbuffer_texel *aos_g = nullptr;
+    float *pinned_image = nullptr;      // W*H*3 pinned staging for the per-frame D2H
+
+    float view_matrix_prev[16];         // denoise.cu:15; identity until the first denoise (glm::mat4())
+    int last_variance_valid = 0;        // var_out holds the final variance of the last frame
+
+    // profiling
+    int profiling = 0;
+    cudaEvent_t ev[16] = {};
+    float stage_ms[11] = {};
+
+    std::string err;
+};
+
+// ---- helpers ---------------------------------------------------------------------------------------
+#define SVGF_CUDA(ctx, call)                                                                          \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return SVGF_ERR_CUDA;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+// kernels / stage launchers (each returns a cudaError_t from the launch)
+struct RtParams {
+    int W, H, row_begin, row_end;       // rows this launch covers
+    int frame, max_depth;
+    int trace_shadowray, reduce_var, denoise, sepcolor;
+    float sintensity, lightradius;
+    svgf_camera cam;
+};
+cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out);
+cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const float4 *nrm_prev,
+                            const float4 *pos, const float4 *hist_cv, const float2 *mom_hist, const int *hlen_in,
+                            float4 *acc_cv, float2 *mom_acc, int *hlen_out, const float *prev_viewmat,
+                            float color_alpha, float moment_alpha, int has_history);
+cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv);
+struct AtrousArgs {
+    const float4 *cv_in; float4 *cv_out;            // cv_out may be null on the last level
+    const float4 *nrm, *pos, *alb;
+    float *denoised_out; float *var_out;            // last level only (AoS vec3 + float plane)
+    int level, is_last, blur_variance, addcolor;
+    float sigma_c, sigma_n, sigma_x;
+};
+cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a);
+cudaError_t launch_cv_to_outputs(svgf_ctx *c, const float4 *cv, float *denoised, float *var_out);
+cudaError_t launch_debug_view(svgf_ctx *c, int option, const int *hlen, const float4 *cv, float *denoised);
+cudaError_t launch_pack_pbo(svgf_ctx *c, unsigned char *pbo, const float *left, const float *right);
+cudaError_t launch_aos_to_soa(svgf_ctx *c, const svgf_gbuffer_texel *g, float4 *nrm, float4 *pos, float4 *alb);
+cudaError_t launch_soa_to_aos(svgf_ctx *c, const float4 *nrm, const float4 *pos, const float4 *alb, svgf_gbuffer_texel *g);
+cudaError_t launch_copy_f3(svgf_ctx *c, float *dst, const float *src);
+
+void svgf_view_matrix(const svgf_camera *cam, float *out16);
