@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SVGF + 1-spp path-trace hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
+
+A "step" is one frame: pathtrace(pbo, frame) = 1-spp path trace -> temporal accumulation -> N-level a-trous ->
+PBO pack, on synthetic input (the reference's own scene description, random-free; RNG seeded by pixel/frame).
+N = 1 runs C2 (cornell 1920x1080, 5 a-trous levels), the configuration BASELINE.json's metric is quoted on.
+Prints ONE JSON line (rank 0). Keys follow the driver's contract; see DESIGN.md "Measurement".
+
+  value     frames/s with everything resident on the device (no host image requested), CUDA events on the
+            library's own stream around exactly K frames, after W warm-up frames.
+  e2e       frames/s through the public C-ABI call a user makes, svgf_render(..., host_image): per frame the
+            camera+parameter structs go in (kernel arguments) and the W*H*3 float image comes back to host memory.
+  roofline  the a-trous level kernel(s): algorithmic bytes (56 B/pixel, 68 B/pixel on the last level) / CUDA-event
+            duration of each level launch, averaged over the timed frames, against the measured HBM copy peak.
+  cpu_baseline  the CPU oracle (port of the reference path, OpenMP) timed on this box's host cores, bounded sample.
+
+--impl reference runs the reference's OWN src/pathtrace.cu + src/denoise.cu (compiled from /root/reference into
+oracle/_ref/libref_gpu.so, unmodified apart from the portability patch) on the same GPU, same scene, same settings.
+The reference has no CPU implementation of this path (it is a CUDA program); if its binary did not travel, the arm
+falls back to the oracle port on the host cores and says so.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "cuda-path-tracer-denoising_b200"
+
+WORKLOADS = {   # BASELINE.json configs
+    "c1": dict(scene="cornell", W=256, H=256, nlevel=3, moving=False, name="C1 cornell.txt 256x256, 1spp, 3 a-trous iters"),
+    "c2": dict(scene="cornell", W=1920, H=1080, nlevel=5, moving=False, name="C2 cornell.txt 1920x1080, 1spp, 5 a-trous iters"),
+    "c3": dict(scene="room", W=1920, H=1080, nlevel=5, moving=False, name="C3 room.txt 1920x1080, 1spp, 5 a-trous iters"),
+    "c4": dict(scene="cornell", W=3840, H=2160, nlevel=5, moving=False, name="C4 cornell.txt 3840x2160, 1spp, 5 a-trous iters"),
+    "c5": dict(scene="bunny", W=1920, H=1080, nlevel=5, moving=True, name="C5 bunny.txt moving camera 1920x1080, 1spp, 5 a-trous iters"),
+}
+C5_SPEEDS = dict(camera_speed_x=0.05, camera_speed_y=0.02, camera_speed_z=0.02, camera_speed_theta=0.02, camera_speed_phi=0.05)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(wl, frames=2):
+    """Oracle port of the whole frame on the host cores, bounded: `frames` frames from a reset."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    sc = orc.Scene(wl["scene"]); o = orc.Oracle(sc, wl["W"], wl["H"]); P = orc.default_params(atrous_nlevel=wl["nlevel"])
+    drv = orc.CameraDriver(sc, wl["W"], wl["H"], automate=wl["moving"])
+    threads = orc.lib().orc_max_threads()
+    t0 = time.perf_counter()
+    for f in range(frames):
+        o.frame(drv.step(), P, f, orc.VAR_JACOBI, threads)
+    dt = time.perf_counter() - t0
+    return {"value": frames / dt, "unit": "frames/sec", "cores": threads, "kind": "port",
+            "sample": "%d frames of %s from reset, oracle/svgf_oracle.cpp (OpenMP, %d threads), %.1f s" % (frames, wl["name"], threads, dt)}
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refh
+    line = {"impl": "reference", "metric": "frames/sec", "unit": "frames/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "scene": wl["scene"], "width": wl["W"], "height": wl["H"], "atrous_levels": wl["nlevel"]}}
+    if refh.available("gpu"):
+        try:
+            h = refh.RefHarness("gpu")
+            h.load_blob(wl["scene"], wl["W"], wl["H"])
+            h.set_params(**refh.ALL_ON); h.set_params(atrous_nlevel=wl["nlevel"])
+            if wl["moving"]:
+                h.set_params(automate_camera=1, **C5_SPEEDS)
+            h.time_frames(max(args.warmup, 1))
+            ms = h.time_frames(args.steps)
+            fps = 1000.0 * args.steps / ms
+            line.update({"value": fps, "ms_per_step": ms / args.steps, "mpixels_per_sec": fps * wl["W"] * wl["H"] / 1e6,
+                         "cpu_baseline": {"value": fps, "unit": "frames/sec", "cores": 0, "kind": "reference",
+                                          "sample": "the reference's own CUDA path (src/pathtrace.cu + src/denoise.cu built for sm_100, "
+                                                    "oracle/_ref/libref_gpu.so) on 1 GPU: it has no CPU implementation; %d frames, host clock "
+                                                    "(every reference frame ends in a blocking D2H)" % args.steps},
+                         "e2e": {"value": fps, "unit": "frames/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": wl["W"] * wl["H"] * 12},
+                         "config": dict(line["config"], parallelism="1 GPU (the reference is single-GPU)", device="gpu")})
+            print(json.dumps(line), flush=True)
+            return
+        except Exception as e:      # fall through to the CPU port
+            line["note"] = "reference GPU binary failed: %s" % e
+    frames = max(1, min(args.steps, 2))
+    cb = cpu_baseline(wl, frames)
+    line.update({"value": cb["value"], "ms_per_step": 1000.0 / cb["value"], "cpu_baseline": cb,
+                 "e2e": {"value": cb["value"], "unit": "frames/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "config": dict(line["config"], parallelism="host cores", device="cpu (oracle port; reference binary absent)")})
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, wl, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    m = importlib.import_module(PKG)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, H, nl = wl["W"], wl["H"], wl["nlevel"]
+    blob, R = m.open_scene(wl["scene"], W, H, device=local_rank)
+    P = m.default_params(atrous_nlevel=nl)
+    drv = blob.camera_driver(W, H, automate=wl["moving"])
+    stream = torch.cuda.ExternalStream(R.stream(), device=torch.device("cuda", local_rank))
+    host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    host_np = host.numpy()
+    frame = 0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        R.pathtrace(drv.step(), P, frame, host_image=host_np); frame += 1
+
+    # ---- device-resident throughput (value) + per-stage events over the same timed region ----
+    clocks = ClockSampler(local_rank); clocks.start()
+    R.set_profiling(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        R.pathtrace(drv.step(), P, frame); frame += 1
+    e1.record(stream)
+    R.sync(); barrier()
+    ms_dev = e0.elapsed_time(e1)
+    stage = R.stage_times()
+    R.set_profiling(False)
+    # ---- end to end through the C ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        R.pathtrace(drv.step(), P, frame, host_image=host_np); frame += 1
+    e3.record(stream)
+    R.sync(); barrier()
+    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    px = W * H
+    # replicas: every rank renders whole frames (see DESIGN.md "Multi-GPU"); aggregate = world x per-rank rate
+    fps_dev = world * args.steps * 1000.0 / ms_dev
+    fps_e2e = world * args.steps * 1000.0 / ms_e2e
+    peak, peak_src = measured_peak()
+    lv_ms = [float(stage[2 + l]) for l in range(nl)]
+    lv_bytes = [px * (68 if l == nl - 1 else 56) for l in range(nl)]
+    lv_gbs = [b / (t * 1e-3) / 1e9 if t > 0 else 0.0 for b, t in zip(lv_bytes, lv_ms)]
+    tot_ms = sum(lv_ms)
+    achieved = sum(lv_bytes) / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "atrous_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    cb = cpu_baseline(wl, 2) if world == 1 and not args.no_cpu_baseline else None
+    launches_per_frame = 1 + 1 + nl + 1
+    line = {
+        "metric": "frames/sec", "value": fps_dev, "unit": "frames/sec", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "scene": wl["scene"], "width": W, "height": H, "atrous_levels": nl,
+                   "parallelism": "1 GPU" if world == 1 else "%d replicas" % world,
+                   "l2": "per-frame working set %.0f MB > 126 MB L2 (no flush needed)" % (px * 196 / 1e6)},
+        "mpixels_per_sec": fps_dev * px / 1e6,
+        "e2e": {"value": fps_e2e, "unit": "frames/sec", "h2d_bytes_per_step": 84 + 80, "d2h_bytes_per_step": px * 12,
+                "ms_per_step": ms_e2e / args.steps, "mpixels_per_sec": fps_e2e * px / 1e6},
+        "gpu_launches": launches_per_frame * args.steps * 2,
+        "roofline": {"bound": "hbm", "kernel": "atrous level (all %d levels)" % nl, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "per_level_us": [t * 1e3 for t in lv_ms], "per_level_gbs": lv_gbs, "per_level_frac": [g / peak for g in lv_gbs],
+                     "algorithmic_bytes_per_pixel": [68 if l == nl - 1 else 56 for l in range(nl)]},
+        "stages_ms": {"pathtrace": float(stage[0]), "temporal": float(stage[1]), "atrous": lv_ms, "pbo_pack": float(stage[9]), "frame": float(stage[10])},
+        "clocks": clk,
+    }
+    if cb:
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload or "c2"]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+    else:
+        run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -81,7 +81,7 @@ class Shard(ctypes.Structure):
 # every symbol include/svgf_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = ["svgf_params_default", "svgf_create", "svgf_destroy", "svgf_reset", "svgf_render", "svgf_denoise", "svgf_sync",
            "svgf_denoise_host", "svgf_atrous_host", "svgf_fetch", "svgf_last_error", "svgf_abi_version", "svgf_stage_times",
-           "svgf_set_profiling", "svgf_set_shard", "svgf_camera_init", "svgf_camera_step"]
+           "svgf_set_profiling", "svgf_stream", "svgf_set_shard", "svgf_camera_init", "svgf_camera_step"]
 
 _lib = None
 
@@ -113,6 +113,8 @@ def lib():
         L.svgf_last_error.restype = cp
         L.svgf_stage_times.argtypes = [vp, vp]
         L.svgf_set_profiling.argtypes = [vp, ci]
+        L.svgf_stream.argtypes = [vp]
+        L.svgf_stream.restype = vp
         L.svgf_set_shard.argtypes = [vp, ctypes.POINTER(Shard)]
         L.svgf_camera_init.argtypes = [ctypes.POINTER(Camera), ctypes.POINTER(CameraRig), vp, vp, vp, cf, ci, ci]
         L.svgf_camera_init.restype = None
@@ -197,6 +199,10 @@ class Renderer:
         a = np.zeros(11, np.float32)
         self._ck(lib().svgf_stage_times(self.h, a.ctypes.data), "svgf_stage_times")
         return a
+
+    def stream(self):
+        """cudaStream_t (int) the context issues its work on."""
+        return lib().svgf_stream(self.h)
 
     def pathtrace(self, cam, params, frame, pbo_dev=None, host_image=None):
         """== pathtrace(pbo, frame). host_image: (H, W, 3) float32 numpy array to fill (scene->state.image), or None."""

@@ -130,7 +130,6 @@ static int alloc_frame_buffers(svgf_ctx *c) {
     CK(dalloc(&c->stale_nm, px)); CK(dalloc(&c->stale_uv, px));
     CK(cudaMalloc((void **)&c->pbo_own, px * 8));
     CK(cudaMallocHost((void **)&c->pinned_image, px * 12));
-    for (int i = 0; i < 16; i++) CK(cudaEventCreate(&c->ev[i]));
     return SVGF_OK;
 }
 
@@ -190,7 +189,8 @@ int svgf_destroy(svgf_ctx *c) {
     cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own);
     cudaFree(c->aos_in); cudaFree(c->aos_out); cudaFree(c->aos_g);
     if (c->pinned_image) cudaFreeHost(c->pinned_image);
-    for (int i = 0; i < 16; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (auto &pf : c->prof_pool) for (int i = 0; i < 12; i++) cudaEventDestroy(pf.ev[i]);
+    for (auto &r : c->registered_hosts) cudaHostUnregister(r.first);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return SVGF_OK;
@@ -229,13 +229,43 @@ int svgf_set_shard(svgf_ctx *c, const svgf_shard *s) {
     return SVGF_OK;
 }
 
-int svgf_set_profiling(svgf_ctx *c, int enabled) { if (!c) return SVGF_ERR_INVALID; c->profiling = enabled != 0; return SVGF_OK; }
+enum { SVGF_PROF_MAX_FRAMES = 512 };
 
+int svgf_set_profiling(svgf_ctx *c, int enabled) {
+    if (!c) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    c->profiling = enabled != 0;
+    c->prof_count = 0;
+    return SVGF_OK;
+}
+
+// Average device time per stage over the frames rendered since profiling was enabled (at most 512):
+// [0] path trace, [1] temporal, [2..8] a-trous level 1..7, [9] pbo pack, [10] whole frame (incl. D2H when requested).
 int svgf_stage_times(svgf_ctx *c, float *ms11) {
     if (!c || !ms11) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    double acc[11] = {0}; int cnt[11] = {0};
+    for (int f = 0; f < c->prof_count; f++) {
+        svgf_ctx::ProfFrame &pf = c->prof_pool[f];
+        float ms;
+        auto add = [&](int slot, cudaEvent_t a, cudaEvent_t b) { if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) { acc[slot] += ms; cnt[slot]++; } };
+        add(0, pf.ev[0], pf.ev[1]);
+        cudaEvent_t prev = pf.ev[1];
+        if (pf.denoise) {
+            add(1, pf.ev[1], pf.ev[2]); prev = pf.ev[2];
+            for (int l = 1; l <= pf.nlevel; l++) { add(1 + l, prev, pf.ev[2 + l]); prev = pf.ev[2 + l]; }
+        }
+        add(9, prev, pf.ev[10]);
+        add(10, pf.ev[0], pf.ev[11]);
+    }
+    (void)cudaGetLastError();
+    for (int i = 0; i < 11; i++) c->stage_ms[i] = cnt[i] ? (float)(acc[i] / cnt[i]) : 0.f;
     memcpy(ms11, c->stage_ms, sizeof(c->stage_ms));
     return SVGF_OK;
 }
+
+void *svgf_stream(svgf_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 int svgf_sync(svgf_ctx *c) {
     if (!c) return SVGF_ERR_INVALID;
@@ -302,21 +332,30 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
 // NOTE on the temporal-off path: the reference still copies moment_acc/history_length_update (never written in that
 // frame, denoise.cu:397-398) over the histories, i.e. leaves them undefined; here they simply stay as they were.
 
-static void collect_times(svgf_ctx *c, int nlevel, bool denoise) {
-    // ev[0] start, ev[1] after rt, ev[2] after temporal, ev[3..9] after a-trous level 1..7, ev[10] after pack, ev[11] end
-    memset(c->stage_ms, 0, sizeof(c->stage_ms));
-    cudaEventElapsedTime(&c->stage_ms[0], c->ev[0], c->ev[1]);
-    cudaEvent_t prev = c->ev[1];
-    if (denoise) {
-        cudaEventElapsedTime(&c->stage_ms[1], c->ev[1], c->ev[2]);
-        prev = c->ev[2];
-        for (int l = 1; l <= nlevel && l <= SVGF_MAX_LEVELS; l++) {
-            cudaEventElapsedTime(&c->stage_ms[1 + l], prev, c->ev[2 + l]);
-            prev = c->ev[2 + l];
-        }
+// ev[0] start, ev[1] after rt, ev[2] after temporal, ev[3..9] after a-trous level 1..7, ev[10] after pack, ev[11] end
+static cudaEvent_t *prof_begin(svgf_ctx *c, const svgf_params *P) {
+    if (!c->profiling || c->prof_count >= SVGF_PROF_MAX_FRAMES) return nullptr;
+    if ((int)c->prof_pool.size() <= c->prof_count) {
+        svgf_ctx::ProfFrame pf;
+        for (int i = 0; i < 12; i++) if (cudaEventCreate(&pf.ev[i]) != cudaSuccess) return nullptr;
+        c->prof_pool.push_back(pf);
     }
-    cudaEventElapsedTime(&c->stage_ms[9], prev, c->ev[10]);
-    cudaEventElapsedTime(&c->stage_ms[10], c->ev[0], c->ev[11]);
+    svgf_ctx::ProfFrame &pf = c->prof_pool[c->prof_count++];
+    const bool filt = P->denoise_enable && P->right_view_option == 0 && P->spatial_enable && P->atrous_nlevel > 0;
+    pf.denoise = P->denoise_enable ? 1 : 0;
+    pf.nlevel = filt ? P->atrous_nlevel : 0;
+    return pf.ev;
+}
+
+// Page-lock a caller buffer the first time it is seen, so the per-frame D2H (pathtrace.cu:450) is a direct DMA.
+static bool host_is_registered(svgf_ctx *c, void *p, size_t bytes) {
+    for (auto &r : c->registered_hosts) if (r.first == p && r.second >= bytes) return true;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;   // already pinned by the caller
+    (void)cudaGetLastError();
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) { c->registered_hosts.push_back({p, bytes}); return true; }
+    (void)cudaGetLastError();
+    return false;
 }
 
 extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, float *host_image) {
@@ -324,7 +363,7 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_render: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
     if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS || P->tracedepth < 0) { c->err = "svgf_render: parameter out of range"; return SVGF_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
-    cudaEvent_t *ev = c->profiling ? c->ev : nullptr;
+    cudaEvent_t *ev = prof_begin(c, P);
     if (ev) CK(cudaEventRecord(ev[0], c->stream));
     RtParams rp;
     rp.W = c->W; rp.H = c->H; rp.row_begin = c->shard.row_begin; rp.row_end = c->shard.row_end;
@@ -342,16 +381,21 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     unsigned char *pbo = pbo_dev ? static_cast<unsigned char *>(pbo_dev) : c->pbo_own;
     CK(launch_pack_pbo(c, pbo, c->image, c->denoised));
     if (ev) CK(cudaEventRecord(ev[10], c->stream));
-    if (host_image) {   // pathtrace.cu:450, through pinned staging so the copy is a real async DMA
+    if (host_image) {   // pathtrace.cu:450 (scene->state.image): synchronous like the reference, but a pinned DMA
         const size_t off = (size_t)c->shard.row_begin * c->W * 3, n = (size_t)(c->shard.row_end - c->shard.row_begin) * c->W * 3;
-        CK(cudaMemcpyAsync(c->pinned_image + off, c->denoised + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        if (ev) CK(cudaEventRecord(ev[11], c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        memcpy(host_image + off, c->pinned_image + off, n * sizeof(float));
+        if (host_is_registered(c, host_image, c->px * 12)) {
+            CK(cudaMemcpyAsync(host_image + off, c->denoised + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            if (ev) CK(cudaEventRecord(ev[11], c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        } else {
+            CK(cudaMemcpyAsync(c->pinned_image + off, c->denoised + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            if (ev) CK(cudaEventRecord(ev[11], c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            memcpy(host_image + off, c->pinned_image + off, n * sizeof(float));
+        }
     } else if (ev) {
         CK(cudaEventRecord(ev[11], c->stream));
     }
-    if (ev) { CK(cudaStreamSynchronize(c->stream)); collect_times(c, P->atrous_nlevel, P->denoise_enable && P->spatial_enable && P->right_view_option == 0); }
     return SVGF_OK;
 }
 
@@ -361,7 +405,7 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_denoise: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
     if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS) { c->err = "svgf_denoise: atrous_nlevel out of range"; return SVGF_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
-    cudaEvent_t *ev = c->profiling ? c->ev : nullptr;
+    cudaEvent_t *ev = prof_begin(c, P);
     if (ev) { CK(cudaEventRecord(ev[0], c->stream)); CK(cudaEventRecord(ev[1], c->stream)); }
     CK(launch_aos_to_soa(c, gbuffer_dev, c->nrm[c->cur_nrm], c->pos, c->alb));
     int rc = denoise_soa(c, input_dev, cam, P, ev);
@@ -369,7 +413,6 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     CK(cudaMemcpyAsync(output_dev, c->denoised, c->px * 12, cudaMemcpyDeviceToDevice, c->stream));
     if (ev) { CK(cudaEventRecord(ev[10], c->stream)); CK(cudaEventRecord(ev[11], c->stream)); }
     CK(cudaStreamSynchronize(c->stream));       // denoise.cu:401
-    if (ev) collect_times(c, P->atrous_nlevel, P->spatial_enable && P->right_view_option == 0);
     return SVGF_OK;
 }
 

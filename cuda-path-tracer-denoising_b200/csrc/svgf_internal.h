@@ -77,10 +77,16 @@ struct svgf_ctx {
     float view_matrix_prev[16];         // denoise.cu:15; identity until the first denoise (glm::mat4())
     int last_variance_valid = 0;        // var_out holds the final variance of the last frame
 
-    // profiling
+    // profiling: a pool of per-frame event sets so that a whole timed region can be measured without a
+    // host synchronisation per frame; svgf_stage_times() averages over the frames recorded since it was enabled
     int profiling = 0;
-    cudaEvent_t ev[16] = {};
+    struct ProfFrame { cudaEvent_t ev[12]; int nlevel; int denoise; };
+    std::vector<ProfFrame> prof_pool;
+    int prof_count = 0;
     float stage_ms[11] = {};
+
+    // host buffers the caller passed as host_image, page-locked once so the per-frame D2H is a direct DMA
+    std::vector<std::pair<void *, size_t>> registered_hosts;
 
     std::string err;
 };

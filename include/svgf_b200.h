@@ -186,11 +186,16 @@ int svgf_fetch(svgf_ctx *ctx, const char *name, void *host, size_t bytes);
 const char *svgf_last_error(const svgf_ctx *ctx);    /* ctx may be NULL: last create error */
 int svgf_abi_version(void);
 
-/* Device-side time (ms) spent in each stage of the last svgf_render/svgf_denoise call, from CUDA events on
- * the context's stream: [0] path trace, [1] temporal, [2..8] a-trous levels 1..7, [9] pbo pack, [10] total. */
-int svgf_stage_times(svgf_ctx *ctx, float *ms11);
-/* Enable/disable per-stage event timing (off by default; it adds event records to the stream). */
+/* Per-stage event timing (off by default; it adds 12 event records per frame to the stream, no host syncs).
+ * Enabling it (re)starts a measurement window of at most 512 frames. */
 int svgf_set_profiling(svgf_ctx *ctx, int enabled);
+/* Average device time (ms) per stage over the frames rendered since profiling was enabled, from CUDA events on the
+ * context's stream: [0] path trace, [1] temporal, [2..8] a-trous level 1..7, [9] pbo pack, [10] whole frame.
+ * Synchronises the stream. */
+int svgf_stage_times(svgf_ctx *ctx, float *ms11);
+/* The CUDA stream (cudaStream_t) all of the context's work is issued on, for callers that bracket it with their
+ * own events. */
+void *svgf_stream(svgf_ctx *ctx);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------------------- */
 int svgf_set_shard(svgf_ctx *ctx, const svgf_shard *shard);
