@@ -10,6 +10,7 @@
 #include "svgf_internal.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -123,11 +124,11 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
 
 static int alloc_frame_buffers(svgf_ctx *c) {
     const size_t px = c->px;
-    for (int i = 0; i < 3; i++) CK(dalloc(&c->cv[i], px));
+    for (int i = 0; i < 3; i++) { CK(dalloc(&c->cv[i], px)); CK(dalloc(&c->lum[i], px)); }
     for (int i = 0; i < 2; i++) { CK(dalloc(&c->nrm[i], px)); CK(dalloc(&c->mom[i], px)); CK(dalloc(&c->hlen[i], px)); }
-    CK(dalloc(&c->pos, px)); CK(dalloc(&c->alb, px));
+    CK(dalloc(&c->pos, px)); CK(dalloc(&c->alb, px)); CK(dalloc(&c->gnp, px)); CK(dalloc(&c->gzl, px));
     CK(dalloc(&c->image, 3 * px)); CK(dalloc(&c->denoised, 3 * px)); CK(dalloc(&c->var_out, px));
-    CK(dalloc(&c->stale_nm, px)); CK(dalloc(&c->stale_uv, px));
+    CK(dalloc(&c->stale_nm, px)); CK(dalloc(&c->stale_uv, px)); CK(dalloc(&c->kl, px));
     CK(cudaMalloc((void **)&c->pbo_own, px * 8));
     CK(cudaMallocHost((void **)&c->pinned_image, px * 12));
     return SVGF_OK;
@@ -162,6 +163,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     if (!c) return SVGF_ERR_INVALID;
     c->device = device; c->W = scene->width; c->H = scene->height; c->px = (size_t)c->W * c->H;
     c->shard = svgf_shard{0, 1, 0, c->H};
+    if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = atoi(v) == 1 ? 1 : 2;    // 1 = direct kernel (A/B testing)
     memset(c->view_matrix_prev, 0, sizeof(c->view_matrix_prev));
     c->view_matrix_prev[0] = c->view_matrix_prev[5] = c->view_matrix_prev[10] = c->view_matrix_prev[15] = 1.0f;   // glm::mat4()
     int rc = SVGF_OK;
@@ -183,10 +185,10 @@ int svgf_destroy(svgf_ctx *c) {
     DeviceScene &s = c->scene;
     cudaFree(s.geoms); cudaFree(s.materials); cudaFree(s.bvh); cudaFree(s.tri_hot); cudaFree(s.tri_cold); cudaFree(s.textures);
     for (unsigned char *p : s.tex_pixels) cudaFree(p);      // the reference leaks these (pathtrace.cu:136 vs 160-183)
-    for (int i = 0; i < 3; i++) cudaFree(c->cv[i]);
+    for (int i = 0; i < 3; i++) { cudaFree(c->cv[i]); cudaFree(c->lum[i]); }
     for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }
-    cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
-    cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own);
+    cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->gnp); cudaFree(c->gzl); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
+    cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl);
     cudaFree(c->aos_in); cudaFree(c->aos_out); cudaFree(c->aos_g);
     if (c->pinned_image) cudaFreeHost(c->pinned_image);
     for (auto &pf : c->prof_pool) for (int i = 0; i < 12; i++) cudaEventDestroy(pf.ev[i]);
@@ -204,13 +206,14 @@ int svgf_reset(svgf_ctx *c) {
     CK(cudaSetDevice(c->device));
     const size_t px = c->px;
     cudaStream_t st = c->stream;
-    for (int i = 0; i < 3; i++) CK(cudaMemsetAsync(c->cv[i], 0, px * sizeof(float4), st));
+    for (int i = 0; i < 3; i++) { CK(cudaMemsetAsync(c->cv[i], 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->lum[i], 0, px * sizeof(float), st)); }
     for (int i = 0; i < 2; i++) {
         CK(cudaMemsetAsync(c->nrm[i], 0, px * sizeof(float4), st));
         CK(cudaMemsetAsync(c->mom[i], 0, px * sizeof(float2), st));
         CK(cudaMemsetAsync(c->hlen[i], 0, px * sizeof(int), st));
     }
     CK(cudaMemsetAsync(c->pos, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->alb, 0, px * sizeof(float4), st));
+    CK(cudaMemsetAsync(c->gnp, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->gzl, 0, px * sizeof(float2), st));
     CK(cudaMemsetAsync(c->image, 0, px * 12, st)); CK(cudaMemsetAsync(c->denoised, 0, px * 12, st));
     CK(cudaMemsetAsync(c->var_out, 0, px * 4, st));
     CK(cudaMemsetAsync(c->stale_nm, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->stale_uv, 0, px * sizeof(float2), st));
@@ -285,10 +288,10 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
     const float moment_alpha = P->temporal_enable ? P->moment_alpha : 1.0f;
     if (P->temporal_enable) {
         CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->nrm[c->cur_nrm ^ 1], c->pos, hist, c->mom[c->cur_mom],
-                           c->hlen[c->cur_hlen], acc, c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1], c->view_matrix_prev,
+                           c->hlen[c->cur_hlen], acc, c->lum[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1], c->view_matrix_prev,
                            color_alpha, moment_alpha, 1));
     } else {
-        CK(launch_no_temporal(c, image, acc));
+        CK(launch_no_temporal(c, image, acc, c->lum[acc_slot]));
     }
     if (ev) CK(cudaEventRecord(ev[2], c->stream));
     int new_hist = acc_slot;        // denoise.cu:366/370: colour history := accumulated (or input) colour
@@ -312,7 +315,8 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             AtrousArgs a;
             a.cv_in = c->cv[src];
             a.cv_out = (!last || is_hist) ? c->cv[dst] : nullptr;
-            a.nrm = c->nrm[c->cur_nrm]; a.pos = c->pos; a.alb = c->alb;
+            a.lum_in = c->lum[src]; a.lum_out = c->lum[dst];
+            a.nrm = c->nrm[c->cur_nrm]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
             a.denoised_out = last ? c->denoised : nullptr; a.var_out = last ? c->var_out : nullptr;
             a.level = level; a.is_last = last; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
             a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;
@@ -369,6 +373,7 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     rp.W = c->W; rp.H = c->H; rp.row_begin = c->shard.row_begin; rp.row_end = c->shard.row_end;
     rp.frame = frame; rp.max_depth = P->tracedepth; rp.trace_shadowray = P->shadowray; rp.reduce_var = P->reducevar;
     rp.denoise = P->denoise_enable; rp.sepcolor = P->sepcolor; rp.sintensity = P->sintensity; rp.lightradius = P->lightradius;
+    atrous_scales(P->sigman, P->sigmax, &rp.kn, &rp.kx);
     rp.cam = *cam;
     CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm]));
     if (ev) CK(cudaEventRecord(ev[1], c->stream));
@@ -407,7 +412,9 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     CK(cudaSetDevice(c->device));
     cudaEvent_t *ev = prof_begin(c, P);
     if (ev) { CK(cudaEventRecord(ev[0], c->stream)); CK(cudaEventRecord(ev[1], c->stream)); }
-    CK(launch_aos_to_soa(c, gbuffer_dev, c->nrm[c->cur_nrm], c->pos, c->alb));
+    float kn, kx;
+    atrous_scales(P->sigman, P->sigmax, &kn, &kx);
+    CK(launch_aos_to_soa(c, gbuffer_dev, c->nrm[c->cur_nrm], c->pos, c->alb, kn, kx));
     int rc = denoise_soa(c, input_dev, cam, P, ev);
     if (rc != SVGF_OK) return rc;
     CK(cudaMemcpyAsync(output_dev, c->denoised, c->px * 12, cudaMemcpyDeviceToDevice, c->stream));
@@ -447,9 +454,17 @@ extern "C" int svgf_atrous_host(svgf_ctx *c, float *color_out, float *variance_o
     for (size_t i = 0; i < px; i++) cv[i] = make_float4(color_in[3 * i], color_in[3 * i + 1], color_in[3 * i + 2], variance_in[i]);
     CK(cudaMemcpyAsync(c->cv[0], cv.data(), px * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->aos_g, gbuffer, px * sizeof(svgf_gbuffer_texel), cudaMemcpyHostToDevice, c->stream));
-    CK(launch_aos_to_soa(c, c->aos_g, c->nrm[0], c->pos, c->alb));
+    float kn, kx;
+    atrous_scales(P->sigman, P->sigmax, &kn, &kx);
+    CK(launch_aos_to_soa(c, c->aos_g, c->nrm[0], c->pos, c->alb, kn, kx));
+    {
+        std::vector<float> lm(px);
+        for (size_t i = 0; i < px; i++) lm[i] = (float)(0.2126 * color_in[3 * i] + 0.7152 * color_in[3 * i + 1] + 0.0722 * color_in[3 * i + 2]);
+        CK(cudaMemcpyAsync(c->lum[0], lm.data(), px * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     AtrousArgs a;
-    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb;
+    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.lum_in = c->lum[0]; a.lum_out = c->lum[1]; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
     a.denoised_out = is_last ? c->denoised : nullptr; a.var_out = is_last ? c->var_out : nullptr;
     a.level = level; a.is_last = is_last != 0; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
     a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;

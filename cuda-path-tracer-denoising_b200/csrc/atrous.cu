@@ -27,7 +27,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct AtrousK {
     const float4 *cv_in; float4 *cv_out;
+    const float *lum_in; float *lum_out;
     const float4 *nrm, *pos, *alb;
+    const float4 *gnp; const float2 *gzl;       // pre-scaled, interleaved G-buffer view (svgf_internal.h)
     float *denoised_out, *var_out;
     int W, H, row_begin, row_end, step;
     int is_last, blur_variance, addcolor;
@@ -101,24 +103,300 @@ atrous_direct_kernel(AtrousK k) {
         d[0] = o.x; d[1] = o.y; d[2] = o.z;
         k.var_out[p] = o.w;
     }
-    if (k.cv_out) k.cv_out[p] = o;
+    if (k.cv_out) { k.cv_out[p] = o; k.lum_out[p] = lum_ref(o.x, o.y, o.z); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2: lattice-tiled kernel.
+//
+// With step s the 5x5 dilated stencil only couples pixels of one residue class (x mod s, y mod s): on that
+// sub-lattice it is a DENSE 5x5 stencil. A block therefore owns a tile of LX x LY lattice points (x C adjacent
+// columns, so every global access is a full 32-byte sector) of one class, stages tile + 2-point apron once into
+// shared memory -- the same code and the same apron cost (1.4x) for step 2 and step 128 -- and every thread
+// computes a 2 x 4 patch of lattice points from a 6 x 8 window of taps held one at a time in registers, so each tap
+// is read from shared memory once per thread and reused for up to 8 centres (4.2 pair evaluations per 48-byte read).
+//   shared memory per tap: {r,g,b,var} {kn*n, lum} {kx*p, -}: normals/positions are pre-scaled by log2(e)/(sigma+1e-6)
+//   so the edge-stopping exponent is  |lq-lp|*kl + |n'q-n'p| + |p'q-p'p|  (2 sqrt.approx + 1 ex2.approx per pair).
+//   Out-of-image taps carry lum = 3e38: their exponent overflows and ex2(-inf) = 0 removes them without a branch.
+// Bank conflicts: a quarter-warp (8 lanes) reads 8 consecutive float4 (even/odd lattice columns are stored in
+// separate halves of a row because a thread's window starts at column 2*ap).
+constexpr int AT_LX = 16, AT_LY = 32, AT_C = 2, AT_TX = 2, AT_TY = 4;
+constexpr int AT_THREADS = (AT_LX / AT_TX) * (AT_LY / AT_TY) * AT_C;        // 128
+constexpr int AT_SW = AT_LX + 4, AT_SH = AT_LY + 4;                         // staged lattice points
+constexpr int AT_TILE = AT_SW * AT_SH * AT_C;                               // 1440 taps
+constexpr int AT_SMEM = AT_TILE * 48;                                       // 69120 B
+
+__device__ __forceinline__ int at_idx(int c, int tb, int ta) {
+    return ((c * AT_SH + tb) * 2 + (ta & 1)) * (AT_SW / 2) + (ta >> 1);
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+struct AtrousT {
+    AtrousK k;
+    int b_first;        // first lattice row index covered by the grid (row_begin / step)
+    int ncg;            // column groups per class row: step / C
+    const float *kl;    // per-pixel luminance-weight scale from atrous_kl_kernel
+};
+
+// Pre-pass of a level: per-pixel luminance-weight scale  kl = log2(e) / (sqrt(max(blur3x3(variance), 0)) * sigma_l + 1e-6)
+// (denoise.cu:100-118,143). The 3x3 Gaussian lives in PIXEL space, i.e. across residue classes, so it is done here where
+// it is coalesced instead of per lattice point inside the tiled kernel. 4 B read (L1-shared) + 4 B written per pixel.
+__global__ void __launch_bounds__(256)
+atrous_kl_kernel(const float4 *__restrict__ cv, float *__restrict__ kl, int W, int H, int row_begin, int row_end,
+                 int blur_variance, float sigma_c) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= row_end) return;
+    float var;
+    if (blur_variance) {
+        float sum = 0.0f, sumw = 0.0f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                const int lx = x + dx, ly = y + dy;
+                if (lx >= 0 && ly >= 0 && lx < W && ly < H) {
+                    const float g = (dx == 0 ? 0.5f : 0.25f) * (dy == 0 ? 0.5f : 0.25f);
+                    sum += g * __ldg(&cv[lx + ly * W].w);
+                    sumw += g;
+                }
+            }
+        var = sum / sumw;
+    } else {
+        var = __ldg(&cv[x + y * W].w);
+    }
+    var = fmaxf(var, 0.0f);
+    // fp32: the reference's fp64 add/divide here (denoise.cu:143) only has to be matched to ~1e-7 relative
+    kl[x + y * W] = 1.4426950408889634f / (sqrtf(var) * sigma_c + 1e-6f);
+}
+
+// Edge-stopping weight and accumulation of ONE (tap, centre) pair, written for Blackwell's packed fp32 pipe
+// (FADD2/FMUL2/FFMA2, sm_100+): normal and position differences travel as float2 {n, p} lanes, so the two squared
+// distances cost 6 packed instructions instead of 12, and {sum w, sum w^2} / {b, var} accumulate as pairs.
+struct AtCentre {           // negated so that tap + centre = difference
+    float2 nx_px, ny_py, nz_pz;     // {-kn*n, -kx*p} per component
+    float lum, kl;
+};
+struct AtAcc { float2 w_w2, b_v; float r, g; };
+struct AtTap { float4 cv; float2 nx_px, ny_py, nz_pz; float lum; };
+
+__device__ __forceinline__ void at_pair(const AtTap &T, const AtCentre &C, AtAcc &A, float h) {
+    const float2 dx = __fadd2_rn(T.nx_px, C.nx_px), dy = __fadd2_rn(T.ny_py, C.ny_py), dz = __fadd2_rn(T.nz_pz, C.nz_pz);
+    const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));       // {|dn|^2, |dp|^2}
+    const float dn = sqrt_approx(d2.x), dp = sqrt_approx(d2.y);
+    const float e = fmaf(fabsf(T.lum - C.lum), C.kl, dn) + dp;
+    float2 ww;
+    ww.x = h * ex2_approx(-e);
+    ww.y = ww.x * ww.x;
+    A.w_w2 = __fadd2_rn(A.w_w2, ww);
+    A.b_v = __ffma2_rn(make_float2(T.cv.z, T.cv.w), ww, A.b_v);
+    A.r = fmaf(T.cv.x, ww.x, A.r);
+    A.g = fmaf(T.cv.y, ww.x, A.g);
+}
+
+// One tap column (window column `tt` of the thread's 6) against the thread's 2 x 4 centres. DO0/DO1 select which of the
+// two centre columns the tap column reaches (|i| <= 2), so the edge columns are peeled without wasted work.
+template <bool DO0, bool DO1>
+__device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np, const float4 *s_zl, int c, int row0, int col,
+                                          const AtCentre (&C)[AT_TX][AT_TY], AtAcc (&A)[AT_TX][AT_TY], float hi0, float hi1) {
+    // h = hi * hj with hj in {3/8, 1/4, 1/16} for |j| = 0, 1, 2
+    const float h0[3] = {hi0 * 0.375f, hi0 * 0.25f, hi0 * 0.0625f}, h1[3] = {hi1 * 0.375f, hi1 * 0.25f, hi1 * 0.0625f};
+#pragma unroll
+    for (int u = 0; u < AT_TY + 4; u++) {
+        const int si = at_idx(c, row0 + u, col);
+        const float4 np = s_np[si], zl = s_zl[si];
+        AtTap T;
+        T.cv = s_cv[si];
+        T.nx_px = make_float2(np.x, np.y); T.ny_py = make_float2(np.z, np.w); T.nz_pz = make_float2(zl.x, zl.y); T.lum = zl.z;
+#pragma unroll
+        for (int cb = 0; cb < AT_TY; cb++) {
+            const int j = u - 2 - cb, aj = j < 0 ? -j : j;
+            if (aj > 2) continue;       // compile-time
+            if (DO0) at_pair(T, C[0][cb], A[0][cb], h0[aj]);
+            if (DO1) at_pair(T, C[1][cb], A[1][cb], h1[aj]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 3)
+atrous_tiled_kernel(AtrousT t) {
+    extern __shared__ __align__(16) float4 at_smem[];
+    // per tap: {r,g,b,var}  {kn*nx, kx*px, kn*ny, kx*py}  {kn*nz, kx*pz, lum, -}  (the G-buffer part arrives pre-scaled)
+    float4 *s_cv = at_smem, *s_np = at_smem + AT_TILE, *s_zl = at_smem + 2 * AT_TILE;
+    const AtrousK &k = t.k;
+    const int W = k.W, H = k.H, step = k.step;
+    const int cg = blockIdx.x % t.ncg, tile_x = blockIdx.x / t.ncg;
+    const int yc = blockIdx.y % step, tile_y = blockIdx.y / step;
+    const int X0 = cg * AT_C;
+    const int a0 = tile_x * AT_LX - 2, b0 = t.b_first + tile_y * AT_LY - 2;
+    const int tid = threadIdx.x;
+
+    // ---- stage tile + apron with cp.async (LDGSTS): every thread queues all of its 16-byte copies back to back and
+    // none of the data passes through registers, so a block exposes ONE memory round trip instead of one per loop trip.
+    // Out-of-image taps: zero-filled colour/geometry and lum = 3e38 (exponent overflows, ex2(-inf) = 0). ----
+    for (int n = tid; n < AT_TILE; n += AT_THREADS) {
+        const int c = n % AT_C, ta = (n / AT_C) % AT_SW, tb = n / (AT_C * AT_SW);
+        const int x = X0 + (a0 + ta) * step + c, y = yc + (b0 + tb) * step;
+        const int si = at_idx(c, tb, ta);
+        if (a0 + ta >= 0 && b0 + tb >= 0 && x < W && y < H) {
+            const int q = x + y * W;
+            cp_async16(&s_cv[si], &k.cv_in[q]);
+            cp_async16(&s_np[si], &k.gnp[q]);
+            cp_async8(&s_zl[si], &k.gzl[q]);
+            cp_async4(&s_zl[si].z, &k.lum_in[q]);
+        } else {
+            s_cv[si] = make_float4(0.f, 0.f, 0.f, 0.f); s_np[si] = make_float4(0.f, 0.f, 0.f, 0.f);
+            s_zl[si] = make_float4(0.f, 0.f, 3e38f, 0.f);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const int ap = tid & 7, c = (tid >> 3) & 1, bq = tid >> 4;
+    // centres' kl from the pre-pass plane, issued before the barrier
+    float c_kl[AT_TX][AT_TY];
+    bool live = false;
+#pragma unroll
+    for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+        for (int cb = 0; cb < AT_TY; cb++) {
+            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + 4 * bq + cb + 2) * step;
+            const bool ok = x < W && y >= k.row_begin && y < k.row_end;
+            live |= ok;
+            c_kl[ca][cb] = ok ? __ldg(&t.kl[x + y * W]) : 0.f;
+        }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!live) return;
+
+    AtCentre C[AT_TX][AT_TY];
+    AtAcc A[AT_TX][AT_TY];
+#pragma unroll
+    for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+        for (int cb = 0; cb < AT_TY; cb++) {
+            const int si = at_idx(c, 4 * bq + cb + 2, 2 * ap + ca + 2);
+            const float4 np = s_np[si], zl = s_zl[si];
+            C[ca][cb].nx_px = make_float2(-np.x, -np.y); C[ca][cb].ny_py = make_float2(-np.z, -np.w);
+            C[ca][cb].nz_pz = make_float2(-zl.x, -zl.y); C[ca][cb].lum = zl.z; C[ca][cb].kl = c_kl[ca][cb];
+            A[ca][cb].w_w2 = make_float2(0.f, 0.f); A[ca][cb].b_v = make_float2(0.f, 0.f); A[ca][cb].r = 0.f; A[ca][cb].g = 0.f;
+        }
+
+    // ---- 6 tap columns x 8 tap rows. Columns 1..4 reach both centre columns and run as a rolled loop whose body is one
+    // large basic block (8 taps, 40 independent pair evaluations: plenty of ILP for 12 warps/SM, 13 KB of SASS);
+    // columns 0 and 5 reach one centre column each and are peeled. The centre tap takes the generic path: all
+    // differences are 0, sqrt(0) = 0, ex2(-0) = 1 exactly. ----
+    const int row0 = 4 * bq, col0 = 2 * ap;
+    at_column<true, false>(s_cv, s_np, s_zl, c, row0, col0 + 0, C, A, 0.0625f, 0.f);        // i = -2 for centre column 0
+#pragma unroll 1
+    for (int tt = 1; tt <= 4; tt++) {
+        const int i0 = tt - 2, i1 = tt - 3;
+        const float hi0 = i0 == 0 ? 0.375f : ((i0 == 1 || i0 == -1) ? 0.25f : 0.0625f);
+        const float hi1 = i1 == 0 ? 0.375f : ((i1 == 1 || i1 == -1) ? 0.25f : 0.0625f);
+        at_column<true, true>(s_cv, s_np, s_zl, c, row0, col0 + tt, C, A, hi0, hi1);
+    }
+    at_column<false, true>(s_cv, s_np, s_zl, c, row0, col0 + 5, C, A, 0.f, 0.0625f);        // i = +2 for centre column 1
+
+    // ---- outputs: all 8 results (incl. the fp64 luminance of the new colour, a long dependent chain) are computed as
+    // straight-line code first, then stored under predicates, so the 8 chains overlap ----
+    float4 o[AT_TX][AT_TY]; float ol[AT_TX][AT_TY]; int op[AT_TX][AT_TY];
+#pragma unroll
+    for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+        for (int cb = 0; cb < AT_TY; cb++) {
+            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + 4 * bq + cb + 2) * step;
+            op[ca][cb] = (x < W && y >= k.row_begin && y < k.row_end) ? x + y * W : -1;
+            // weights_sum >= 9/64 always (the centre tap), so the reference's `else` branch (denoise.cu:162-164) is dead
+            const AtAcc &a = A[ca][cb];
+            const float rw = __frcp_rn(a.w_w2.x);
+            o[ca][cb] = make_float4(a.r * rw, a.g * rw, a.b_v.x * rw, __fdividef(a.b_v.y, a.w_w2.y));
+        }
+    if (k.is_last && k.addcolor) {
+#pragma unroll
+        for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+            for (int cb = 0; cb < AT_TY; cb++) {
+                const float4 al = __ldg(&k.alb[max(op[ca][cb], 0)]);
+                o[ca][cb].x *= al.x; o[ca][cb].y *= al.y; o[ca][cb].z *= al.z;
+            }
+    }
+    if (k.cv_out) {
+#pragma unroll
+        for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+            for (int cb = 0; cb < AT_TY; cb++) ol[ca][cb] = lum_ref(o[ca][cb].x, o[ca][cb].y, o[ca][cb].z);
+    }
+#pragma unroll
+    for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+        for (int cb = 0; cb < AT_TY; cb++) {
+            const int p = op[ca][cb];
+            if (p < 0) continue;
+            if (k.is_last) {
+                float *d = k.denoised_out + 3 * (size_t)p;
+                d[0] = o[ca][cb].x; d[1] = o[ca][cb].y; d[2] = o[ca][cb].z;
+                k.var_out[p] = o[ca][cb].w;
+            }
+            if (k.cv_out) { k.cv_out[p] = o[ca][cb]; k.lum_out[p] = ol[ca][cb]; }
+        }
 }
 
 }  // namespace
+
+// log2(e) / (sigma + 1e-6) in fp64 (the reference adds and divides in double, denoise.cu:144-145)
+void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx) {
+    const double log2e = 1.4426950408889634;
+    *kn = (float)(log2e / ((double)sigma_n + 1e-6));
+    *kx = (float)(log2e / ((double)sigma_x + 1e-6));
+}
 
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     AtrousK k;
-    k.cv_in = a.cv_in; k.cv_out = a.cv_out; k.nrm = a.nrm; k.pos = a.pos; k.alb = a.alb;
+    k.cv_in = a.cv_in; k.cv_out = a.cv_out; k.lum_in = a.lum_in; k.lum_out = a.lum_out; k.nrm = a.nrm; k.pos = a.pos; k.alb = a.alb;
+    k.gnp = a.gnp; k.gzl = a.gzl;
     k.denoised_out = a.denoised_out; k.var_out = a.var_out;
     k.W = c->W; k.H = c->H; k.row_begin = c->shard.row_begin; k.row_end = c->shard.row_end; k.step = 1 << a.level;
     k.is_last = a.is_last; k.blur_variance = a.blur_variance; k.addcolor = a.addcolor;
     k.sigma_c = a.sigma_c;
-    const double log2e = 1.4426950408889634;
-    k.kn = (float)(log2e / ((double)a.sigma_n + 1e-6));
-    k.kx = (float)(log2e / ((double)a.sigma_x + 1e-6));
-    dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
-    atrous_direct_kernel<<<g, b, 0, c->stream>>>(k);
+    atrous_scales(a.sigma_n, a.sigma_x, &k.kn, &k.kx);
+    if (c->atrous_variant == 1) {
+        dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
+        atrous_direct_kernel<<<g, b, 0, c->stream>>>(k);
+        return cudaGetLastError();
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(atrous_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    AtrousT t;
+    t.k = k; t.kl = c->kl;
+    {
+        dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
+        atrous_kl_kernel<<<g, b, 0, c->stream>>>(k.cv_in, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c);
+    }
+    const int step = k.step;
+    t.b_first = k.row_begin / step;
+    t.ncg = step / AT_C;
+    const int lat_w = (c->W + step - 1) / step;                                 // lattice columns per class
+    const int lat_rows = (k.row_end - 1) / step - t.b_first + 1;                // lattice rows touching the strip
+    dim3 g(((lat_w + AT_LX - 1) / AT_LX) * t.ncg, ((lat_rows + AT_LY - 1) / AT_LY) * step);
+    atrous_tiled_kernel<<<g, AT_THREADS, AT_SMEM, c->stream>>>(t);
     return cudaGetLastError();
 }

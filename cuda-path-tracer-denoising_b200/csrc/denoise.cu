@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256)
 temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
                 const float4 *__restrict__ nrm_cur, const float4 *__restrict__ nrm_prev, const float4 *__restrict__ pos,
                 const float4 *__restrict__ hist_cv, const float2 *__restrict__ mom_hist, const int *__restrict__ hlen_in,
-                float4 *__restrict__ acc_cv, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
+                float4 *__restrict__ acc_cv, float *__restrict__ acc_lum, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
                 float color_alpha_min, float moment_alpha_min) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
@@ -121,23 +121,29 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
             const float second = moment_alpha * pm2 + (1.0f - moment_alpha) * luminance * luminance;
             mom_acc[p] = make_float2(first, second);
             const float variance = second - first * first;
-            acc_cv[p] = make_float4(sr * color_alpha + pr * (1.0f - color_alpha), sg * color_alpha + pg * (1.0f - color_alpha),
-                                    sb * color_alpha + pb * (1.0f - color_alpha), variance > 0.0f ? variance : 0.0f);
+            const float ar = sr * color_alpha + pr * (1.0f - color_alpha), ag = sg * color_alpha + pg * (1.0f - color_alpha),
+                        ab = sb * color_alpha + pb * (1.0f - color_alpha);
+            acc_cv[p] = make_float4(ar, ag, ab, variance > 0.0f ? variance : 0.0f);
+            acc_lum[p] = (float)(0.2126 * ar + 0.7152 * ag + 0.0722 * ab);      // what the a-trous taps will read (denoise.cu:121,138)
             return;
         }
     }
     hlen_out[p] = 1;
     mom_acc[p] = make_float2(luminance, luminance * luminance);
     acc_cv[p] = make_float4(sr, sg, sb, 100.0f);
+    acc_lum[p] = luminance;
 }
 
 __global__ void __launch_bounds__(256)
-no_temporal_kernel(int W, int row_begin, int row_end, const float *__restrict__ image, float4 *__restrict__ acc_cv) {
+no_temporal_kernel(int W, int row_begin, int row_end, const float *__restrict__ image, float4 *__restrict__ acc_cv,
+                   float *__restrict__ acc_lum) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= row_end) return;
     const size_t p = x + (size_t)y * W;
-    acc_cv[p] = make_float4(image[3 * p], image[3 * p + 1], image[3 * p + 2], 10.0f);
+    const float r = image[3 * p], g = image[3 * p + 1], b = image[3 * p + 2];
+    acc_cv[p] = make_float4(r, g, b, 10.0f);
+    acc_lum[p] = (float)(0.2126 * r + 0.7152 * g + 0.0722 * b);
 }
 
 // clamp((int)(v * 255.0), 0, 255) with the reference's DOUBLE product (pathtrace.cu:60-62), evaluated in fp32:
@@ -183,7 +189,7 @@ cv_to_outputs_kernel(size_t begin, size_t end, const float4 *__restrict__ cv, fl
 
 __global__ void __launch_bounds__(256)
 aos_to_soa_kernel(size_t n, const svgf_gbuffer_texel *__restrict__ g, float4 *__restrict__ nrm, float4 *__restrict__ pos,
-                  float4 *__restrict__ alb) {
+                  float4 *__restrict__ alb, float4 *__restrict__ gnp, float2 *__restrict__ gzl, float kn, float kx) {
     const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
     const float *t = reinterpret_cast<const float *>(g + p);
@@ -191,6 +197,8 @@ aos_to_soa_kernel(size_t n, const svgf_gbuffer_texel *__restrict__ g, float4 *__
     pos[p] = make_float4(t[3], t[4], t[5], 0.f);
     // the last a-trous level multiplies by albedo * ialbedo (denoise.cu:167); fold ialbedo in here
     alb[p] = make_float4(t[6] * t[9], t[7] * t[10], t[8] * t[11], 0.f);
+    gnp[p] = make_float4(t[0] * kn, t[3] * kx, t[1] * kn, t[4] * kx);
+    gzl[p] = make_float2(t[2] * kn, t[5] * kx);
 }
 
 __global__ void __launch_bounds__(256)
@@ -217,23 +225,23 @@ inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (
 
 cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const float4 *nrm_prev,
                             const float4 *pos, const float4 *hist_cv, const float2 *mom_hist, const int *hlen_in,
-                            float4 *acc_cv, float2 *mom_acc, int *hlen_out, const float *prev_viewmat,
+                            float4 *acc_cv, float *acc_lum, float2 *mom_acc, int *hlen_out, const float *prev_viewmat,
                             float color_alpha, float moment_alpha, int) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     Mat4 vm; for (int i = 0; i < 16; i++) vm.m[i] = prev_viewmat[i];
     dim3 b(32, 8);
     temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
-                                                                 nrm_prev, pos, hist_cv, mom_hist, hlen_in, acc_cv, mom_acc,
+                                                                 nrm_prev, pos, hist_cv, mom_hist, hlen_in, acc_cv, acc_lum, mom_acc,
                                                                  hlen_out, vm, color_alpha, moment_alpha);
     return cudaGetLastError();
 }
 
-cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv) {
+cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float *acc_lum) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     dim3 b(32, 8);
-    no_temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->shard.row_begin, c->shard.row_end, image, acc_cv);
+    no_temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->shard.row_begin, c->shard.row_end, image, acc_cv, acc_lum);
     return cudaGetLastError();
 }
 
@@ -264,8 +272,8 @@ cudaError_t launch_cv_to_outputs(svgf_ctx *c, const float4 *cv, float *denoised,
     return cudaGetLastError();
 }
 
-cudaError_t launch_aos_to_soa(svgf_ctx *c, const svgf_gbuffer_texel *g, float4 *nrm, float4 *pos, float4 *alb) {
-    aos_to_soa_kernel<<<(unsigned)((c->px + 255) / 256), 256, 0, c->stream>>>(c->px, g, nrm, pos, alb);
+cudaError_t launch_aos_to_soa(svgf_ctx *c, const svgf_gbuffer_texel *g, float4 *nrm, float4 *pos, float4 *alb, float kn, float kx) {
+    aos_to_soa_kernel<<<(unsigned)((c->px + 255) / 256), 256, 0, c->stream>>>(c->px, g, nrm, pos, alb, c->gnp, c->gzl, kn, kx);
     return cudaGetLastError();
 }
 

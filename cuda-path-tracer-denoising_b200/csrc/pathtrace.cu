@@ -349,7 +349,8 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
           int n_materials, const float4 *__restrict__ bvh, int n_nodes, const float4 *__restrict__ tri_hot,
           const float4 *__restrict__ tri_cold, const TexD *__restrict__ textures,
           float4 *__restrict__ nrm_out, float4 *__restrict__ pos_out, float4 *__restrict__ alb_out,
-          float *__restrict__ image, float4 *__restrict__ stale_nm, float2 *__restrict__ stale_uv) {
+          float *__restrict__ image, float4 *__restrict__ stale_nm, float2 *__restrict__ stale_uv,
+          float4 *__restrict__ gnp_out, float2 *__restrict__ gzl_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     GeomD *s_geoms = reinterpret_cast<GeomD *>(smem);
     svgf_material *s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomD) * n_geoms);
@@ -395,6 +396,8 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
         nrm_out[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.geomId));
         pos_out[idx] = make_float4(p.x, p.y, p.z, 0.f);
         alb_out[idx] = make_float4(a.x, a.y, a.z, 0.f);
+        gnp_out[idx] = make_float4(is.n.x * P.kn, p.x * P.kx, is.n.y * P.kn, p.y * P.kx);
+        gzl_out[idx] = make_float2(is.n.z * P.kn, p.z * P.kx);
     }
     F3 acc = mk(0, 0, 0);
     for (int depth = 1; depth <= P.max_depth; depth++) {
@@ -460,6 +463,6 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
     dim3 block(RT_BX, RT_BY), grid((p.W + RT_BX - 1) / RT_BX, (rows + RT_BY - 1) / RT_BY);
     rt_kernel<<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes,
                                                 s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, c->alb, c->image,
-                                                c->stale_nm, c->stale_uv);
+                                                c->stale_nm, c->stale_uv, c->gnp, c->gzl);
     return cudaGetLastError();
 }

@@ -58,16 +58,22 @@ struct svgf_ctx {
     svgf_shard shard{0, 1, 0, 0};
 
     float4 *cv[3] = {nullptr, nullptr, nullptr};
+    float *lum[3] = {nullptr, nullptr, nullptr};    // luminance of cv[i].rgb, the reference's fp64 formula (denoise.cu:121)
+    int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled
     int hist_cv = -1;                   // which cv[] holds the colour history for the next frame (-1: none yet)
     float4 *nrm[2] = {nullptr, nullptr};
     int cur_nrm = 0;
     float4 *pos = nullptr, *alb = nullptr;
+    // a-trous view of the G-buffer, pre-scaled by the edge-stopping constants kn = log2(e)/(sigma_n + 1e-6) and
+    // kx = log2(e)/(sigma_x + 1e-6) and interleaved for the packed-fp32 distance code: {kn nx, kx px, kn ny, kx py}, {kn nz, kx pz}
+    float4 *gnp = nullptr; float2 *gzl = nullptr;
     float2 *mom[2] = {nullptr, nullptr};
     int cur_mom = 0;                    // mom[cur_mom] = history, the other = accumulated
     int *hlen[2] = {nullptr, nullptr};
     int cur_hlen = 0;
     float *image = nullptr, *denoised = nullptr, *var_out = nullptr;
     float4 *stale_nm = nullptr; float2 *stale_uv = nullptr;
+    float *kl = nullptr;                // per-level scratch: luminance-weight scale per pixel (atrous.cu)
     unsigned char *pbo_own = nullptr;   // used when the caller passes no PBO
 
     // scratch for the AoS entry point svgf_denoise() and the host conveniences
@@ -107,17 +113,21 @@ struct RtParams {
     int frame, max_depth;
     int trace_shadowray, reduce_var, denoise, sepcolor;
     float sintensity, lightradius;
+    float kn, kx;                       // a-trous edge-stopping scales for the pre-scaled G-buffer planes
     svgf_camera cam;
 };
+void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx);
 cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out);
 cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const float4 *nrm_prev,
                             const float4 *pos, const float4 *hist_cv, const float2 *mom_hist, const int *hlen_in,
-                            float4 *acc_cv, float2 *mom_acc, int *hlen_out, const float *prev_viewmat,
+                            float4 *acc_cv, float *acc_lum, float2 *mom_acc, int *hlen_out, const float *prev_viewmat,
                             float color_alpha, float moment_alpha, int has_history);
-cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv);
+cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float *acc_lum);
 struct AtrousArgs {
     const float4 *cv_in; float4 *cv_out;            // cv_out may be null on the last level
+    const float *lum_in; float *lum_out;
     const float4 *nrm, *pos, *alb;
+    const float4 *gnp; const float2 *gzl;
     float *denoised_out; float *var_out;            // last level only (AoS vec3 + float plane)
     int level, is_last, blur_variance, addcolor;
     float sigma_c, sigma_n, sigma_x;
@@ -126,7 +136,7 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a);
 cudaError_t launch_cv_to_outputs(svgf_ctx *c, const float4 *cv, float *denoised, float *var_out);
 cudaError_t launch_debug_view(svgf_ctx *c, int option, const int *hlen, const float4 *cv, float *denoised);
 cudaError_t launch_pack_pbo(svgf_ctx *c, unsigned char *pbo, const float *left, const float *right);
-cudaError_t launch_aos_to_soa(svgf_ctx *c, const svgf_gbuffer_texel *g, float4 *nrm, float4 *pos, float4 *alb);
+cudaError_t launch_aos_to_soa(svgf_ctx *c, const svgf_gbuffer_texel *g, float4 *nrm, float4 *pos, float4 *alb, float kn, float kx);
 cudaError_t launch_soa_to_aos(svgf_ctx *c, const float4 *nrm, const float4 *pos, const float4 *alb, svgf_gbuffer_texel *g);
 cudaError_t launch_copy_f3(svgf_ctx *c, float *dst, const float *src);
 
