@@ -5,7 +5,9 @@
 
 A "step" is one frame: pathtrace(pbo, frame) = 1-spp path trace -> temporal accumulation -> N-level a-trous ->
 PBO pack, on synthetic input (the reference's own scene description, random-free; RNG seeded by pixel/frame).
-N = 1 runs C2 (cornell 1920x1080, 5 a-trous levels), the configuration BASELINE.json's metric is quoted on.
+N = 1 runs C2 (cornell 1920x1080, 5 a-trous levels), the configuration BASELINE.json's metric is quoted on;
+N > 1 runs C4 (cornell 3840x2160) with the frame sharded by row strips over the N GPUs (strong scaling). `value` is
+Mpixels/sec (BASELINE.json: "frames/sec & Mpixels/sec") so that the two resolutions share a unit; `fps` is alongside.
 Prints ONE JSON line (rank 0). Keys follow the driver's contract; see DESIGN.md "Measurement".
 
   value     frames/s with everything resident on the device (no host image requested), CUDA events on the
@@ -108,7 +110,7 @@ def cpu_baseline(wl, frames=2):
     for f in range(frames):
         o.frame(drv.step(), P, f, orc.VAR_JACOBI, threads)
     dt = time.perf_counter() - t0
-    return {"value": frames / dt, "unit": "frames/sec", "cores": threads, "kind": "port",
+    return {"value": frames / dt * wl["W"] * wl["H"] / 1e6, "unit": "Mpixels/sec", "fps": frames / dt, "cores": threads, "kind": "port",
             "sample": "%d frames of %s from reset, oracle/svgf_oracle.cpp (OpenMP, %d threads), %.1f s" % (frames, wl["name"], threads, dt)}
 
 
@@ -117,7 +119,8 @@ def run_reference(args, wl, rank, world):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refh
-    line = {"impl": "reference", "metric": "frames/sec", "unit": "frames/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    px = wl["W"] * wl["H"]
+    line = {"impl": "reference", "metric": "Mpixels/sec", "unit": "Mpixels/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "scene": wl["scene"], "width": wl["W"], "height": wl["H"], "atrous_levels": wl["nlevel"]}}
     if refh.available("gpu"):
@@ -130,12 +133,12 @@ def run_reference(args, wl, rank, world):
             h.time_frames(max(args.warmup, 1))
             ms = h.time_frames(args.steps)
             fps = 1000.0 * args.steps / ms
-            line.update({"value": fps, "ms_per_step": ms / args.steps, "mpixels_per_sec": fps * wl["W"] * wl["H"] / 1e6,
-                         "cpu_baseline": {"value": fps, "unit": "frames/sec", "cores": 0, "kind": "reference",
+            line.update({"value": fps * px / 1e6, "fps": fps, "ms_per_step": ms / args.steps,
+                         "cpu_baseline": {"value": fps * px / 1e6, "unit": "Mpixels/sec", "cores": 0, "kind": "reference",
                                           "sample": "the reference's own CUDA path (src/pathtrace.cu + src/denoise.cu built for sm_100, "
                                                     "oracle/_ref/libref_gpu.so) on 1 GPU: it has no CPU implementation; %d frames, host clock "
                                                     "(every reference frame ends in a blocking D2H)" % args.steps},
-                         "e2e": {"value": fps, "unit": "frames/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": wl["W"] * wl["H"] * 12},
+                         "e2e": {"value": fps * px / 1e6, "unit": "Mpixels/sec", "fps": fps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": px * 12},
                          "config": dict(line["config"], parallelism="1 GPU (the reference is single-GPU)", device="gpu")})
             print(json.dumps(line), flush=True)
             return
@@ -143,8 +146,8 @@ def run_reference(args, wl, rank, world):
             line["note"] = "reference GPU binary failed: %s" % e
     frames = max(1, min(args.steps, 2))
     cb = cpu_baseline(wl, frames)
-    line.update({"value": cb["value"], "ms_per_step": 1000.0 / cb["value"], "cpu_baseline": cb,
-                 "e2e": {"value": cb["value"], "unit": "frames/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    line.update({"value": cb["value"], "fps": cb["fps"], "ms_per_step": 1000.0 / cb["fps"], "cpu_baseline": cb,
+                 "e2e": {"value": cb["value"], "unit": "Mpixels/sec", "fps": cb["fps"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "config": dict(line["config"], parallelism="host cores", device="cpu (oracle port; reference binary absent)")})
     print(json.dumps(line), flush=True)
 
@@ -161,6 +164,9 @@ def run_ours(args, wl, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W, H, nl = wl["W"], wl["H"], wl["nlevel"]
     blob, R = m.open_scene(wl["scene"], W, H, device=local_rank)
+    rows = [0, H]
+    if world > 1:       # shard the frame by row strips; other strips' rows are read in place over NVLink (CUDA IPC)
+        rows = m.connect_ranks(R, dist, rank, world)
     P = m.default_params(atrous_nlevel=nl)
     drv = blob.camera_driver(W, H, automate=wl["moving"])
     stream = torch.cuda.ExternalStream(R.stream(), device=torch.device("cuda", local_rank))
@@ -208,12 +214,13 @@ def run_ours(args, wl, rank, world, local_rank):
     if rank != 0:
         return
     px = W * H
-    # replicas: every rank renders whole frames (see DESIGN.md "Multi-GPU"); aggregate = world x per-rank rate
-    fps_dev = world * args.steps * 1000.0 / ms_dev
-    fps_e2e = world * args.steps * 1000.0 / ms_e2e
+    # strong scaling: all ranks together render ONE frame per step (row strips)
+    fps_dev = args.steps * 1000.0 / ms_dev
+    fps_e2e = args.steps * 1000.0 / ms_e2e
     peak, peak_src = measured_peak()
     lv_ms = [float(stage[2 + l]) for l in range(nl)]
-    lv_bytes = [px * (68 if l == nl - 1 else 56) for l in range(nl)]
+    strip_px = W * (rows[rank + 1] - rows[rank]) if world > 1 else px       # rank 0's launches cover its strip
+    lv_bytes = [strip_px * (68 if l == nl - 1 else 56) for l in range(nl)]
     lv_gbs = [b / (t * 1e-3) / 1e9 if t > 0 else 0.0 for b, t in zip(lv_bytes, lv_ms)]
     tot_ms = sum(lv_ms)
     achieved = sum(lv_bytes) / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
@@ -222,18 +229,18 @@ def run_ours(args, wl, rank, world, local_rank):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     cb = cpu_baseline(wl, 2) if world == 1 and not args.no_cpu_baseline else None
-    launches_per_frame = 1 + 1 + nl + 1
+    launches_per_frame = 1 + 1 + 2 * nl + 1 + (0 if world == 1 else 3 + 2 * nl)     # rt, temporal, (kl + tiled) x levels, pack [+ signal/wait]
     line = {
-        "metric": "frames/sec", "value": fps_dev, "unit": "frames/sec", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+        "metric": "Mpixels/sec", "value": fps_dev * px / 1e6, "unit": "Mpixels/sec", "fps": fps_dev, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "scene": wl["scene"], "width": W, "height": H, "atrous_levels": nl,
-                   "parallelism": "1 GPU" if world == 1 else "%d replicas" % world,
+                   "parallelism": "1 GPU" if world == 1 else "%d row strips, peer reads over NVLink (CUDA IPC), no collective on the data path" % world,
                    "l2": "per-frame working set %.0f MB > 126 MB L2 (no flush needed)" % (px * 196 / 1e6)},
-        "mpixels_per_sec": fps_dev * px / 1e6,
-        "e2e": {"value": fps_e2e, "unit": "frames/sec", "h2d_bytes_per_step": 84 + 80, "d2h_bytes_per_step": px * 12,
-                "ms_per_step": ms_e2e / args.steps, "mpixels_per_sec": fps_e2e * px / 1e6},
-        "gpu_launches": launches_per_frame * args.steps * 2,
+        "e2e": {"value": fps_e2e * px / 1e6, "unit": "Mpixels/sec", "fps": fps_e2e, "h2d_bytes_per_step": (84 + 80) * world,
+                "d2h_bytes_per_step": px * 12, "ms_per_step": ms_e2e / args.steps,
+                "note": "every rank copies its own strip of the image to its host buffer each frame" if world > 1 else "whole image to host each frame"},
+        "gpu_launches": launches_per_frame * args.steps * 2 * world,
         "roofline": {"bound": "hbm", "kernel": "atrous level (all %d levels)" % nl, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "per_level_us": [t * 1e3 for t in lv_ms], "per_level_gbs": lv_gbs, "per_level_frac": [g / peak for g in lv_gbs],
@@ -256,7 +263,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = WORKLOADS[args.workload or "c2"]
+    wl = WORKLOADS[args.workload or ("c2" if args.gpus == 1 else "c4")]
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
     else:

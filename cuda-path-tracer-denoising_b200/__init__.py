@@ -81,7 +81,8 @@ class Shard(ctypes.Structure):
 # every symbol include/svgf_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = ["svgf_params_default", "svgf_create", "svgf_destroy", "svgf_reset", "svgf_render", "svgf_denoise", "svgf_sync",
            "svgf_denoise_host", "svgf_atrous_host", "svgf_fetch", "svgf_last_error", "svgf_abi_version", "svgf_stage_times",
-           "svgf_set_profiling", "svgf_stream", "svgf_set_shard", "svgf_camera_init", "svgf_camera_step"]
+           "svgf_set_profiling", "svgf_stream", "svgf_set_shard", "svgf_ipc_handles_size", "svgf_ipc_export",
+           "svgf_ipc_connect", "svgf_peer_connect_local", "svgf_peer_error", "svgf_camera_init", "svgf_camera_step"]
 
 _lib = None
 
@@ -116,6 +117,10 @@ def lib():
         L.svgf_stream.argtypes = [vp]
         L.svgf_stream.restype = vp
         L.svgf_set_shard.argtypes = [vp, ctypes.POINTER(Shard)]
+        L.svgf_ipc_export.argtypes = [vp, vp]
+        L.svgf_ipc_connect.argtypes = [vp, ci, ci, vp, vp]
+        L.svgf_peer_connect_local.argtypes = [vp, ci, vp]
+        L.svgf_peer_error.argtypes = [vp]
         L.svgf_camera_init.argtypes = [ctypes.POINTER(Camera), ctypes.POINTER(CameraRig), vp, vp, vp, cf, ci, ci]
         L.svgf_camera_init.restype = None
         L.svgf_camera_step.argtypes = [ctypes.POINTER(Camera), ctypes.POINTER(CameraRig), ci, vp]
@@ -191,6 +196,20 @@ class Renderer:
     def set_shard(self, rank, world, row_begin, row_end):
         s = Shard(rank, world, row_begin, row_end)
         self._ck(lib().svgf_set_shard(self.h, ctypes.byref(s)), "svgf_set_shard")
+
+    def ipc_export(self):
+        """This rank's IPC handles (bytes) for svgf_ipc_connect on the other ranks."""
+        buf = np.zeros(lib().svgf_ipc_handles_size(), np.uint8)
+        self._ck(lib().svgf_ipc_export(self.h, buf.ctypes.data), "svgf_ipc_export")
+        return buf
+
+    def ipc_connect(self, rank, world, all_handles, row_starts):
+        a = np.ascontiguousarray(all_handles, np.uint8); rs = np.ascontiguousarray(row_starts, np.int32)
+        assert a.size == world * lib().svgf_ipc_handles_size() and rs.size == world + 1
+        self._ck(lib().svgf_ipc_connect(self.h, rank, world, a.ctypes.data, rs.ctypes.data), "svgf_ipc_connect")
+
+    def peer_error(self):
+        return lib().svgf_peer_error(self.h)
 
     def set_profiling(self, on):
         self._ck(lib().svgf_set_profiling(self.h, int(on)), "svgf_set_profiling")
@@ -287,6 +306,21 @@ class SceneBlob:
         return CameraDriver(lc.position[:], lc.lookAt[:], lc.up[:], self.fovy, W, H, automate, speeds)
 
 
+def row_partition(H, world):
+    """Row strips [start[r], start[r+1]) of a frame of H rows over `world` ranks."""
+    return [r * H // world for r in range(world)] + [H]
+
+
+def connect_local(renderers, row_starts=None):
+    """Wire several Renderers living in this process as the ranks of one sharded frame (svgf_peer_connect_local)."""
+    world = len(renderers)
+    rs = np.ascontiguousarray(row_starts if row_starts is not None else row_partition(renderers[0].H, world), np.int32)
+    arr = (ctypes.c_void_p * world)(*[r.h for r in renderers])
+    rc = lib().svgf_peer_connect_local(arr, world, rs.ctypes.data)
+    if rc != SVGF_OK:
+        raise SvgfError("svgf_peer_connect_local -> %d" % rc)
+
+
 def scene_path(name):
     if os.path.exists(name):
         return name
@@ -297,3 +331,24 @@ def open_scene(name, W, H, device=0):
     """Convenience: blob -> (SceneBlob, Renderer)."""
     blob = SceneBlob(scene_path(name))
     return blob, Renderer(blob.desc(W, H), W, H, device)
+
+
+def gather_handles(local_handles, dist, world):
+    """All-gather every rank's IPC handle bytes in rank order over torch.distributed (any backend): the plumbing step
+    between svgf_ipc_export and svgf_ipc_connect. Returns a (world * n,) uint8 numpy array."""
+    import torch
+    mine = torch.from_numpy(np.ascontiguousarray(local_handles, np.uint8).copy())
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = mine.to(dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return torch.cat(out).cpu().numpy()
+
+
+def connect_ranks(renderer, dist, rank, world):
+    """Shard `renderer`'s frame over the ranks of an initialised torch.distributed group (one process per GPU)."""
+    rs = row_partition(renderer.H, world)
+    allh = gather_handles(renderer.ipc_export(), dist, world)
+    renderer.ipc_connect(rank, world, allh, rs)
+    dist.barrier()
+    return rs

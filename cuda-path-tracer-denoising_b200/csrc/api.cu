@@ -122,6 +122,26 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
     return SVGF_OK;
 }
 
+// The planes another rank may read, in the fixed order used for IPC export (SVGF_IPC_NBUF entries).
+static void shared_bufs(svgf_ctx *c, void **o) {
+    int n = 0;
+    for (int i = 0; i < 3; i++) o[n++] = c->cv[i];
+    for (int i = 0; i < 3; i++) o[n++] = c->lum[i];
+    for (int i = 0; i < 2; i++) o[n++] = c->nrm[i];
+    for (int i = 0; i < 2; i++) o[n++] = c->mom[i];
+    for (int i = 0; i < 2; i++) o[n++] = c->hlen[i];
+    o[n++] = c->gnp; o[n++] = c->gzl; o[n++] = c->flags;
+}
+static void set_peer(svgf_ctx *c, int r, void *const *b) {
+    int n = 0;
+    for (int i = 0; i < 3; i++) c->p_cv[i].p[r] = (float4 *)b[n++];
+    for (int i = 0; i < 3; i++) c->p_lum[i].p[r] = (float *)b[n++];
+    for (int i = 0; i < 2; i++) c->p_nrm[i].p[r] = (float4 *)b[n++];
+    for (int i = 0; i < 2; i++) c->p_mom[i].p[r] = (float2 *)b[n++];
+    for (int i = 0; i < 2; i++) c->p_hlen[i].p[r] = (int *)b[n++];
+    c->p_gnp.p[r] = (float4 *)b[n++]; c->p_gzl.p[r] = (float2 *)b[n++]; c->p_flags.p[r] = (unsigned *)b[n++];
+}
+
 static int alloc_frame_buffers(svgf_ctx *c) {
     const size_t px = c->px;
     for (int i = 0; i < 3; i++) { CK(dalloc(&c->cv[i], px)); CK(dalloc(&c->lum[i], px)); }
@@ -130,6 +150,13 @@ static int alloc_frame_buffers(svgf_ctx *c) {
     CK(dalloc(&c->image, 3 * px)); CK(dalloc(&c->denoised, 3 * px)); CK(dalloc(&c->var_out, px));
     CK(dalloc(&c->stale_nm, px)); CK(dalloc(&c->stale_uv, px)); CK(dalloc(&c->kl, px));
     CK(cudaMalloc((void **)&c->pbo_own, px * 8));
+    CK(cudaMalloc((void **)&c->flags, (SVGF_MAX_RANKS * SVGF_NUM_STAGES + 1) * sizeof(unsigned)));
+    CK(cudaMemset(c->flags, 0, (SVGF_MAX_RANKS * SVGF_NUM_STAGES + 1) * sizeof(unsigned)));
+    {   // until peers are connected every table entry is this context's own plane
+        void *own[SVGF_IPC_NBUF]; shared_bufs(c, own);
+        for (int r = 0; r < SVGF_MAX_RANKS; r++) set_peer(c, r, own);
+        c->rows.world = 1; c->rows.start[0] = 0; for (int r = 1; r <= SVGF_MAX_RANKS; r++) c->rows.start[r] = c->H;
+    }
     CK(cudaMallocHost((void **)&c->pinned_image, px * 12));
     return SVGF_OK;
 }
@@ -188,7 +215,8 @@ int svgf_destroy(svgf_ctx *c) {
     for (int i = 0; i < 3; i++) { cudaFree(c->cv[i]); cudaFree(c->lum[i]); }
     for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }
     cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->gnp); cudaFree(c->gzl); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
-    cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl);
+    cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl); cudaFree(c->flags);
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->aos_in); cudaFree(c->aos_out); cudaFree(c->aos_g);
     if (c->pinned_image) cudaFreeHost(c->pinned_image);
     for (auto &pf : c->prof_pool) for (int i = 0; i < 12; i++) cudaEventDestroy(pf.ev[i]);
@@ -230,6 +258,80 @@ int svgf_set_shard(svgf_ctx *c, const svgf_shard *s) {
     }
     c->shard = *s;
     return SVGF_OK;
+}
+
+// ---- multi-GPU wiring: who owns which rows, and where every rank's planes are mapped ----
+static int set_rows(svgf_ctx *c, int rank, int world, const int *row_starts) {
+    if (world < 1 || world > SVGF_MAX_RANKS || rank < 0 || rank >= world || !row_starts || row_starts[0] != 0 || row_starts[world] != c->H) {
+        c->err = "invalid rank/world/row partition"; return SVGF_ERR_INVALID;
+    }
+    for (int r = 0; r < world; r++) if (row_starts[r] > row_starts[r + 1]) { c->err = "row partition not monotonic"; return SVGF_ERR_INVALID; }
+    c->rows.world = world;
+    for (int r = 0; r <= SVGF_MAX_RANKS; r++) c->rows.start[r] = r <= world ? row_starts[r] : c->H;
+    c->shard = svgf_shard{rank, world, row_starts[rank], row_starts[rank + 1]};
+    return SVGF_OK;
+}
+
+int svgf_ipc_handles_size(void) { return SVGF_IPC_NBUF * (int)sizeof(cudaIpcMemHandle_t); }
+
+int svgf_ipc_export(svgf_ctx *c, void *out) {
+    if (!c || !out) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    void *b[SVGF_IPC_NBUF]; shared_bufs(c, b);
+    cudaIpcMemHandle_t *h = static_cast<cudaIpcMemHandle_t *>(out);
+    for (int i = 0; i < SVGF_IPC_NBUF; i++) CK(cudaIpcGetMemHandle(&h[i], b[i]));
+    return SVGF_OK;
+}
+
+// all_handles: world x SVGF_IPC_NBUF handles in rank order (an all-gather of svgf_ipc_export); row_starts: world + 1 entries.
+int svgf_ipc_connect(svgf_ctx *c, int rank, int world, const void *all_handles, const int *row_starts) {
+    if (!c || !all_handles) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = set_rows(c, rank, world, row_starts);
+    if (rc) return rc;
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int r = 0; r < world; r++) {
+        void *b[SVGF_IPC_NBUF];
+        if (r == rank) shared_bufs(c, b);
+        else for (int i = 0; i < SVGF_IPC_NBUF; i++) {
+            cudaError_t e = cudaIpcOpenMemHandle(&b[i], h[r * SVGF_IPC_NBUF + i], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { c->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); return SVGF_ERR_COMM; }
+            c->ipc_opened.push_back(b[i]);
+        }
+        set_peer(c, r, b);
+    }
+    return SVGF_OK;
+}
+
+// Ranks living in ONE process (tests on a single GPU, or a single-process multi-GPU host): wire them directly.
+int svgf_peer_connect_local(svgf_ctx **ctxs, int world, const int *row_starts) {
+    if (!ctxs || world < 1 || world > SVGF_MAX_RANKS) return SVGF_ERR_INVALID;
+    for (int r = 0; r < world; r++) {
+        svgf_ctx *c = ctxs[r];
+        if (!c || c->W != ctxs[0]->W || c->H != ctxs[0]->H) return SVGF_ERR_INVALID;
+        int rc = set_rows(c, r, world, row_starts);
+        if (rc) return rc;
+        for (int q = 0; q < world; q++) {
+            if (ctxs[q]->device != c->device) {
+                cudaSetDevice(c->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { c->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return SVGF_ERR_COMM; }
+                (void)cudaGetLastError();
+            }
+            void *b[SVGF_IPC_NBUF]; shared_bufs(ctxs[q], b);
+            set_peer(c, q, b);
+        }
+    }
+    return SVGF_OK;
+}
+
+// 1 if a cross-rank wait timed out since the context was created (a peer stopped making progress).
+int svgf_peer_error(svgf_ctx *c) {
+    if (!c) return SVGF_ERR_INVALID;
+    unsigned v = 0;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(&v, c->flags + SVGF_MAX_RANKS * SVGF_NUM_STAGES, sizeof(v), cudaMemcpyDeviceToHost));
+    return (int)v;
 }
 
 enum { SVGF_PROF_MAX_FRAMES = 512 };
@@ -282,17 +384,17 @@ int svgf_sync(svgf_ctx *c) {
 // Inputs: c->image (1-spp colour), c->nrm[cur_nrm], c->pos, c->alb. Output: c->denoised, c->var_out.
 static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, const svgf_params *P, cudaEvent_t *ev) {
     const int acc_slot = (c->hist_cv + 1) % 3;          // any buffer that is not the current history
-    const float4 *hist = c->cv[c->hist_cv];
     float4 *acc = c->cv[acc_slot];
     const float color_alpha = P->temporal_enable ? P->color_alpha : 1.0f;
     const float moment_alpha = P->temporal_enable ? P->moment_alpha : 1.0f;
     if (P->temporal_enable) {
-        CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->nrm[c->cur_nrm ^ 1], c->pos, hist, c->mom[c->cur_mom],
-                           c->hlen[c->cur_hlen], acc, c->lum[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1], c->view_matrix_prev,
-                           color_alpha, moment_alpha, 1));
+        CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->p_nrm[c->cur_nrm ^ 1], c->pos, c->p_cv[c->hist_cv], c->p_mom[c->cur_mom],
+                           c->p_hlen[c->cur_hlen], acc, c->lum[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1],
+                           c->view_matrix_prev, color_alpha, moment_alpha));
     } else {
         CK(launch_no_temporal(c, image, acc, c->lum[acc_slot]));
     }
+    CK(launch_signal(c, SVGF_STAGE_TEMPORAL));
     if (ev) CK(cudaEventRecord(ev[2], c->stream));
     int new_hist = acc_slot;        // denoise.cu:366/370: colour history := accumulated (or input) colour
     if (P->right_view_option == 1) {
@@ -312,7 +414,11 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             // destination: any slot that is neither the source nor the (new) history
             int dst = -1;
             for (int s = 0; s < 3; s++) if (s != src && s != new_hist) { dst = s; break; }
+            // a level reads its input planes (and the G-buffer) of rows owned by other ranks in place: those ranks
+            // must have finished producing them, and must be done reading what this level overwrites (same condition)
+            CK(launch_wait(c, level == 1 ? SVGF_STAGE_TEMPORAL : SVGF_STAGE_LEVEL0 + level - 1, c->seq));
             AtrousArgs a;
+            a.src_slot = src;
             a.cv_in = c->cv[src];
             a.cv_out = (!last || is_hist) ? c->cv[dst] : nullptr;
             a.lum_in = c->lum[src]; a.lum_out = c->lum[dst];
@@ -321,6 +427,7 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             a.level = level; a.is_last = last; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
             a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;
             CK(launch_atrous(c, a));
+            CK(launch_signal(c, SVGF_STAGE_LEVEL0 + level));
             if (ev && level <= SVGF_MAX_LEVELS) CK(cudaEventRecord(ev[2 + level], c->stream));
             if (is_hist) new_hist = dst;     // denoise.cu:391: colour history := this level's output
             src = dst;
@@ -369,6 +476,9 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     CK(cudaSetDevice(c->device));
     cudaEvent_t *ev = prof_begin(c, P);
     if (ev) CK(cudaEventRecord(ev[0], c->stream));
+    c->seq++;
+    // before this frame overwrites planes that peers read in place, they must have finished the previous frame
+    if (c->seq > 1) CK(launch_wait(c, SVGF_STAGE_FRAME, c->seq - 1));
     RtParams rp;
     rp.W = c->W; rp.H = c->H; rp.row_begin = c->shard.row_begin; rp.row_end = c->shard.row_end;
     rp.frame = frame; rp.max_depth = P->tracedepth; rp.trace_shadowray = P->shadowray; rp.reduce_var = P->reducevar;
@@ -376,6 +486,7 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     atrous_scales(P->sigman, P->sigmax, &rp.kn, &rp.kx);
     rp.cam = *cam;
     CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm]));
+    CK(launch_signal(c, SVGF_STAGE_RT));
     if (ev) CK(cudaEventRecord(ev[1], c->stream));
     if (P->denoise_enable) {
         int rc = denoise_soa(c, c->image, cam, P, ev);
@@ -383,6 +494,7 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     } else {
         CK(launch_copy_f3(c, c->denoised, c->image));        // pathtrace.cu:440
     }
+    CK(launch_signal(c, SVGF_STAGE_FRAME));
     unsigned char *pbo = pbo_dev ? static_cast<unsigned char *>(pbo_dev) : c->pbo_own;
     CK(launch_pack_pbo(c, pbo, c->image, c->denoised));
     if (ev) CK(cudaEventRecord(ev[10], c->stream));
@@ -409,6 +521,7 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     if (!c || !output_dev || !input_dev || !gbuffer_dev || !cam || !P) return SVGF_ERR_INVALID;
     if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_denoise: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
     if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS) { c->err = "svgf_denoise: atrous_nlevel out of range"; return SVGF_ERR_INVALID; }
+    if (c->shard.world > 1) { c->err = "svgf_denoise: the AoS entry point is single-GPU; sharded frames go through svgf_render"; return SVGF_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
     cudaEvent_t *ev = prof_begin(c, P);
     if (ev) { CK(cudaEventRecord(ev[0], c->stream)); CK(cudaEventRecord(ev[1], c->stream)); }
@@ -464,6 +577,7 @@ extern "C" int svgf_atrous_host(svgf_ctx *c, float *color_out, float *variance_o
         CK(cudaStreamSynchronize(c->stream));
     }
     AtrousArgs a;
+    a.src_slot = 0;
     a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.lum_in = c->lum[0]; a.lum_out = c->lum[1]; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
     a.denoised_out = is_last ? c->denoised : nullptr; a.var_out = is_last ? c->var_out : nullptr;
     a.level = level; a.is_last = is_last != 0; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);

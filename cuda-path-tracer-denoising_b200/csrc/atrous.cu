@@ -147,6 +147,8 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
 
 struct AtrousT {
     AtrousK k;
+    RowOwner ro;                // multi-GPU: which rank owns a row, and that rank's base pointers
+    PeerPtr<const float4> p_cv; PeerPtr<const float> p_lum; PeerPtr<const float4> p_gnp; PeerPtr<const float2> p_gzl;
     int b_first;        // first lattice row index covered by the grid (row_begin / step)
     int ncg;            // column groups per class row: step / C
     const float *kl;    // per-pixel luminance-weight scale from atrous_kl_kernel
@@ -156,7 +158,7 @@ struct AtrousT {
 // (denoise.cu:100-118,143). The 3x3 Gaussian lives in PIXEL space, i.e. across residue classes, so it is done here where
 // it is coalesced instead of per lattice point inside the tiled kernel. 4 B read (L1-shared) + 4 B written per pixel.
 __global__ void __launch_bounds__(256)
-atrous_kl_kernel(const float4 *__restrict__ cv, float *__restrict__ kl, int W, int H, int row_begin, int row_end,
+atrous_kl_kernel(const PeerPtr<const float4> cv, const RowOwner ro, float *__restrict__ kl, int W, int H, int row_begin, int row_end,
                  int blur_variance, float sigma_c) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
@@ -171,13 +173,13 @@ atrous_kl_kernel(const float4 *__restrict__ cv, float *__restrict__ kl, int W, i
                 const int lx = x + dx, ly = y + dy;
                 if (lx >= 0 && ly >= 0 && lx < W && ly < H) {
                     const float g = (dx == 0 ? 0.5f : 0.25f) * (dy == 0 ? 0.5f : 0.25f);
-                    sum += g * __ldg(&cv[lx + ly * W].w);
+                    sum += g * __ldg(&cv.p[owner_of(ro, ly)][lx + ly * W].w);
                     sumw += g;
                 }
             }
         var = sum / sumw;
     } else {
-        var = __ldg(&cv[x + y * W].w);
+        var = __ldg(&cv.p[owner_of(ro, y)][x + y * W].w);
     }
     var = fmaxf(var, 0.0f);
     // fp32: the reference's fp64 add/divide here (denoise.cu:143) only has to be matched to ~1e-7 relative
@@ -252,12 +254,14 @@ atrous_tiled_kernel(AtrousT t) {
         const int c = n % AT_C, ta = (n / AT_C) % AT_SW, tb = n / (AT_C * AT_SW);
         const int x = X0 + (a0 + ta) * step + c, y = yc + (b0 + tb) * step;
         const int si = at_idx(c, tb, ta);
-        if (a0 + ta >= 0 && b0 + tb >= 0 && x < W && y < H) {
-            const int q = x + y * W;
-            cp_async16(&s_cv[si], &k.cv_in[q]);
-            cp_async16(&s_np[si], &k.gnp[q]);
-            cp_async8(&s_zl[si], &k.gzl[q]);
-            cp_async4(&s_zl[si].z, &k.lum_in[q]);
+        // only rows a live centre of this strip can reach (strip +- 2 steps): a tile of a coarse level spans far more
+        // rows than the strip, and for a sharded frame those rows would be fetched from a peer for nothing
+        if (a0 + ta >= 0 && b0 + tb >= 0 && x < W && y < H && y >= k.row_begin - 2 * step && y < k.row_end + 2 * step) {
+            const int q = x + y * W, o = owner_of(t.ro, y);     // rows of other strips come straight from their owner
+            cp_async16(&s_cv[si], &t.p_cv.p[o][q]);
+            cp_async16(&s_np[si], &t.p_gnp.p[o][q]);
+            cp_async8(&s_zl[si], &t.p_gzl.p[o][q]);
+            cp_async4(&s_zl[si].z, &t.p_lum.p[o][q]);
         } else {
             s_cv[si] = make_float4(0.f, 0.f, 0.f, 0.f); s_np[si] = make_float4(0.f, 0.f, 0.f, 0.f);
             s_zl[si] = make_float4(0.f, 0.f, 3e38f, 0.f);
@@ -374,7 +378,7 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     k.is_last = a.is_last; k.blur_variance = a.blur_variance; k.addcolor = a.addcolor;
     k.sigma_c = a.sigma_c;
     atrous_scales(a.sigma_n, a.sigma_x, &k.kn, &k.kx);
-    if (c->atrous_variant == 1) {
+    if (c->atrous_variant == 1 && c->shard.world == 1) {
         dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
         atrous_direct_kernel<<<g, b, 0, c->stream>>>(k);
         return cudaGetLastError();
@@ -386,10 +390,15 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
         attr_set = true;
     }
     AtrousT t;
-    t.k = k; t.kl = c->kl;
+    t.k = k; t.kl = c->kl; t.ro = c->rows;
+    for (int r = 0; r < SVGF_MAX_RANKS; r++) {
+        const bool peer = r < c->shard.world && a.src_slot >= 0;
+        t.p_cv.p[r] = peer ? c->p_cv[a.src_slot].p[r] : a.cv_in; t.p_lum.p[r] = peer ? c->p_lum[a.src_slot].p[r] : a.lum_in;
+        t.p_gnp.p[r] = peer ? c->p_gnp.p[r] : a.gnp; t.p_gzl.p[r] = peer ? c->p_gzl.p[r] : a.gzl;
+    }
     {
         dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
-        atrous_kl_kernel<<<g, b, 0, c->stream>>>(k.cv_in, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c);
+        atrous_kl_kernel<<<g, b, 0, c->stream>>>(t.p_cv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c);
     }
     const int step = k.step;
     t.b_first = k.row_begin / step;

@@ -21,11 +21,11 @@ __device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, f
 // isReprjValid, denoise.cu:172-182, for a tap at float coordinates (px, py) of the previous frame.
 // Returns the linear index of the tap through `q`.
 __device__ __forceinline__ bool reprj_valid(int W, int H, float px, float py, const float4 &ncur,
-                                            const float4 *__restrict__ nrm_prev, int &q) {
+                                            const PeerPtr<float4> &nrm_prev, const RowOwner &ro, int &q) {
     // NaN coordinates pass the reference's bounds test and index garbage (undefined); rejected here.
     if (!(px >= 0.f) || !(px < (float)W) || !(py >= 0.f) || !(py < (float)H)) return false;
     q = (int)(px + py * (float)W);
-    const float4 np = __ldg(&nrm_prev[q]);
+    const float4 np = __ldg(&nrm_prev.p[owner_of(ro, q / W)][q]);
     const int gprev = __float_as_int(np.w), gcur = __float_as_int(ncur.w);
     if (gprev == -1 || gprev != gcur) return false;
     if (dist3(np.x, np.y, np.z, ncur.x, ncur.y, ncur.z) > 1e-1f) return false;
@@ -39,15 +39,15 @@ struct Mat4 { float m[16]; };
 // writes {colour,variance} 16 + moments 8 + history length 4.
 __global__ void __launch_bounds__(256)
 temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
-                const float4 *__restrict__ nrm_cur, const float4 *__restrict__ nrm_prev, const float4 *__restrict__ pos,
-                const float4 *__restrict__ hist_cv, const float2 *__restrict__ mom_hist, const int *__restrict__ hlen_in,
+                const float4 *__restrict__ nrm_cur, const PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
+                const PeerPtr<float4> hist_cv, const PeerPtr<float2> mom_hist, const PeerPtr<int> hlen_tab, const RowOwner ro, int me,
                 float4 *__restrict__ acc_cv, float *__restrict__ acc_lum, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
                 float color_alpha_min, float moment_alpha_min) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= row_end) return;
     const int p = x + y * W;
-    const int N = hlen_in[p];
+    const int N = hlen_tab.p[me][p];     // own pixel (denoise.cu:194)
     const float sr = image[3 * (size_t)p], sg = image[3 * (size_t)p + 1], sb = image[3 * (size_t)p + 2];
     const float luminance = 0.2126 * sr + 0.7152 * sg + 0.0722 * sb;    // double, as denoise.cu:196
     const float4 ncur = nrm_cur[p];
@@ -70,7 +70,7 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
         for (int s = 0; s < 4; s++) {
             const int lx = (int)((unsigned)ifx + (unsigned)(s & 1)), ly = (int)((unsigned)ify + (unsigned)(s >> 1));
             qi[s] = 0;
-            v[s] = reprj_valid(W, H, (float)lx, (float)ly, ncur, nrm_prev, qi[s]);
+            v[s] = reprj_valid(W, H, (float)lx, (float)ly, ncur, nrm_prev, ro, qi[s]);
             qi[s] = lx + ly * W;
             valid = valid && v[s];
         }
@@ -81,10 +81,11 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 if (v[s]) {
-                    const float4 hc = __ldg(&hist_cv[qi[s]]); const float2 hm = __ldg(&mom_hist[qi[s]]);
+                    const int o = owner_of(ro, qi[s] / W);
+                    const float4 hc = __ldg(&hist_cv.p[o][qi[s]]); const float2 hm = __ldg(&mom_hist.p[o][qi[s]]);
                     pr += w[s] * hc.x; pg += w[s] * hc.y; pb += w[s] * hc.z;
                     pm1 += w[s] * hm.x; pm2 += w[s] * hm.y;
-                    phl += w[s] * (float)__ldg(&hlen_in[qi[s]]);
+                    phl += w[s] * (float)__ldg(&hlen_tab.p[o][qi[s]]);
                     sumw += w[s];
                 }
             }
@@ -99,11 +100,12 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
                 for (int xx = -1; xx <= 1; xx++) {
                     const float lx = floorx + (float)xx, ly = floory + (float)yy;
                     int q = 0;
-                    if (reprj_valid(W, H, lx, ly, ncur, nrm_prev, q)) {
+                    if (reprj_valid(W, H, lx, ly, ncur, nrm_prev, ro, q)) {
                         q = (int)(lx + (float)W * ly);
-                        const float4 hc = __ldg(&hist_cv[q]); const float2 hm = __ldg(&mom_hist[q]);
+                        const int o = owner_of(ro, q / W);
+                        const float4 hc = __ldg(&hist_cv.p[o][q]); const float2 hm = __ldg(&mom_hist.p[o][q]);
                         pr += hc.x; pg += hc.y; pb += hc.z; pm1 += hm.x; pm2 += hm.y;
-                        phl += (float)__ldg(&hlen_in[q]);
+                        phl += (float)__ldg(&hlen_tab.p[o][q]);
                         cnt += 1.0f;
                     }
                 }
@@ -219,20 +221,43 @@ copy_f3_kernel(size_t begin, size_t end, float *__restrict__ dst, const float *_
     if (i < end) dst[i] = src[i];
 }
 
+// ---- cross-rank ordering: sequence flags pushed into every peer's memory, polled locally ----
+__global__ void signal_kernel(PeerPtr<unsigned> flags, int world, int me, int stage, unsigned seq) {
+    const int j = threadIdx.x;
+    if (j >= world) return;
+    __threadfence_system();
+    volatile unsigned *f = flags.p[j] + me * SVGF_NUM_STAGES + stage;
+    *f = seq;
+}
+__global__ void wait_kernel(unsigned *flags, int world, int stage, unsigned seq) {
+    const int j = threadIdx.x;
+    if (j >= world) return;
+    volatile unsigned *f = flags + j * SVGF_NUM_STAGES + stage;
+    const long long t0 = clock64();
+    while ((int)(*f - seq) < 0) {
+        if (clock64() - t0 > 4000000000LL) {        // ~2 s: a peer died; record it instead of hanging the GPU
+            flags[SVGF_MAX_RANKS * SVGF_NUM_STAGES] = 1u;
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (rows + b.y - 1) / b.y); }
 
 }  // namespace
 
-cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const float4 *nrm_prev,
-                            const float4 *pos, const float4 *hist_cv, const float2 *mom_hist, const int *hlen_in,
-                            float4 *acc_cv, float *acc_lum, float2 *mom_acc, int *hlen_out, const float *prev_viewmat,
-                            float color_alpha, float moment_alpha, int) {
+cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const PeerPtr<float4> &nrm_prev,
+                            const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
+                            const PeerPtr<int> &hlen_in, float4 *acc_cv, float *acc_lum, float2 *mom_acc, int *hlen_out,
+                            const float *prev_viewmat, float color_alpha, float moment_alpha) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     Mat4 vm; for (int i = 0; i < 16; i++) vm.m[i] = prev_viewmat[i];
     dim3 b(32, 8);
     temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
-                                                                 nrm_prev, pos, hist_cv, mom_hist, hlen_in, acc_cv, acc_lum, mom_acc,
+                                                                 nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lum, mom_acc,
                                                                  hlen_out, vm, color_alpha, moment_alpha);
     return cudaGetLastError();
 }
@@ -251,6 +276,17 @@ cudaError_t launch_pack_pbo(svgf_ctx *c, unsigned char *pbo, const float *left, 
     dim3 b(32, 8);
     pack_pbo_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->shard.row_begin, c->shard.row_end,
                                                                  reinterpret_cast<uchar4 *>(pbo), left, right);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_signal(svgf_ctx *c, int stage) {
+    if (c->shard.world <= 1) return cudaSuccess;
+    signal_kernel<<<1, 32, 0, c->stream>>>(c->p_flags, c->shard.world, c->shard.rank, stage, c->seq);
+    return cudaGetLastError();
+}
+cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq) {
+    if (c->shard.world <= 1) return cudaSuccess;
+    wait_kernel<<<1, 32, 0, c->stream>>>(c->flags, c->shard.world, stage, seq);
     return cudaGetLastError();
 }
 

@@ -45,7 +45,25 @@ struct DeviceScene {
     std::vector<unsigned char *> tex_pixels;
 };
 
-enum { SVGF_MAX_LEVELS = 7 };
+enum { SVGF_MAX_LEVELS = 7, SVGF_MAX_RANKS = 8 };
+
+// ---- multi-GPU: a frame is sharded by row strips, one process per GPU. Every rank allocates full-frame planes and
+// owns the rows of its strip; rows of other strips are read IN PLACE from the owner's memory over NVLink (CUDA IPC
+// mappings), so there is no halo copy and no collective on the data path: the a-trous tile loader and the temporal
+// reprojection simply pick the owner's base pointer for each row they touch. Ordering between ranks is a per-stage
+// sequence flag pushed into every peer's memory (signal kernel) and polled locally (wait kernel). ----
+struct RowOwner {               // rows [start[r], start[r+1]) belong to rank r
+    int world;
+    int start[SVGF_MAX_RANKS + 1];
+};
+template <typename T> struct PeerPtr { T *p[SVGF_MAX_RANKS]; };
+__host__ __device__ inline int owner_of(const RowOwner &ro, int y) {
+    int r = 0;
+    for (int i = 1; i < ro.world; i++) r += (y >= ro.start[i]);
+    return r;
+}
+enum { SVGF_STAGE_RT = 0, SVGF_STAGE_TEMPORAL = 1, SVGF_STAGE_LEVEL0 = 1 /* + level */, SVGF_STAGE_FRAME = 9, SVGF_NUM_STAGES = 10 };
+enum { SVGF_IPC_NBUF = 15 };    // cv[3] lum[3] nrm[2] mom[2] hlen[2] gnp gzl flags
 
 struct svgf_ctx {
     int device = 0;
@@ -56,6 +74,13 @@ struct svgf_ctx {
 
     // shard (rows [row_begin,row_end) of the frame); world==1: whole frame
     svgf_shard shard{0, 1, 0, 0};
+    RowOwner rows{1, {0}};
+    // peer views of every plane another rank may read (index [rank]; [shard.rank] is this context's own pointer)
+    PeerPtr<float4> p_cv[3]; PeerPtr<float> p_lum[3]; PeerPtr<float4> p_nrm[2]; PeerPtr<float2> p_mom[2]; PeerPtr<int> p_hlen[2];
+    PeerPtr<float4> p_gnp; PeerPtr<float2> p_gzl; PeerPtr<unsigned> p_flags;
+    unsigned *flags = nullptr;          // [SVGF_MAX_RANKS][SVGF_NUM_STAGES] sequence numbers written by the peers, + 1 error word
+    unsigned seq = 0;                   // frame sequence number (identical on all ranks)
+    std::vector<void *> ipc_opened;
 
     float4 *cv[3] = {nullptr, nullptr, nullptr};
     float *lum[3] = {nullptr, nullptr, nullptr};    // luminance of cv[i].rgb, the reference's fp64 formula (denoise.cu:121)
@@ -118,12 +143,15 @@ struct RtParams {
 };
 void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx);
 cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out);
-cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const float4 *nrm_prev,
-                            const float4 *pos, const float4 *hist_cv, const float2 *mom_hist, const int *hlen_in,
-                            float4 *acc_cv, float *acc_lum, float2 *mom_acc, int *hlen_out, const float *prev_viewmat,
-                            float color_alpha, float moment_alpha, int has_history);
+cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const PeerPtr<float4> &nrm_prev,
+                            const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
+                            const PeerPtr<int> &hlen_in, float4 *acc_cv, float *acc_lum, float2 *mom_acc, int *hlen_out,
+                            const float *prev_viewmat, float color_alpha, float moment_alpha);
+cudaError_t launch_signal(svgf_ctx *c, int stage);
+cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq);
 cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float *acc_lum);
 struct AtrousArgs {
+    int src_slot;                                   // cv/lum input = c->p_cv[src_slot] / c->p_lum[src_slot] (peer-readable)
     const float4 *cv_in; float4 *cv_out;            // cv_out may be null on the last level
     const float *lum_in; float *lum_out;
     const float4 *nrm, *pos, *alb;

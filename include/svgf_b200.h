@@ -197,7 +197,22 @@ int svgf_stage_times(svgf_ctx *ctx, float *ms11);
  * own events. */
 void *svgf_stream(svgf_ctx *ctx);
 
-/* ---- multi-GPU (one process per GPU) ------------------------------------------------------------------- */
+/* ---- multi-GPU: a frame sharded by row strips, one process (context) per GPU -------------------------------- */
+/* Every rank holds full-frame planes and renders rows [row_starts[rank], row_starts[rank+1]); rows owned by other
+ * ranks are read in place from the owner's memory over NVLink (CUDA IPC), ordered by per-stage flags -- no halo copy,
+ * no collective on the data path. All ranks must call svgf_reset/svgf_render in lock-step with identical arguments.
+ *   1. every rank:  svgf_ipc_export(ctx, my_handles)          (svgf_ipc_handles_size() bytes)
+ *   2. all-gather the handles in rank order (torch.distributed / MPI / any byte transport)
+ *   3. every rank:  svgf_ipc_connect(ctx, rank, world, all_handles, row_starts)   (row_starts: world + 1 ints, 0 .. H)
+ * The reference has no multi-GPU path; this is new. */
+int svgf_ipc_handles_size(void);
+int svgf_ipc_export(svgf_ctx *ctx, void *handles_out);
+int svgf_ipc_connect(svgf_ctx *ctx, int rank, int world, const void *all_handles, const int *row_starts);
+/* Ranks that live in one process (several contexts on one or more GPUs): wire them without IPC. */
+int svgf_peer_connect_local(svgf_ctx **ctxs, int world, const int *row_starts);
+/* 1 if a cross-rank wait gave up (a peer stopped making progress), else 0. */
+int svgf_peer_error(svgf_ctx *ctx);
+/* Restrict a lone context to a row strip (no peers: taps outside the strip read this context's own planes). */
 int svgf_set_shard(svgf_ctx *ctx, const svgf_shard *shard);
 
 /* ---- camera control: the host logic either side of the path (main.cpp:77-101, 154-190) ------------------ */
