@@ -485,6 +485,7 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     rp.denoise = P->denoise_enable; rp.sepcolor = P->sepcolor; rp.sintensity = P->sintensity; rp.lightradius = P->lightradius;
     atrous_scales(P->sigman, P->sigmax, &rp.kn, &rp.kx);
     rp.cam = *cam;
+    c->gbuf_nrm = c->cur_nrm;            // where this frame's normals/geomIds live (svgf_fetch("gbuffer"))
     CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm]));
     CK(launch_signal(c, SVGF_STAGE_RT));
     if (ev) CK(cudaEventRecord(ev[1], c->stream));
@@ -527,6 +528,7 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     if (ev) { CK(cudaEventRecord(ev[0], c->stream)); CK(cudaEventRecord(ev[1], c->stream)); }
     float kn, kx;
     atrous_scales(P->sigman, P->sigmax, &kn, &kx);
+    c->gbuf_nrm = c->cur_nrm;
     CK(launch_aos_to_soa(c, gbuffer_dev, c->nrm[c->cur_nrm], c->pos, c->alb, kn, kx));
     int rc = denoise_soa(c, input_dev, cam, P, ev);
     if (rc != SVGF_OK) return rc;
@@ -625,8 +627,7 @@ extern "C" int svgf_fetch(svgf_ctx *c, const char *name, void *host, size_t byte
         return !strcmp(name, "color_history") ? d2h(c->aos_out, px * 12) : d2h(c->aos_g, px * 4);
     }
     if (!strcmp(name, "gbuffer") || !strcmp(name, "gbuffer_prev")) {
-        // the frame's G-buffer; after the rotation its normals sit in the "previous" slot
-        CK(launch_soa_to_aos(c, c->nrm[c->cur_nrm ^ 1], c->pos, c->alb, c->aos_g));
+        CK(launch_soa_to_aos(c, c->nrm[c->gbuf_nrm], c->pos, c->alb, c->aos_g));
         CK(cudaStreamSynchronize(c->stream));
         return d2h(c->aos_g, px * sizeof(svgf_gbuffer_texel));
     }

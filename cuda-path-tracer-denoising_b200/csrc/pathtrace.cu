@@ -58,7 +58,7 @@ struct Ray { F3 origin, direction; };
 // interactions.h:10-30
 __device__ __forceinline__ unsigned int initRand(unsigned int val0, unsigned int val1) {
     unsigned int v0 = val0, v1 = val1, s0 = 0;
-#pragma unroll
+#pragma unroll 4
     for (unsigned int n = 0; n < 16; n++) {
         s0 += 0x9e3779b9;
         v0 += ((v1 << 4) + 0xa341316c) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4);
@@ -341,10 +341,18 @@ __device__ void scatterRay(PathState &ps, F3 intersect, F3 normal, const svgf_ma
     }
 }
 
-// One thread per pixel. Block = 8x16 pixel tile so a warp covers an 8x4 patch (coherent primary rays).
+// One thread per pixel, block = 8x16 pixel tile (a warp covers an 8x4 patch: coherent primary rays).
+//
+// The reference's rt kernel inlines its closest-hit routine three times (primary, shadow, bounce: pathtrace.cu:314,370,390);
+// compiled that way the kernel is ~80 KB of SASS and spends half its time waiting for instruction fetches, because the
+// lanes of a warp sit in different copies. Here the path is a small state machine around ONE closest-hit call site:
+// every trip of the loop intersects "the current ray" -- the path ray or the shadow ray -- so lanes that are in
+// different phases of their path still execute the same intersection code together, and the whole kernel fits the
+// instruction cache. Per-pixel results are unchanged: the RNG is re-seeded from (pixel, frame + depth) at every depth.
 constexpr int RT_BX = 8, RT_BY = 16;
+enum { Q_PATH = 0, Q_SHADOW = 1 };
 
-__global__ void __launch_bounds__(RT_BX *RT_BY)
+__global__ void __launch_bounds__(RT_BX *RT_BY, 4)
 rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf_material *__restrict__ g_materials,
           int n_materials, const float4 *__restrict__ bvh, int n_nodes, const float4 *__restrict__ tri_hot,
           const float4 *__restrict__ tri_cold, const TexD *__restrict__ textures,
@@ -382,58 +390,76 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
         - mk(cam.up[0], cam.up[1], cam.up[2]) * cam.pixelLength[1] * ((float)y - (float)(P.H * 0.5f - 0.5f)));
     seg.diffuse = false;
 
-    Isect is;
-    bool any_hit = false;
-    bool hit = computeIntersection(sc, seg.ray, is);
-    if (!hit) {     // stale record from earlier frames (pathtrace.cu:85,119-120,316-322)
-        const float4 s = stale_nm[idx]; const float2 suv = stale_uv[idx];
-        is.n = mk(s.x, s.y, s.z); is.materialId = __float_as_int(s.w); is.u = suv.x; is.v = suv.y;
-    } else any_hit = true;
-    {
-        const svgf_material &material = sc.materials[is.materialId];
-        const F3 p = seg.ray.origin + is.t * seg.ray.direction;
-        const F3 a = materialAlbedo(sc, material, is.u, is.v);
-        nrm_out[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.geomId));
-        pos_out[idx] = make_float4(p.x, p.y, p.z, 0.f);
-        alb_out[idx] = make_float4(a.x, a.y, a.z, 0.f);
-        gnp_out[idx] = make_float4(is.n.x * P.kn, p.x * P.kx, is.n.y * P.kn, p.y * P.kx);
-        gzl_out[idx] = make_float2(is.n.z * P.kn, p.z * P.kx);
-    }
+    Isect is;               // the persistent per-pixel ShadeableIntersection (pathtrace.cu:85,310)
+    is.t = 0.f; is.n = mk(0, 0, 0); is.materialId = 0; is.geomId = 0; is.u = is.v = 0.f;
+    bool any_hit = false, stale_loaded = false;
     F3 acc = mk(0, 0, 0);
-    for (int depth = 1; depth <= P.max_depth; depth++) {
-        if (!hit) break;
-        unsigned int seed = initRand(idx, P.frame + depth);
-        const svgf_material &material = sc.materials[is.materialId];
-        if (material.emittance > 0.0f) {
-            if (!P.trace_shadowray || !P.reduce_var || !seg.diffuse)
-                acc = acc + seg.color * mk(material.color[0], material.color[1], material.color[2]) * material.emittance;
-            break;
-        }
-        const F3 ipos = seg.ray.origin + is.t * seg.ray.direction;
-        const F3 inrm = is.n;
-        const bool materialIsDiffuse = material.hasReflective < 1e-6 && material.hasRefractive < 1e-6;
-        if (!(P.denoise && P.sepcolor) || depth > 1) seg.color = seg.color * materialAlbedo(sc, material, is.u, is.v);
-        if (P.trace_shadowray && materialIsDiffuse) {
-            const GeomD &light = sc.geoms[0];
-            const F3 lpos = mk(light.translation[0], light.translation[1], light.translation[2]);
-            Ray sr; float expectDist = 0.0f;
-            computeShadowRay(sr, ipos + 1e-4f * inrm, lpos, P.lightradius, expectDist, seed);
-            Isect sh; sh.geomId = -2; sh.materialId = 0;
-            computeIntersection(sc, sr, sh);
-            if (sh.geomId == 0) {
-                const svgf_material &sm = sc.materials[sh.materialId];
+    int depth = 0;          // 0: the primary query is in flight
+    int kind = Q_PATH;
+    Ray cur = seg.ray;
+    // shading context carried across a shadow query (pathtrace.cu:358-392 uses them after the shadow test)
+    unsigned int seed = 0; F3 ipos = mk(0, 0, 0), inrm = mk(0, 0, 0); float expectDist = 0.f;
+
+    while (true) {
+        Isect res; res.geomId = -2; res.materialId = 0; res.t = 0.f; res.n = mk(0, 0, 0); res.u = res.v = 0.f;
+        const bool hit = computeIntersection(sc, cur, res);      // <- the only closest-hit call site
+        if (kind == Q_SHADOW) {
+            if (res.geomId == 0) {                               // pathtrace.cu:374-384 (lightIdx == 0)
+                const svgf_material &sm = sc.materials[res.materialId];
                 if (sm.emittance > 0.0f) {
-                    float diffuse = gmax(0.0f, dot(sr.direction, inrm));
-                    float shadowIntensity = P.sintensity / powf(expectDist, 2.0f);
+                    const float diffuse = gmax(0.0f, dot(cur.direction, inrm));
+                    const float shadowIntensity = P.sintensity / powf(expectDist, 2.0f);
                     acc = acc + seg.color * sm.emittance * mk(sm.color[0], sm.color[1], sm.color[2]) * shadowIntensity * diffuse;
                 }
             }
+        } else {
+            // the path ray's result lands in the persistent record; a miss only touches t and geomId (pathtrace.cu:267-271)
+            if (hit) { is = res; any_hit = true; }
+            else {
+                is.t = -1.0f; is.geomId = -1;
+                if (depth == 0 && !stale_loaded) {               // stale record of earlier frames (pathtrace.cu:119-120,316-322)
+                    const float4 s4 = stale_nm[idx]; const float2 suv = stale_uv[idx];
+                    is.n = mk(s4.x, s4.y, s4.z); is.materialId = __float_as_int(s4.w); is.u = suv.x; is.v = suv.y;
+                    stale_loaded = true;
+                }
+            }
+            if (depth == 0) {                                    // G-buffer from the primary hit, pathtrace.cu:316-323
+                const svgf_material &material = sc.materials[is.materialId];
+                const F3 p = seg.ray.origin + is.t * seg.ray.direction;
+                const F3 a = materialAlbedo(sc, material, is.u, is.v);
+                nrm_out[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.geomId));
+                pos_out[idx] = make_float4(p.x, p.y, p.z, 0.f);
+                alb_out[idx] = make_float4(a.x, a.y, a.z, 0.f);
+                gnp_out[idx] = make_float4(is.n.x * P.kn, p.x * P.kx, is.n.y * P.kn, p.y * P.kx);
+                gzl_out[idx] = make_float2(is.n.z * P.kn, p.z * P.kx);
+            }
+            depth++;
+            // ---- top of the reference's bounce loop for `depth` (pathtrace.cu:325-356) ----
+            if (depth > P.max_depth || !hit) break;
+            seed = initRand(idx, P.frame + depth);
+            const svgf_material &material = sc.materials[is.materialId];
+            if (material.emittance > 0.0f) {
+                if (!P.trace_shadowray || !P.reduce_var || !seg.diffuse)
+                    acc = acc + seg.color * mk(material.color[0], material.color[1], material.color[2]) * material.emittance;
+                break;
+            }
+            ipos = seg.ray.origin + is.t * seg.ray.direction;
+            inrm = is.n;
+            const bool materialIsDiffuse = material.hasReflective < 1e-6 && material.hasRefractive < 1e-6;
+            if (!(P.denoise && P.sepcolor) || depth > 1) seg.color = seg.color * materialAlbedo(sc, material, is.u, is.v);
+            if (P.trace_shadowray && materialIsDiffuse) {        // pathtrace.cu:358-371
+                const GeomD &light = sc.geoms[0];
+                computeShadowRay(cur, ipos + 1e-4f * inrm, mk(light.translation[0], light.translation[1], light.translation[2]),
+                                 P.lightradius, expectDist, seed);
+                kind = Q_SHADOW;
+                continue;
+            }
         }
-        if (depth < P.max_depth) {
-            scatterRay(seg, ipos, inrm, material, seed);
-            hit = computeIntersection(sc, seg.ray, is);
-            any_hit |= hit;
-        }
+        // ---- bounce (pathtrace.cu:387-392) ----
+        if (depth >= P.max_depth) break;
+        scatterRay(seg, ipos, inrm, sc.materials[is.materialId], seed);
+        cur = seg.ray;
+        kind = Q_PATH;
     }
     float *img = image + 3 * (size_t)idx;
     if (P.denoise) { img[0] = acc.x; img[1] = acc.y; img[2] = acc.z; }

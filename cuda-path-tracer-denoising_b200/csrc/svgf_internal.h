@@ -87,7 +87,7 @@ struct svgf_ctx {
     int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled
     int hist_cv = -1;                   // which cv[] holds the colour history for the next frame (-1: none yet)
     float4 *nrm[2] = {nullptr, nullptr};
-    int cur_nrm = 0;
+    int cur_nrm = 0, gbuf_nrm = 0;
     float4 *pos = nullptr, *alb = nullptr;
     // a-trous view of the G-buffer, pre-scaled by the edge-stopping constants kn = log2(e)/(sigma_n + 1e-6) and
     // kx = log2(e)/(sigma_x + 1e-6) and interleaved for the packed-fp32 distance code: {kn nx, kx px, kn ny, kx py}, {kn nz, kx pz}
