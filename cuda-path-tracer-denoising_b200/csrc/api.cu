@@ -11,6 +11,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 
@@ -55,6 +56,29 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
         memcpy(o.translation, g.translation, 12);
         memcpy(o.inverseTransform, g.inverseTransform, 64); memcpy(o.transform, g.transform, 64); memcpy(o.invTranspose, g.invTranspose, 64);
         if (g.materialid < 0 || g.materialid >= d->n_materials) { c->err = "geom references a material out of range"; return SVGF_ERR_INVALID; }
+        {   // conservative world bounds (fp64): cube = hull of the 8 transformed corners; sphere (r = 0.5) = centre +- 0.5 * |row_i of M3x3|
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            const float *M = g.transform;       // column-major
+            if (g.type == 0) {
+                for (int i = 0; i < 3; i++) {
+                    const double e = 0.5 * sqrt((double)M[0 + i] * M[0 + i] + (double)M[4 + i] * M[4 + i] + (double)M[8 + i] * M[8 + i]);
+                    lo[i] = M[12 + i] - e; hi[i] = M[12 + i] + e;
+                }
+            } else {
+                for (int k = 0; k < 8; k++) {
+                    const double x = (k & 1) ? 0.5 : -0.5, y = (k & 2) ? 0.5 : -0.5, z = (k & 4) ? 0.5 : -0.5;
+                    for (int i = 0; i < 3; i++) {
+                        const double v = M[0 + i] * x + M[4 + i] * y + M[8 + i] * z + M[12 + i];
+                        if (v < lo[i]) lo[i] = v;
+                        if (v > hi[i]) hi[i] = v;
+                    }
+                }
+            }
+            const double diag = sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+            const double pad = 0.01 * diag + 1e-3;
+            for (int i = 0; i < 3; i++) { o.aabb_min[i] = (float)(lo[i] - pad); o.aabb_max[i] = (float)(hi[i] + pad); }
+            if (!(diag == diag) || g.type == 2) for (int i = 0; i < 3; i++) { o.aabb_min[i] = -3e38f; o.aabb_max[i] = 3e38f; }
+        }
     }
     s.n_geoms = d->n_geoms; s.n_materials = d->n_materials; s.n_nodes = d->n_bvh_nodes; s.n_tris = d->n_triangles; s.n_textures = d->n_textures;
     CK(dalloc(&s.geoms, gd.size()));
@@ -190,6 +214,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     if (!c) return SVGF_ERR_INVALID;
     c->device = device; c->W = scene->width; c->H = scene->height; c->px = (size_t)c->W * c->H;
     c->shard = svgf_shard{0, 1, 0, c->H};
+    if (const char *v = getenv("SVGF_RT_VARIANT")) c->rt_variant = (!strcmp(v, "wavefront") || !strcmp(v, "1")) ? 1 : 0;
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = atoi(v) == 1 ? 1 : 2;    // 1 = direct kernel (A/B testing)
     memset(c->view_matrix_prev, 0, sizeof(c->view_matrix_prev));
     c->view_matrix_prev[0] = c->view_matrix_prev[5] = c->view_matrix_prev[10] = c->view_matrix_prev[15] = 1.0f;   // glm::mat4()
@@ -215,7 +240,7 @@ int svgf_destroy(svgf_ctx *c) {
     for (int i = 0; i < 3; i++) { cudaFree(c->cv[i]); cudaFree(c->lum[i]); }
     for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }
     cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->gnp); cudaFree(c->gzl); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
-    cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl); cudaFree(c->flags);
+    cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl); cudaFree(c->flags); cudaFree(c->wf_mem);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->aos_in); cudaFree(c->aos_out); cudaFree(c->aos_g);
     if (c->pinned_image) cudaFreeHost(c->pinned_image);

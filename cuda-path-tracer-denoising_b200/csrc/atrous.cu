@@ -158,7 +158,7 @@ struct AtrousT {
 // (denoise.cu:100-118,143). The 3x3 Gaussian lives in PIXEL space, i.e. across residue classes, so it is done here where
 // it is coalesced instead of per lattice point inside the tiled kernel. 4 B read (L1-shared) + 4 B written per pixel.
 __global__ void __launch_bounds__(256)
-atrous_kl_kernel(const PeerPtr<const float4> cv, const RowOwner ro, float *__restrict__ kl, int W, int H, int row_begin, int row_end,
+atrous_kl_kernel(const __grid_constant__ PeerPtr<const float4> cv, const __grid_constant__ RowOwner ro, float *__restrict__ kl, int W, int H, int row_begin, int row_end,
                  int blur_variance, float sigma_c) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
@@ -235,7 +235,7 @@ __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 3)
-atrous_tiled_kernel(AtrousT t) {
+atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     extern __shared__ __align__(16) float4 at_smem[];
     // per tap: {r,g,b,var}  {kn*nx, kx*px, kn*ny, kx*py}  {kn*nz, kx*pz, lum, -}  (the G-buffer part arrives pre-scaled)
     float4 *s_cv = at_smem, *s_np = at_smem + AT_TILE, *s_zl = at_smem + 2 * AT_TILE;

@@ -39,8 +39,9 @@ struct Mat4 { float m[16]; };
 // writes {colour,variance} 16 + moments 8 + history length 4.
 __global__ void __launch_bounds__(256)
 temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
-                const float4 *__restrict__ nrm_cur, const PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
-                const PeerPtr<float4> hist_cv, const PeerPtr<float2> mom_hist, const PeerPtr<int> hlen_tab, const RowOwner ro, int me,
+                const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
+                const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,
+                const __grid_constant__ PeerPtr<int> hlen_tab, const __grid_constant__ RowOwner ro, int me,
                 float4 *__restrict__ acc_cv, float *__restrict__ acc_lum, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
                 float color_alpha_min, float moment_alpha_min) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;

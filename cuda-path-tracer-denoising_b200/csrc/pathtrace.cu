@@ -140,11 +140,10 @@ struct SceneView {
 // glm::intersectRayTriangle (gtx/intersect.inl:37-74); same near-first order, same 64-entry stack
 // (overflow drops the subtree), same "first strictly smaller t wins".
 struct TriBest { float t, bx, by; int slot; };
-__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, TriBest &best) {
+__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, TriBest &best) {
     if (sc.n_nodes == 0) return false;
     bool hit = false;
     const int neg[3] = {ray.direction.x < 0.f, ray.direction.y < 0.f, ray.direction.z < 0.f};
-    const F3 invdir = mk(1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z);
     int top = 0, cur = 0;
     int stack[64];
     best.t = FLT_MAX; best.slot = -1; best.bx = best.by = 0.f;
@@ -213,16 +212,29 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
     bool mesh_done = false, mesh_hit = false;
     TriBest tb; tb.t = FLT_MAX; tb.slot = -1; tb.bx = tb.by = 0.f;
     int tri_id = -1;
+    // 1 / direction exactly as IntersectBVH forms it (intersections.h:276); also feeds the conservative bounds pre-test
+    const F3 invdir = mk(1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z);
     for (int i = 0; i < sc.n_geoms; i++) {
         const GeomD &g = sc.geoms[i];
         float t;
         F3 tmp_n = mk(0, 0, 0);
+        if (g.type != 2) {
+            // Slab test against the inflated world bounds. A NaN direction keeps every term NaN (no reject: the exact test
+            // then runs as in the reference); 0 * inf only arises for a ray lying IN an inflated face plane, which is
+            // >= 1e-3 outside the real surface, so dropping that NaN (fminf/fmaxf) can only reject true misses.
+            const float ax = (g.aabb_min[0] - ray.origin.x) * invdir.x, bx = (g.aabb_max[0] - ray.origin.x) * invdir.x;
+            const float ay = (g.aabb_min[1] - ray.origin.y) * invdir.y, by = (g.aabb_max[1] - ray.origin.y) * invdir.y;
+            const float az = (g.aabb_min[2] - ray.origin.z) * invdir.z, bz = (g.aabb_max[2] - ray.origin.z) * invdir.z;
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            if (tf < tn || tf < 0.f) continue;      // the exact test would return -1 (no hit): t_min is unaffected
+        }
         if (g.type == 1) t = boxIntersectionTest(g, ray, tmp_n);
         else if (g.type == 0) t = sphereIntersectionTest(g, ray, tmp_n);
         else {
             if (!mesh_done) {
                 mesh_done = true;
-                mesh_hit = intersectBVH(sc, ray, tb);
+                mesh_hit = intersectBVH(sc, ray, invdir, tb);
                 if (mesh_hit) tri_id = __float_as_int(__ldg(&sc.tri_hot[3 * tb.slot]).w);
             }
             t = -1.0f;
@@ -265,7 +277,9 @@ __device__ __forceinline__ F3 materialAlbedo(const SceneView &sc, const svgf_mat
 }
 
 // computeShadowRay, pathtrace.cu:284-297; glm::rotation (gtx/quaternion.inl:248-283), quat*vec3 (gtc/quaternion.inl:319-326)
-__device__ void computeShadowRay(Ray &sr, F3 originPos, F3 lightPos, float lightRadius, float &expectDist, unsigned int &seed) {
+// (noinline: one compiled copy shared by the state-machine kernel and the wavefront stages, see add_direct_light)
+__device__ __noinline__ void computeShadowRay(Ray &sr, F3 ipos, F3 inrm, F3 lightPos, float lightRadius, float &expectDist, unsigned int &seed) {
+    const F3 originPos = ipos + 1e-4f * inrm;       // pathtrace.cu:366
     F3 dirToCenter = normalize(lightPos - originPos);
     const F3 orig = mk(0.0f, 0.0f, 1.0f);
     float qw; F3 qv;
@@ -312,7 +326,7 @@ __device__ F3 calculateRandomDirectionInHemisphere(F3 normal, unsigned int &seed
 struct PathState { Ray ray; F3 color; bool diffuse; };
 
 // scatterRay, interactions.h:94-136
-__device__ void scatterRay(PathState &ps, F3 intersect, F3 normal, const svgf_material &m, unsigned int &seed) {
+__device__ __noinline__ void scatterRay(PathState &ps, F3 intersect, F3 normal, const svgf_material &m, unsigned int &seed) {
     ps.ray.origin = intersect + 1e-4f * normal;
     const F3 spec = mk(m.specular_color[0], m.specular_color[1], m.specular_color[2]);
     if (m.hasRefractive) {
@@ -340,6 +354,20 @@ __device__ void scatterRay(PathState &ps, F3 intersect, F3 normal, const svgf_ma
         ps.diffuse = true;
     }
 }
+
+// Radiance accumulation, compiled ONCE (noinline) so that the state-machine kernel and the wavefront stages contract
+// the same multiplies into the same FMAs and stay bit-identical to each other.
+__device__ __noinline__ F3 add_direct_light(F3 acc, F3 throughput, const svgf_material &light, float sintensity, float expectDist,
+                                            F3 shadow_dir, F3 normal) {        // pathtrace.cu:377-382
+    const float diffuse = gmax(0.0f, dot(shadow_dir, normal));
+    const float shadowIntensity = sintensity / powf(expectDist, 2.0f);
+    return acc + throughput * light.emittance * mk(light.color[0], light.color[1], light.color[2]) * shadowIntensity * diffuse;
+}
+__device__ __noinline__ F3 add_emission(F3 acc, F3 throughput, const svgf_material &m) {       // pathtrace.cu:333
+    return acc + throughput * mk(m.color[0], m.color[1], m.color[2]) * m.emittance;
+}
+
+__device__ __noinline__ F3 hit_point(F3 origin, F3 direction, float t) { return origin + t * direction; }     // pathtrace.cu:317,338
 
 // One thread per pixel, block = 8x16 pixel tile (a warp covers an 8x4 patch: coherent primary rays).
 //
@@ -406,11 +434,7 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
         if (kind == Q_SHADOW) {
             if (res.geomId == 0) {                               // pathtrace.cu:374-384 (lightIdx == 0)
                 const svgf_material &sm = sc.materials[res.materialId];
-                if (sm.emittance > 0.0f) {
-                    const float diffuse = gmax(0.0f, dot(cur.direction, inrm));
-                    const float shadowIntensity = P.sintensity / powf(expectDist, 2.0f);
-                    acc = acc + seg.color * sm.emittance * mk(sm.color[0], sm.color[1], sm.color[2]) * shadowIntensity * diffuse;
-                }
+                if (sm.emittance > 0.0f) acc = add_direct_light(acc, seg.color, sm, P.sintensity, expectDist, cur.direction, inrm);
             }
         } else {
             // the path ray's result lands in the persistent record; a miss only touches t and geomId (pathtrace.cu:267-271)
@@ -425,7 +449,7 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
             }
             if (depth == 0) {                                    // G-buffer from the primary hit, pathtrace.cu:316-323
                 const svgf_material &material = sc.materials[is.materialId];
-                const F3 p = seg.ray.origin + is.t * seg.ray.direction;
+                const F3 p = hit_point(seg.ray.origin, seg.ray.direction, is.t);
                 const F3 a = materialAlbedo(sc, material, is.u, is.v);
                 nrm_out[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.geomId));
                 pos_out[idx] = make_float4(p.x, p.y, p.z, 0.f);
@@ -439,17 +463,16 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
             seed = initRand(idx, P.frame + depth);
             const svgf_material &material = sc.materials[is.materialId];
             if (material.emittance > 0.0f) {
-                if (!P.trace_shadowray || !P.reduce_var || !seg.diffuse)
-                    acc = acc + seg.color * mk(material.color[0], material.color[1], material.color[2]) * material.emittance;
+                if (!P.trace_shadowray || !P.reduce_var || !seg.diffuse) acc = add_emission(acc, seg.color, material);
                 break;
             }
-            ipos = seg.ray.origin + is.t * seg.ray.direction;
+            ipos = hit_point(seg.ray.origin, seg.ray.direction, is.t);
             inrm = is.n;
             const bool materialIsDiffuse = material.hasReflective < 1e-6 && material.hasRefractive < 1e-6;
             if (!(P.denoise && P.sepcolor) || depth > 1) seg.color = seg.color * materialAlbedo(sc, material, is.u, is.v);
             if (P.trace_shadowray && materialIsDiffuse) {        // pathtrace.cu:358-371
                 const GeomD &light = sc.geoms[0];
-                computeShadowRay(cur, ipos + 1e-4f * inrm, mk(light.translation[0], light.translation[1], light.translation[2]),
+                computeShadowRay(cur, ipos, inrm, mk(light.translation[0], light.translation[1], light.translation[2]),
                                  P.lightradius, expectDist, seed);
                 kind = Q_SHADOW;
                 continue;
@@ -475,9 +498,273 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Wavefront variant (SVGF_RT_VARIANT=wavefront): the same per-ray functions, split into stages with SoA ray/hit
+// buffers in HBM and queues of live paths compacted with a warp ballot. One "slot" per pixel holds a path's state;
+// queues hold slot indices, so compaction moves 4 bytes per path, never the state. Stage kernels are launched for the
+// worst case and exit on the device-side queue length, so a frame needs no host synchronisation:
+//     generate -> [ intersect(path queue) -> shade -> intersect(shadow queue) -> shade_shadow ] x max_depth
+// Every result equals the state-machine kernel's bit for bit (same functions, same inputs, RNG keyed by pixel/frame/depth);
+// tests/test_gpu_parity.py::test_wavefront_equals_megakernel checks that. It exists for scenes where many paths die
+// early (open scenes); in closed boxes like cornell.txt hardly any path terminates before max depth and the extra HBM
+// round trips of the ray state make it slower than the state machine, which stays the default.
+struct WfBuffers {
+    float4 *ray_o, *ray_d;      // {origin, -} {direction, -}   current query ray of the slot (path or shadow)
+    float4 *seg_o, *seg_d;      // the path segment's own ray (kept while a shadow query is in flight)
+    float4 *color;              // {throughput rgb, diffuse flag}
+    float4 *acc;                // {radiance rgb, depth}
+    float4 *ctx0, *ctx1;        // {ipos, seed bits} {inrm, expectDist}
+    float4 *hit0, *hit1;        // {t, n} {u, v, materialId bits, geomId bits}; hit1.w == -2 marks "no result yet"
+    int *q_path[2], *q_shadow;  // queues of slots
+    int *counts;                // [0],[1]: path queue lengths (ping-pong), [2]: shadow queue length
+};
+
+__device__ __forceinline__ void wf_push(int *queue, int *count, int slot, bool pred) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) queue[base + __popc(m & ((1u << lane) - 1))] = slot;
+}
+
+__device__ __forceinline__ SceneView wf_scene(unsigned char *smem, const GeomD *g_geoms, int n_geoms, const svgf_material *g_materials,
+                                              int n_materials, const float4 *bvh, int n_nodes, const float4 *tri_hot,
+                                              const float4 *tri_cold, const TexD *textures) {
+    GeomD *s_geoms = reinterpret_cast<GeomD *>(smem);
+    svgf_material *s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomD) * n_geoms);
+    const int gw = sizeof(GeomD) / 4 * n_geoms, mw = sizeof(svgf_material) / 4 * n_materials;
+    const int *src = reinterpret_cast<const int *>(g_geoms); int *dst = reinterpret_cast<int *>(s_geoms);
+    for (int i = threadIdx.x; i < gw; i += blockDim.x) dst[i] = src[i];
+    src = reinterpret_cast<const int *>(g_materials); dst = reinterpret_cast<int *>(s_mats);
+    for (int i = threadIdx.x; i < mw; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    SceneView sc;
+    sc.geoms = s_geoms; sc.n_geoms = n_geoms; sc.materials = s_mats; sc.bvh = bvh; sc.n_nodes = n_nodes;
+    sc.tri_hot = tri_hot; sc.tri_cold = tri_cold; sc.textures = textures;
+    return sc;
+}
+
+struct WfScene { const GeomD *geoms; int n_geoms; const svgf_material *materials; int n_materials; const float4 *bvh; int n_nodes;
+                 const float4 *tri_hot, *tri_cold; const TexD *textures; };
+
+__global__ void __launch_bounds__(128)
+wf_generate_kernel(RtParams P, WfBuffers B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int npx = P.W * (P.row_end - P.row_begin);
+    if (i == 0) { B.counts[0] = npx; B.counts[1] = 0; B.counts[2] = 0; }
+    if (i >= npx) return;
+    const int x = i % P.W, y = P.row_begin + i / P.W;
+    const svgf_camera &cam = P.cam;
+    const F3 o = mk(cam.position[0], cam.position[1], cam.position[2]);
+    const F3 d = normalize(mk(cam.view[0], cam.view[1], cam.view[2])
+        - mk(cam.right[0], cam.right[1], cam.right[2]) * cam.pixelLength[0] * ((float)x - (float)(P.W * 0.5f - 0.5f))
+        - mk(cam.up[0], cam.up[1], cam.up[2]) * cam.pixelLength[1] * ((float)y - (float)(P.H * 0.5f - 0.5f)));
+    B.ray_o[i] = make_float4(o.x, o.y, o.z, 0.f); B.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
+    B.seg_o[i] = B.ray_o[i]; B.seg_d[i] = B.ray_d[i];
+    B.color[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    B.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.q_path[0][i] = i;
+}
+
+__global__ void __launch_bounds__(128)
+wf_intersect_kernel(WfScene S, WfBuffers B, const int *queue, const int *count) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SceneView sc = wf_scene(smem, S.geoms, S.n_geoms, S.materials, S.n_materials, S.bvh, S.n_nodes, S.tri_hot, S.tri_cold, S.textures);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    const int slot = queue[i];
+    const float4 o = B.ray_o[slot], d = B.ray_d[slot];
+    Ray r; r.origin = mk(o.x, o.y, o.z); r.direction = mk(d.x, d.y, d.z);
+    Isect res; res.geomId = -2; res.materialId = 0; res.t = 0.f; res.n = mk(0, 0, 0); res.u = res.v = 0.f;
+    const bool hit = computeIntersection(sc, r, res);
+    B.hit0[slot] = make_float4(res.t, res.n.x, res.n.y, res.n.z);
+    B.hit1[slot] = make_float4(res.u, res.v, __int_as_float(res.materialId), __int_as_float(hit ? res.geomId : -1));
+}
+
+__device__ __forceinline__ void wf_finish(const RtParams &P, float *image, int pix, F3 acc) {
+    float *img = image + 3 * (size_t)pix;
+    if (P.denoise) { img[0] = acc.x; img[1] = acc.y; img[2] = acc.z; }
+    else {
+        const float f = (float)P.frame, f1 = (float)(P.frame + 1);
+        const F3 nw = mk(img[0], img[1], img[2]) * f / f1 + acc / f1;
+        img[0] = nw.x; img[1] = nw.y; img[2] = nw.z;
+    }
+}
+
+// Processes the result of a PATH query (the body of the reference's bounce loop up to the shadow ray, pathtrace.cu:314-371)
+__global__ void __launch_bounds__(128)
+wf_shade_kernel(RtParams P, WfScene S, WfBuffers B, int in_q, float4 *__restrict__ nrm_out, float4 *__restrict__ pos_out,
+                float4 *__restrict__ alb_out, float4 *__restrict__ gnp_out, float2 *__restrict__ gzl_out, float *__restrict__ image,
+                float4 *__restrict__ stale_nm, float2 *__restrict__ stale_uv) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SceneView sc = wf_scene(smem, S.geoms, S.n_geoms, S.materials, S.n_materials, S.bvh, S.n_nodes, S.tri_hot, S.tri_cold, S.textures);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < B.counts[in_q];
+    int slot = 0; bool to_shadow = false, to_path = false;
+    if (live) {
+        slot = B.q_path[in_q][i];
+        const int pix = (P.row_begin + slot / P.W) * P.W + slot % P.W;
+        const float4 h0 = B.hit0[slot], h1 = B.hit1[slot];
+        const bool hit = __float_as_int(h1.w) != -1;
+        float4 acc4 = B.acc[slot]; float4 col4 = B.color[slot];
+        int depth = (int)acc4.w;
+        const float4 so = B.seg_o[slot], sd = B.seg_d[slot];
+        PathState seg; seg.ray.origin = mk(so.x, so.y, so.z); seg.ray.direction = mk(sd.x, sd.y, sd.z);
+        seg.color = mk(col4.x, col4.y, col4.z); seg.diffuse = col4.w != 0.f;
+        F3 acc = mk(acc4.x, acc4.y, acc4.z);
+        // persistent record (pathtrace.cu:85): a hit rewrites it, a miss only t/geomId
+        Isect is;
+        if (hit) { is.t = h0.x; is.n = mk(h0.y, h0.z, h0.w); is.u = h1.x; is.v = h1.y; is.materialId = __float_as_int(h1.z); is.geomId = __float_as_int(h1.w);
+                   stale_nm[pix] = make_float4(is.n.x, is.n.y, is.n.z, h1.z); stale_uv[pix] = make_float2(is.u, is.v); }
+        else { const float4 s4 = stale_nm[pix]; const float2 suv = stale_uv[pix];
+               is.t = -1.0f; is.geomId = -1; is.n = mk(s4.x, s4.y, s4.z); is.materialId = __float_as_int(s4.w); is.u = suv.x; is.v = suv.y; }
+        if (depth == 0) {
+            const svgf_material &material = sc.materials[is.materialId];
+            const F3 p = hit_point(seg.ray.origin, seg.ray.direction, is.t);
+            const F3 a = materialAlbedo(sc, material, is.u, is.v);
+            nrm_out[pix] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.geomId));
+            pos_out[pix] = make_float4(p.x, p.y, p.z, 0.f);
+            alb_out[pix] = make_float4(a.x, a.y, a.z, 0.f);
+            gnp_out[pix] = make_float4(is.n.x * P.kn, p.x * P.kx, is.n.y * P.kn, p.y * P.kx);
+            gzl_out[pix] = make_float2(is.n.z * P.kn, p.z * P.kx);
+        }
+        depth++;
+        bool done = depth > P.max_depth || !hit;
+        if (!done) {
+            unsigned int seed = initRand(pix, P.frame + depth);
+            const svgf_material &material = sc.materials[is.materialId];
+            if (material.emittance > 0.0f) {
+                if (!P.trace_shadowray || !P.reduce_var || !seg.diffuse) acc = add_emission(acc, seg.color, material);
+                done = true;
+            } else {
+                const F3 ipos = hit_point(seg.ray.origin, seg.ray.direction, is.t), inrm = is.n;
+                const bool materialIsDiffuse = material.hasReflective < 1e-6 && material.hasRefractive < 1e-6;
+                if (!(P.denoise && P.sepcolor) || depth > 1) seg.color = seg.color * materialAlbedo(sc, material, is.u, is.v);
+                if (P.trace_shadowray && materialIsDiffuse) {
+                    const GeomD &light = sc.geoms[0];
+                    Ray sr; float expectDist = 0.f;
+                    computeShadowRay(sr, ipos, inrm, mk(light.translation[0], light.translation[1], light.translation[2]),
+                                     P.lightradius, expectDist, seed);
+                    B.ray_o[slot] = make_float4(sr.origin.x, sr.origin.y, sr.origin.z, 0.f);
+                    B.ray_d[slot] = make_float4(sr.direction.x, sr.direction.y, sr.direction.z, 0.f);
+                    B.ctx0[slot] = make_float4(ipos.x, ipos.y, ipos.z, __uint_as_float(seed));
+                    B.ctx1[slot] = make_float4(inrm.x, inrm.y, inrm.z, expectDist);
+                    to_shadow = true;
+                } else if (depth < P.max_depth) {
+                    scatterRay(seg, ipos, inrm, material, seed);
+                    B.ray_o[slot] = make_float4(seg.ray.origin.x, seg.ray.origin.y, seg.ray.origin.z, 0.f);
+                    B.ray_d[slot] = make_float4(seg.ray.direction.x, seg.ray.direction.y, seg.ray.direction.z, 0.f);
+                    B.seg_o[slot] = B.ray_o[slot]; B.seg_d[slot] = B.ray_d[slot];
+                    to_path = true;
+                } else done = true;
+            }
+        }
+        B.color[slot] = make_float4(seg.color.x, seg.color.y, seg.color.z, seg.diffuse ? 1.f : 0.f);
+        B.acc[slot] = make_float4(acc.x, acc.y, acc.z, (float)depth);
+        if (done) wf_finish(P, image, pix, acc);
+    }
+    wf_push(B.q_shadow, &B.counts[2], slot, to_shadow);
+    wf_push(B.q_path[in_q ^ 1], &B.counts[in_q ^ 1], slot, to_path);
+}
+
+// Processes the result of a SHADOW query, then bounces (pathtrace.cu:373-392)
+__global__ void __launch_bounds__(128)
+wf_shade_shadow_kernel(RtParams P, WfScene S, WfBuffers B, int out_q, float *__restrict__ image, const float4 *__restrict__ stale_nm) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SceneView sc = wf_scene(smem, S.geoms, S.n_geoms, S.materials, S.n_materials, S.bvh, S.n_nodes, S.tri_hot, S.tri_cold, S.textures);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < B.counts[2];
+    int slot = 0; bool to_path = false;
+    if (live) {
+        slot = B.q_shadow[i];
+        const int pix = (P.row_begin + slot / P.W) * P.W + slot % P.W;
+        const float4 h1 = B.hit1[slot];
+        float4 acc4 = B.acc[slot]; const float4 col4 = B.color[slot];
+        const int depth = (int)acc4.w;
+        const float4 c0 = B.ctx0[slot], c1 = B.ctx1[slot];
+        const F3 ipos = mk(c0.x, c0.y, c0.z), inrm = mk(c1.x, c1.y, c1.z);
+        unsigned int seed = __float_as_uint(c0.w);
+        PathState seg; seg.color = mk(col4.x, col4.y, col4.z); seg.diffuse = col4.w != 0.f;
+        const float4 so = B.seg_o[slot], sd = B.seg_d[slot];
+        seg.ray.origin = mk(so.x, so.y, so.z); seg.ray.direction = mk(sd.x, sd.y, sd.z);
+        F3 acc = mk(acc4.x, acc4.y, acc4.z);
+        if (__float_as_int(h1.w) == 0) {
+            const svgf_material &sm = sc.materials[__float_as_int(h1.z)];
+            if (sm.emittance > 0.0f) {
+                const float4 rd = B.ray_d[slot];
+                acc = add_direct_light(acc, seg.color, sm, P.sintensity, c1.w, mk(rd.x, rd.y, rd.z), inrm);
+            }
+        }
+        if (depth < P.max_depth) {
+            const int materialId = __float_as_int(stale_nm[pix].w);     // the persistent record's material
+            scatterRay(seg, ipos, inrm, sc.materials[materialId], seed);
+            B.ray_o[slot] = make_float4(seg.ray.origin.x, seg.ray.origin.y, seg.ray.origin.z, 0.f);
+            B.ray_d[slot] = make_float4(seg.ray.direction.x, seg.ray.direction.y, seg.ray.direction.z, 0.f);
+            B.seg_o[slot] = B.ray_o[slot]; B.seg_d[slot] = B.ray_d[slot];
+            B.color[slot] = make_float4(seg.color.x, seg.color.y, seg.color.z, seg.diffuse ? 1.f : 0.f);
+            to_path = true;
+        }
+        B.acc[slot] = make_float4(acc.x, acc.y, acc.z, (float)depth);
+        if (!to_path) wf_finish(P, image, pix, acc);
+    }
+    wf_push(B.q_path[out_q], &B.counts[out_q], slot, to_path);
+}
+
+__global__ void wf_reset_counts_kernel(int *counts, int which_a, int which_b) {
+    if (threadIdx.x == 0) { counts[which_a] = 0; if (which_b >= 0) counts[which_b] = 0; }
+}
+
 }  // namespace
 
+static cudaError_t launch_pathtrace_wavefront(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
+    const DeviceScene &s = c->scene;
+    const int rows = p.row_end - p.row_begin;
+    if (rows <= 0) return cudaSuccess;
+    const int npx = p.W * rows;
+    if (!c->wf_mem) {       // lazily: 10 float4 planes + 3 int queues + counters, sized for the whole frame
+        const size_t n = c->px;
+        cudaError_t e = cudaMalloc(&c->wf_mem, n * (10 * sizeof(float4) + 3 * sizeof(int)) + 64);
+        if (e != cudaSuccess) return e;
+    }
+    WfBuffers B;
+    float4 *f4 = static_cast<float4 *>(c->wf_mem);
+    const size_t n = c->px;
+    B.ray_o = f4; B.ray_d = f4 + n; B.seg_o = f4 + 2 * n; B.seg_d = f4 + 3 * n; B.color = f4 + 4 * n; B.acc = f4 + 5 * n;
+    B.ctx0 = f4 + 6 * n; B.ctx1 = f4 + 7 * n; B.hit0 = f4 + 8 * n; B.hit1 = f4 + 9 * n;
+    int *qi = reinterpret_cast<int *>(f4 + 10 * n);
+    B.q_path[0] = qi; B.q_path[1] = qi + n; B.q_shadow = qi + 2 * n; B.counts = qi + 3 * n;
+    WfScene S{s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes, s.tri_hot, s.tri_cold, s.textures};
+    const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(wf_intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(wf_shade_shadow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    const int blocks = (npx + 127) / 128;
+    cudaStream_t st = c->stream;
+    wf_generate_kernel<<<blocks, 128, 0, st>>>(p, B);
+    int q = 0;
+    // bounce k shades path depth k + 1 (incl. its shadow ray); depth == max_depth never scatters, so max_depth rounds
+    // finish every path (one round even for max_depth == 0: the primary hit still has to produce the G-buffer)
+    const int rounds = p.max_depth > 1 ? p.max_depth : 1;
+    for (int k = 0; k < rounds; k++) {
+        wf_intersect_kernel<<<blocks, 128, smem, st>>>(S, B, B.q_path[q], &B.counts[q]);
+        wf_reset_counts_kernel<<<1, 32, 0, st>>>(B.counts, q ^ 1, 2);
+        wf_shade_kernel<<<blocks, 128, smem, st>>>(p, S, B, q, nrm_out, c->pos, c->alb, c->gnp, c->gzl, c->image, c->stale_nm, c->stale_uv);
+        if (p.trace_shadowray) {
+            wf_intersect_kernel<<<blocks, 128, smem, st>>>(S, B, B.q_shadow, &B.counts[2]);
+            wf_shade_shadow_kernel<<<blocks, 128, smem, st>>>(p, S, B, q ^ 1, c->image, c->stale_nm);
+        }
+        q ^= 1;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
+    if (c->rt_variant == 1) return launch_pathtrace_wavefront(c, p, nrm_out);
     const DeviceScene &s = c->scene;
     const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
     if (smem > 48 * 1024) {

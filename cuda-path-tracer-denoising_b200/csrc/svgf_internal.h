@@ -26,12 +26,15 @@
 //                                         ShadeableIntersection that survives a miss (pathtrace.cu:267-271,316-322)
 // ---------------------------------------------------------------------------------------------------
 
-struct GeomD {              // what the closest-hit loop needs of a Geom (sceneStructs.h:33-47), 224 B
+struct GeomD {              // what the closest-hit loop needs of a Geom (sceneStructs.h:33-47), 256 B
     int type, materialid, tri_begin, tri_end;
     float translation[3], pad_;
     float inverseTransform[16], transform[16], invTranspose[16];
+    // conservative world-space bounds of a cube/sphere (inflated by 1 % of the diagonal + 1e-3): a ray that misses them
+    // cannot pass the reference's exact object-space test, so that test (2 mat4 x vec4, a normalize, 6 IEEE divides) is skipped
+    float aabb_min[3], pad1_, aabb_max[3], pad2_;
 };
-static_assert(sizeof(GeomD) == 224, "GeomD");
+static_assert(sizeof(GeomD) == 256, "GeomD");
 
 struct TexD { int w, h, comp, pad; const unsigned char *px; };
 
@@ -85,6 +88,8 @@ struct svgf_ctx {
     float4 *cv[3] = {nullptr, nullptr, nullptr};
     float *lum[3] = {nullptr, nullptr, nullptr};    // luminance of cv[i].rgb, the reference's fp64 formula (denoise.cu:121)
     int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled
+    int rt_variant = 0;                 // 0 = state-machine kernel, 1 = wavefront (stage kernels + ballot-compacted queues)
+    void *wf_mem = nullptr;             // wavefront ray/hit/queue buffers (allocated on first use)
     int hist_cv = -1;                   // which cv[] holds the colour history for the next frame (-1: none yet)
     float4 *nrm[2] = {nullptr, nullptr};
     int cur_nrm = 0, gbuf_nrm = 0;
