@@ -165,10 +165,28 @@ def run_ours(args, wl, rank, world, local_rank):
     W, H, nl = wl["W"], wl["H"], wl["nlevel"]
     blob, R = m.open_scene(wl["scene"], W, H, device=local_rank)
     rows = [0, H]
-    if world > 1:       # shard the frame by row strips; other strips' rows are read in place over NVLink (CUDA IPC)
-        rows = m.connect_ranks(R, dist, rank, world)
     P = m.default_params(atrous_nlevel=nl)
     drv = blob.camera_driver(W, H, automate=wl["moving"])
+    if world > 1:       # shard the frame by row strips; other strips' rows are read in place over NVLink (CUDA IPC)
+        rows = m.connect_ranks(R, dist, rank, world)
+        # Equal-height strips are not equal-time strips (path-tracing cost follows the geometry a row sees): measure each
+        # rank's own device time per frame (waits excluded), move the boundaries, restart the history. Untimed set-up.
+        for _ in range(3):
+            R.set_profiling(True)
+            for f in range(4):
+                R.pathtrace(drv.cam if not drv.first else drv.step(), P, f)
+            st = R.stage_times(); R.set_profiling(False)
+            # per-level event intervals include the cross-rank waits, so the (uniform per pixel) denoise cost per row is
+            # taken from the rank that waited least; path trace + temporal intervals contain no waits
+            my_rows = max(1, rows[rank + 1] - rows[rank])
+            mine = torch.tensor([float(st[0] + st[1]), float(sum(st[2:9]) + st[9]) / my_rows], device="cuda", dtype=torch.float64)
+            allc = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allc, mine)
+            kappa = min(float(t[1].item()) for t in allc)
+            cost = [float(allc[r][0].item()) + kappa * (rows[r + 1] - rows[r]) for r in range(world)]
+            rows = m.balanced_partition(rows, cost)
+            dist.barrier(); R.sync(); R.reset()
+            rows = m.connect_ranks(R, dist, rank, world, rows)
     stream = torch.cuda.ExternalStream(R.stream(), device=torch.device("cuda", local_rank))
     host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
     host_np = host.numpy()
@@ -235,7 +253,7 @@ def run_ours(args, wl, rank, world, local_rank):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "scene": wl["scene"], "width": W, "height": H, "atrous_levels": nl,
-                   "parallelism": "1 GPU" if world == 1 else "%d row strips, peer reads over NVLink (CUDA IPC), no collective on the data path" % world,
+                   "parallelism": "1 GPU" if world == 1 else "%d row strips (cost-balanced, rows %s), peer reads over NVLink (CUDA IPC), no collective on the data path" % (world, rows),
                    "l2": "per-frame working set %.0f MB > 126 MB L2 (no flush needed)" % (px * 196 / 1e6)},
         "e2e": {"value": fps_e2e * px / 1e6, "unit": "Mpixels/sec", "fps": fps_e2e, "h2d_bytes_per_step": (84 + 80) * world,
                 "d2h_bytes_per_step": px * 12, "ms_per_step": ms_e2e / args.steps,

@@ -345,10 +345,31 @@ def gather_handles(local_handles, dist, world):
     return torch.cat(out).cpu().numpy()
 
 
-def connect_ranks(renderer, dist, rank, world):
+def connect_ranks(renderer, dist, rank, world, row_starts=None):
     """Shard `renderer`'s frame over the ranks of an initialised torch.distributed group (one process per GPU)."""
-    rs = row_partition(renderer.H, world)
+    rs = list(row_starts) if row_starts is not None else row_partition(renderer.H, world)
     allh = gather_handles(renderer.ipc_export(), dist, world)
     renderer.ipc_connect(rank, world, allh, rs)
     dist.barrier()
     return rs
+
+
+def balanced_partition(row_starts, cost_ms, min_rows=8):
+    """New strip boundaries that equalise the measured per-rank cost, assuming each strip's cost is spread evenly over
+    its rows (piecewise-constant cost density). Path-tracing cost per row depends on what the rows see, so equal-height
+    strips are not equal-time strips; a static, measured partition fixes that without touching the data path."""
+    world = len(cost_ms)
+    H = row_starts[-1]
+    dens = []
+    for r in range(world):
+        rows = max(1, row_starts[r + 1] - row_starts[r])
+        dens += [max(float(cost_ms[r]), 1e-6) / rows] * (row_starts[r + 1] - row_starts[r])
+    cum = np.concatenate([[0.0], np.cumsum(dens)])
+    target = cum[-1] / world
+    out = [0]
+    for r in range(1, world):
+        y = int(np.argmin(np.abs(cum - r * target)))
+        y = min(max(y, out[-1] + min_rows), H - (world - r) * min_rows)
+        out.append(y)
+    out.append(H)
+    return out

@@ -151,6 +151,7 @@ static void shared_bufs(svgf_ctx *c, void **o) {
     int n = 0;
     for (int i = 0; i < 3; i++) o[n++] = c->cv[i];
     for (int i = 0; i < 3; i++) o[n++] = c->lum[i];
+    for (int i = 0; i < 3; i++) o[n++] = c->varp[i];
     for (int i = 0; i < 2; i++) o[n++] = c->nrm[i];
     for (int i = 0; i < 2; i++) o[n++] = c->mom[i];
     for (int i = 0; i < 2; i++) o[n++] = c->hlen[i];
@@ -160,6 +161,7 @@ static void set_peer(svgf_ctx *c, int r, void *const *b) {
     int n = 0;
     for (int i = 0; i < 3; i++) c->p_cv[i].p[r] = (float4 *)b[n++];
     for (int i = 0; i < 3; i++) c->p_lum[i].p[r] = (float *)b[n++];
+    for (int i = 0; i < 3; i++) c->p_varp[i].p[r] = (float *)b[n++];
     for (int i = 0; i < 2; i++) c->p_nrm[i].p[r] = (float4 *)b[n++];
     for (int i = 0; i < 2; i++) c->p_mom[i].p[r] = (float2 *)b[n++];
     for (int i = 0; i < 2; i++) c->p_hlen[i].p[r] = (int *)b[n++];
@@ -168,7 +170,7 @@ static void set_peer(svgf_ctx *c, int r, void *const *b) {
 
 static int alloc_frame_buffers(svgf_ctx *c) {
     const size_t px = c->px;
-    for (int i = 0; i < 3; i++) { CK(dalloc(&c->cv[i], px)); CK(dalloc(&c->lum[i], px)); }
+    for (int i = 0; i < 3; i++) { CK(dalloc(&c->cv[i], px)); CK(dalloc(&c->lum[i], px)); CK(dalloc(&c->varp[i], px)); }
     for (int i = 0; i < 2; i++) { CK(dalloc(&c->nrm[i], px)); CK(dalloc(&c->mom[i], px)); CK(dalloc(&c->hlen[i], px)); }
     CK(dalloc(&c->pos, px)); CK(dalloc(&c->alb, px)); CK(dalloc(&c->gnp, px)); CK(dalloc(&c->gzl, px));
     CK(dalloc(&c->image, 3 * px)); CK(dalloc(&c->denoised, 3 * px)); CK(dalloc(&c->var_out, px));
@@ -237,7 +239,7 @@ int svgf_destroy(svgf_ctx *c) {
     DeviceScene &s = c->scene;
     cudaFree(s.geoms); cudaFree(s.materials); cudaFree(s.bvh); cudaFree(s.tri_hot); cudaFree(s.tri_cold); cudaFree(s.textures);
     for (unsigned char *p : s.tex_pixels) cudaFree(p);      // the reference leaks these (pathtrace.cu:136 vs 160-183)
-    for (int i = 0; i < 3; i++) { cudaFree(c->cv[i]); cudaFree(c->lum[i]); }
+    for (int i = 0; i < 3; i++) { cudaFree(c->cv[i]); cudaFree(c->lum[i]); cudaFree(c->varp[i]); }
     for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }
     cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->gnp); cudaFree(c->gzl); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
     cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl); cudaFree(c->flags); cudaFree(c->wf_mem);
@@ -259,7 +261,10 @@ int svgf_reset(svgf_ctx *c) {
     CK(cudaSetDevice(c->device));
     const size_t px = c->px;
     cudaStream_t st = c->stream;
-    for (int i = 0; i < 3; i++) { CK(cudaMemsetAsync(c->cv[i], 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->lum[i], 0, px * sizeof(float), st)); }
+    for (int i = 0; i < 3; i++) {
+        CK(cudaMemsetAsync(c->cv[i], 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->lum[i], 0, px * sizeof(float), st));
+        CK(cudaMemsetAsync(c->varp[i], 0, px * sizeof(float), st));
+    }
     for (int i = 0; i < 2; i++) {
         CK(cudaMemsetAsync(c->nrm[i], 0, px * sizeof(float4), st));
         CK(cudaMemsetAsync(c->mom[i], 0, px * sizeof(float2), st));
@@ -414,10 +419,10 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
     const float moment_alpha = P->temporal_enable ? P->moment_alpha : 1.0f;
     if (P->temporal_enable) {
         CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->p_nrm[c->cur_nrm ^ 1], c->pos, c->p_cv[c->hist_cv], c->p_mom[c->cur_mom],
-                           c->p_hlen[c->cur_hlen], acc, c->lum[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1],
+                           c->p_hlen[c->cur_hlen], acc, c->lum[acc_slot], c->varp[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1],
                            c->view_matrix_prev, color_alpha, moment_alpha));
     } else {
-        CK(launch_no_temporal(c, image, acc, c->lum[acc_slot]));
+        CK(launch_no_temporal(c, image, acc, c->lum[acc_slot], c->varp[acc_slot]));
     }
     CK(launch_signal(c, SVGF_STAGE_TEMPORAL));
     if (ev) CK(cudaEventRecord(ev[2], c->stream));
@@ -446,7 +451,7 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             a.src_slot = src;
             a.cv_in = c->cv[src];
             a.cv_out = (!last || is_hist) ? c->cv[dst] : nullptr;
-            a.lum_in = c->lum[src]; a.lum_out = c->lum[dst];
+            a.lum_in = c->lum[src]; a.lum_out = c->lum[dst]; a.var_in = c->varp[src]; a.varp_out = c->varp[dst];
             a.nrm = c->nrm[c->cur_nrm]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
             a.denoised_out = last ? c->denoised : nullptr; a.var_out = last ? c->var_out : nullptr;
             a.level = level; a.is_last = last; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
@@ -500,10 +505,10 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS || P->tracedepth < 0) { c->err = "svgf_render: parameter out of range"; return SVGF_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
     cudaEvent_t *ev = prof_begin(c, P);
-    if (ev) CK(cudaEventRecord(ev[0], c->stream));
     c->seq++;
     // before this frame overwrites planes that peers read in place, they must have finished the previous frame
     if (c->seq > 1) CK(launch_wait(c, SVGF_STAGE_FRAME, c->seq - 1));
+    if (ev) CK(cudaEventRecord(ev[0], c->stream));      // after the wait: stage times measure this rank's own work
     RtParams rp;
     rp.W = c->W; rp.H = c->H; rp.row_begin = c->shard.row_begin; rp.row_end = c->shard.row_end;
     rp.frame = frame; rp.max_depth = P->tracedepth; rp.trace_shadowray = P->shadowray; rp.reduce_var = P->reducevar;
@@ -601,11 +606,12 @@ extern "C" int svgf_atrous_host(svgf_ctx *c, float *color_out, float *variance_o
         std::vector<float> lm(px);
         for (size_t i = 0; i < px; i++) lm[i] = (float)(0.2126 * color_in[3 * i] + 0.7152 * color_in[3 * i + 1] + 0.0722 * color_in[3 * i + 2]);
         CK(cudaMemcpyAsync(c->lum[0], lm.data(), px * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->varp[0], variance_in, px * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     AtrousArgs a;
     a.src_slot = 0;
-    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.lum_in = c->lum[0]; a.lum_out = c->lum[1]; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
+    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.lum_in = c->lum[0]; a.lum_out = c->lum[1]; a.var_in = c->varp[0]; a.varp_out = c->varp[1]; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
     a.denoised_out = is_last ? c->denoised : nullptr; a.var_out = is_last ? c->var_out : nullptr;
     a.level = level; a.is_last = is_last != 0; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
     a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;

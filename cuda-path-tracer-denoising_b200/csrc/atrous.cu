@@ -28,6 +28,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 struct AtrousK {
     const float4 *cv_in; float4 *cv_out;
     const float *lum_in; float *lum_out;
+    float *varp_out;                            // dense copy of the output variance for the next level's 3x3 blur
     const float4 *nrm, *pos, *alb;
     const float4 *gnp; const float2 *gzl;       // pre-scaled, interleaved G-buffer view (svgf_internal.h)
     float *denoised_out, *var_out;
@@ -103,7 +104,7 @@ atrous_direct_kernel(AtrousK k) {
         d[0] = o.x; d[1] = o.y; d[2] = o.z;
         k.var_out[p] = o.w;
     }
-    if (k.cv_out) { k.cv_out[p] = o; k.lum_out[p] = lum_ref(o.x, o.y, o.z); }
+    if (k.cv_out) { k.cv_out[p] = o; k.lum_out[p] = lum_ref(o.x, o.y, o.z); k.varp_out[p] = o.w; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -120,15 +121,19 @@ atrous_direct_kernel(AtrousK k) {
 //   Out-of-image taps carry lum = 3e38: their exponent overflows and ex2(-inf) = 0 removes them without a branch.
 // Bank conflicts: a quarter-warp (8 lanes) reads 8 consecutive float4 (even/odd lattice columns are stored in
 // separate halves of a row because a thread's window starts at column 2*ap).
-constexpr int AT_LX = 16, AT_LY = 32, AT_C = 2, AT_TX = 2, AT_TY = 4;
-constexpr int AT_THREADS = (AT_LX / AT_TX) * (AT_LY / AT_TY) * AT_C;        // 128
-constexpr int AT_SW = AT_LX + 4, AT_SH = AT_LY + 4;                         // staged lattice points
-constexpr int AT_TILE = AT_SW * AT_SH * AT_C;                               // 1440 taps
-constexpr int AT_SMEM = AT_TILE * 48;                                       // 69120 B
-
-__device__ __forceinline__ int at_idx(int c, int tb, int ta) {
-    return ((c * AT_SH + tb) * 2 + (ta & 1)) * (AT_SW / 2) + (ta >> 1);
-}
+constexpr int AT_C = 2, AT_TX = 2, AT_TY = 4;
+// Tile shape <LX, LY> (lattice points per block, LX * LY = 512): 16x32 for fine levels, 32x16 when the lattice of a
+// residue class is short (coarse levels: 34 lattice rows at step 32 for 1080 rows; narrow strips of a sharded frame).
+template <int LX, int LY> struct AtShape {
+    static constexpr int SW = LX + 4, SH = LY + 4;                  // staged lattice points (tile + 2-point apron)
+    static constexpr int THREADS = (LX / AT_TX) * (LY / AT_TY) * AT_C;
+    static constexpr int TILE = SW * SH * AT_C;
+    static constexpr int PLANE = SW * SH + 4;                       // float4 per column plane; +4 so that the two planes land in
+                                                                    // different bank groups when a warp stages (c, ta) pairs
+    static constexpr int ARR = PLANE * AT_C;
+    static constexpr int SMEM = ARR * 48;
+    __device__ static __forceinline__ int idx(int c, int tb, int ta) { return c * PLANE + (tb * 2 + (ta & 1)) * (SW / 2) + (ta >> 1); }
+};
 __device__ __forceinline__ float sqrt_approx(float x) {
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -158,32 +163,57 @@ struct AtrousT {
 // (denoise.cu:100-118,143). The 3x3 Gaussian lives in PIXEL space, i.e. across residue classes, so it is done here where
 // it is coalesced instead of per lattice point inside the tiled kernel. 4 B read (L1-shared) + 4 B written per pixel.
 __global__ void __launch_bounds__(256)
-atrous_kl_kernel(const __grid_constant__ PeerPtr<const float4> cv, const __grid_constant__ RowOwner ro, float *__restrict__ kl, int W, int H, int row_begin, int row_end,
-                 int blur_variance, float sigma_c) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+atrous_kl_kernel(const __grid_constant__ PeerPtr<const float> varp, const __grid_constant__ RowOwner ro, float *__restrict__ kl,
+                 int W, int H, int row_begin, int row_end, int blur_variance, float sigma_c) {
+    // one thread = 4 consecutive pixels of a row: 3 rows x (left neighbour, float4, right neighbour) from the dense plane
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= row_end) return;
-    float var;
-    if (blur_variance) {
-        float sum = 0.0f, sumw = 0.0f;
+    if (x0 >= W || y >= row_end) return;
+    float v[3][6];
+    bool rok[3];
 #pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
+    for (int r = 0; r < 3; r++) {
+        const int ly = y + r - 1;
+        rok[r] = ly >= 0 && ly < H && (blur_variance || r == 1);
 #pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-                const int lx = x + dx, ly = y + dy;
-                if (lx >= 0 && ly >= 0 && lx < W && ly < H) {
-                    const float g = (dx == 0 ? 0.5f : 0.25f) * (dy == 0 ? 0.5f : 0.25f);
-                    sum += g * __ldg(&cv.p[owner_of(ro, ly)][lx + ly * W].w);
-                    sumw += g;
-                }
-            }
-        var = sum / sumw;
-    } else {
-        var = __ldg(&cv.p[owner_of(ro, y)][x + y * W].w);
+        for (int i = 0; i < 6; i++) v[r][i] = 0.f;
+        if (rok[r]) {
+            const float *row = varp.p[owner_of(ro, ly)] + (size_t)ly * W;
+            if (((W & 3) == 0) && x0 + 3 < W) { const float4 m = __ldg(reinterpret_cast<const float4 *>(row + x0)); v[r][1] = m.x; v[r][2] = m.y; v[r][3] = m.z; v[r][4] = m.w; }
+            else for (int i = 0; i < 4; i++) if (x0 + i < W) v[r][1 + i] = __ldg(row + x0 + i);
+            if (x0 > 0) v[r][0] = __ldg(row + x0 - 1);
+            if (x0 + 4 < W) v[r][5] = __ldg(row + x0 + 4);
+        }
     }
-    var = fmaxf(var, 0.0f);
-    // fp32: the reference's fp64 add/divide here (denoise.cu:143) only has to be matched to ~1e-7 relative
-    kl[x + y * W] = 1.4426950408889634f / (sqrtf(var) * sigma_c + 1e-6f);
+    float out[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = x0 + i;
+        float var;
+        if (blur_variance) {        // same tap order as the reference: rows outer, columns inner (denoise.cu:105-114)
+            float sum = 0.0f, sumw = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int lx = x + dx;
+                    if (rok[r] && lx >= 0 && lx < W) {
+                        const float g = (dx == 0 ? 0.5f : 0.25f) * (r == 1 ? 0.5f : 0.25f);
+                        sum += g * v[r][1 + i + dx];
+                        sumw += g;
+                    }
+                }
+            var = sum / sumw;
+        } else {
+            var = v[1][1 + i];
+        }
+        var = fmaxf(var, 0.0f);
+        // fp32: the reference's fp64 add/divide here (denoise.cu:143) only has to be matched to ~1e-7 relative
+        out[i] = 1.4426950408889634f / (sqrtf(var) * sigma_c + 1e-6f);
+    }
+    float *dst = kl + (size_t)y * W + x0;
+    if (((W & 3) == 0) && x0 + 3 < W) *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+    else for (int i = 0; i < 4; i++) if (x0 + i < W) dst[i] = out[i];
 }
 
 // Edge-stopping weight and accumulation of ONE (tap, centre) pair, written for Blackwell's packed fp32 pipe
@@ -212,14 +242,14 @@ __device__ __forceinline__ void at_pair(const AtTap &T, const AtCentre &C, AtAcc
 
 // One tap column (window column `tt` of the thread's 6) against the thread's 2 x 4 centres. DO0/DO1 select which of the
 // two centre columns the tap column reaches (|i| <= 2), so the edge columns are peeled without wasted work.
-template <bool DO0, bool DO1>
+template <class SH, bool DO0, bool DO1>
 __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np, const float4 *s_zl, int c, int row0, int col,
                                           const AtCentre (&C)[AT_TX][AT_TY], AtAcc (&A)[AT_TX][AT_TY], float hi0, float hi1) {
     // h = hi * hj with hj in {3/8, 1/4, 1/16} for |j| = 0, 1, 2
     const float h0[3] = {hi0 * 0.375f, hi0 * 0.25f, hi0 * 0.0625f}, h1[3] = {hi1 * 0.375f, hi1 * 0.25f, hi1 * 0.0625f};
 #pragma unroll
     for (int u = 0; u < AT_TY + 4; u++) {
-        const int si = at_idx(c, row0 + u, col);
+        const int si = SH::idx(c, row0 + u, col);
         const float4 np = s_np[si], zl = s_zl[si];
         AtTap T;
         T.cv = s_cv[si];
@@ -234,11 +264,14 @@ __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np
     }
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 3)
+template <int LX, int LY>
+__global__ void __launch_bounds__((AtShape<LX, LY>::THREADS), 3)
 atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
+    using SH = AtShape<LX, LY>;
+    constexpr int AT_LX = LX, AT_LY = LY, AT_SW = SH::SW, AT_SH = SH::SH, AT_ARR = SH::ARR, AT_THREADS = SH::THREADS;
     extern __shared__ __align__(16) float4 at_smem[];
     // per tap: {r,g,b,var}  {kn*nx, kx*px, kn*ny, kx*py}  {kn*nz, kx*pz, lum, -}  (the G-buffer part arrives pre-scaled)
-    float4 *s_cv = at_smem, *s_np = at_smem + AT_TILE, *s_zl = at_smem + 2 * AT_TILE;
+    float4 *s_cv = at_smem, *s_np = at_smem + AT_ARR, *s_zl = at_smem + 2 * AT_ARR;
     const AtrousK &k = t.k;
     const int W = k.W, H = k.H, step = k.step;
     const int cg = blockIdx.x % t.ncg, tile_x = blockIdx.x / t.ncg;
@@ -250,26 +283,36 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     // ---- stage tile + apron with cp.async (LDGSTS): every thread queues all of its 16-byte copies back to back and
     // none of the data passes through registers, so a block exposes ONE memory round trip instead of one per loop trip.
     // Out-of-image taps: zero-filled colour/geometry and lum = 3e38 (exponent overflows, ex2(-inf) = 0). ----
-    for (int n = tid; n < AT_TILE; n += AT_THREADS) {
-        const int c = n % AT_C, ta = (n / AT_C) % AT_SW, tb = n / (AT_C * AT_SW);
-        const int x = X0 + (a0 + ta) * step + c, y = yc + (b0 + tb) * step;
-        const int si = at_idx(c, tb, ta);
-        // only rows a live centre of this strip can reach (strip +- 2 steps): a tile of a coarse level spans far more
-        // rows than the strip, and for a sharded frame those rows would be fetched from a peer for nothing
-        if (a0 + ta >= 0 && b0 + tb >= 0 && x < W && y < H && y >= k.row_begin - 2 * step && y < k.row_end + 2 * step) {
-            const int q = x + y * W, o = owner_of(t.ro, y);     // rows of other strips come straight from their owner
-            cp_async16(&s_cv[si], &t.p_cv.p[o][q]);
-            cp_async16(&s_np[si], &t.p_gnp.p[o][q]);
-            cp_async8(&s_zl[si], &t.p_gzl.p[o][q]);
-            cp_async4(&s_zl[si].z, &t.p_lum.p[o][q]);
-        } else {
-            s_cv[si] = make_float4(0.f, 0.f, 0.f, 0.f); s_np[si] = make_float4(0.f, 0.f, 0.f, 0.f);
-            s_zl[si] = make_float4(0.f, 0.f, 3e38f, 0.f);
+    // Each of the first 120 threads owns one (lattice column, sub-column) of the tile and walks down its 36 rows in
+    // steps of 3: everything that depends on x is computed once, per row there is one bounds test and one owner lookup.
+    constexpr int ST_STRIDE = AT_THREADS / (AT_SW * AT_C);      // rows advanced per trip (3 for 16x32, 1 for 32x16)
+    if (tid < ST_STRIDE * AT_SW * AT_C) {
+        const int slot = tid % (AT_SW * AT_C), r0 = tid / (AT_SW * AT_C);
+        const int c = slot % AT_C, ta = slot / AT_C;
+        const int x = X0 + (a0 + ta) * step + c;
+        const bool x_ok = a0 + ta >= 0 && x < W;
+        const int y_lo = max(0, k.row_begin - 2 * step), y_hi = min(H, k.row_end + 2 * step);
+#pragma unroll 4
+        for (int tb = r0; tb < AT_SH; tb += ST_STRIDE) {
+            const int y = yc + (b0 + tb) * step;
+            const int si = SH::idx(c, tb, ta);
+            // only rows a live centre of this strip can reach (strip +- 2 steps): a tile of a coarse level spans far more
+            // rows than the strip, and for a sharded frame those rows would be fetched from a peer for nothing
+            if (x_ok && b0 + tb >= 0 && y >= y_lo && y < y_hi) {
+                const int q = x + y * W, o = owner_of(t.ro, y);     // rows of other strips come straight from their owner
+                cp_async16(&s_cv[si], &t.p_cv.p[o][q]);
+                cp_async16(&s_np[si], &t.p_gnp.p[o][q]);
+                cp_async8(&s_zl[si], &t.p_gzl.p[o][q]);
+                cp_async4(&s_zl[si].z, &t.p_lum.p[o][q]);
+            } else {
+                s_cv[si] = make_float4(0.f, 0.f, 0.f, 0.f); s_np[si] = make_float4(0.f, 0.f, 0.f, 0.f);
+                s_zl[si] = make_float4(0.f, 0.f, 3e38f, 0.f);
+            }
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 
-    const int ap = tid & 7, c = (tid >> 3) & 1, bq = tid >> 4;
+    const int ap = tid % (AT_LX / 2), c = (tid / (AT_LX / 2)) & 1, bq = tid / AT_LX;
     // centres' kl from the pre-pass plane, issued before the barrier
     float c_kl[AT_TX][AT_TY];
     bool live = false;
@@ -292,7 +335,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     for (int ca = 0; ca < AT_TX; ca++)
 #pragma unroll
         for (int cb = 0; cb < AT_TY; cb++) {
-            const int si = at_idx(c, 4 * bq + cb + 2, 2 * ap + ca + 2);
+            const int si = SH::idx(c, 4 * bq + cb + 2, 2 * ap + ca + 2);
             const float4 np = s_np[si], zl = s_zl[si];
             C[ca][cb].nx_px = make_float2(-np.x, -np.y); C[ca][cb].ny_py = make_float2(-np.z, -np.w);
             C[ca][cb].nz_pz = make_float2(-zl.x, -zl.y); C[ca][cb].lum = zl.z; C[ca][cb].kl = c_kl[ca][cb];
@@ -304,15 +347,15 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     // columns 0 and 5 reach one centre column each and are peeled. The centre tap takes the generic path: all
     // differences are 0, sqrt(0) = 0, ex2(-0) = 1 exactly. ----
     const int row0 = 4 * bq, col0 = 2 * ap;
-    at_column<true, false>(s_cv, s_np, s_zl, c, row0, col0 + 0, C, A, 0.0625f, 0.f);        // i = -2 for centre column 0
+    at_column<SH, true, false>(s_cv, s_np, s_zl, c, row0, col0 + 0, C, A, 0.0625f, 0.f);        // i = -2 for centre column 0
 #pragma unroll 1
     for (int tt = 1; tt <= 4; tt++) {
         const int i0 = tt - 2, i1 = tt - 3;
         const float hi0 = i0 == 0 ? 0.375f : ((i0 == 1 || i0 == -1) ? 0.25f : 0.0625f);
         const float hi1 = i1 == 0 ? 0.375f : ((i1 == 1 || i1 == -1) ? 0.25f : 0.0625f);
-        at_column<true, true>(s_cv, s_np, s_zl, c, row0, col0 + tt, C, A, hi0, hi1);
+        at_column<SH, true, true>(s_cv, s_np, s_zl, c, row0, col0 + tt, C, A, hi0, hi1);
     }
-    at_column<false, true>(s_cv, s_np, s_zl, c, row0, col0 + 5, C, A, 0.f, 0.0625f);        // i = +2 for centre column 1
+    at_column<SH, false, true>(s_cv, s_np, s_zl, c, row0, col0 + 5, C, A, 0.f, 0.0625f);        // i = +2 for centre column 1
 
     // ---- outputs: all 8 results (incl. the fp64 luminance of the new colour, a long dependent chain) are computed as
     // straight-line code first, then stored under predicates, so the 8 chains overlap ----
@@ -354,7 +397,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
                 d[0] = o[ca][cb].x; d[1] = o[ca][cb].y; d[2] = o[ca][cb].z;
                 k.var_out[p] = o[ca][cb].w;
             }
-            if (k.cv_out) { k.cv_out[p] = o[ca][cb]; k.lum_out[p] = ol[ca][cb]; }
+            if (k.cv_out) { k.cv_out[p] = o[ca][cb]; k.lum_out[p] = ol[ca][cb]; k.varp_out[p] = o[ca][cb].w; }
         }
 }
 
@@ -371,7 +414,8 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     AtrousK k;
-    k.cv_in = a.cv_in; k.cv_out = a.cv_out; k.lum_in = a.lum_in; k.lum_out = a.lum_out; k.nrm = a.nrm; k.pos = a.pos; k.alb = a.alb;
+    k.cv_in = a.cv_in; k.cv_out = a.cv_out; k.lum_in = a.lum_in; k.lum_out = a.lum_out; k.varp_out = a.varp_out;
+    k.nrm = a.nrm; k.pos = a.pos; k.alb = a.alb;
     k.gnp = a.gnp; k.gzl = a.gzl;
     k.denoised_out = a.denoised_out; k.var_out = a.var_out;
     k.W = c->W; k.H = c->H; k.row_begin = c->shard.row_begin; k.row_end = c->shard.row_end; k.step = 1 << a.level;
@@ -383,12 +427,6 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
         atrous_direct_kernel<<<g, b, 0, c->stream>>>(k);
         return cudaGetLastError();
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(atrous_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     AtrousT t;
     t.k = k; t.kl = c->kl; t.ro = c->rows;
     for (int r = 0; r < SVGF_MAX_RANKS; r++) {
@@ -397,15 +435,32 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
         t.p_gnp.p[r] = peer ? c->p_gnp.p[r] : a.gnp; t.p_gzl.p[r] = peer ? c->p_gzl.p[r] : a.gzl;
     }
     {
-        dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
-        atrous_kl_kernel<<<g, b, 0, c->stream>>>(t.p_cv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c);
+        PeerPtr<const float> pv;
+        for (int r = 0; r < SVGF_MAX_RANKS; r++) pv.p[r] = (r < c->shard.world && a.src_slot >= 0) ? c->p_varp[a.src_slot].p[r] : a.var_in;
+        dim3 b(32, 8), g(((c->W + 3) / 4 + 31) / 32, (rows + 7) / 8);
+        atrous_kl_kernel<<<g, b, 0, c->stream>>>(pv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c);
     }
     const int step = k.step;
     t.b_first = k.row_begin / step;
     t.ncg = step / AT_C;
     const int lat_w = (c->W + step - 1) / step;                                 // lattice columns per class
     const int lat_rows = (k.row_end - 1) / step - t.b_first + 1;                // lattice rows touching the strip
-    dim3 g(((lat_w + AT_LX - 1) / AT_LX) * t.ncg, ((lat_rows + AT_LY - 1) / AT_LY) * step);
-    atrous_tiled_kernel<<<g, AT_THREADS, AT_SMEM, c->stream>>>(t);
+    // pick the tile shape that wastes fewer lattice points (work is issued per warp: 16 x 8 resp. 32 x 4 points)
+    auto padded = [&](int lx, int ly, int wy) {
+        return (double)(((lat_w + lx - 1) / lx) * lx) * (((lat_rows + wy - 1) / wy) * wy) + 0.15 * (double)(((lat_w + lx - 1) / lx) * lx) * (((lat_rows + ly - 1) / ly) * ly);
+    };
+    if (!c->atrous_attr_set) {      // per context (= per device)
+        cudaError_t e = cudaFuncSetAttribute(atrous_tiled_kernel<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtShape<16, 32>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(atrous_tiled_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtShape<32, 16>::SMEM);
+        if (e != cudaSuccess) return e;
+        c->atrous_attr_set = true;
+    }
+    if (padded(16, 32, 8) <= padded(32, 16, 4)) {
+        dim3 g(((lat_w + 15) / 16) * t.ncg, ((lat_rows + 31) / 32) * step);
+        atrous_tiled_kernel<16, 32><<<g, AtShape<16, 32>::THREADS, AtShape<16, 32>::SMEM, c->stream>>>(t);
+    } else {
+        dim3 g(((lat_w + 31) / 32) * t.ncg, ((lat_rows + 15) / 16) * step);
+        atrous_tiled_kernel<32, 16><<<g, AtShape<32, 16>::THREADS, AtShape<32, 16>::SMEM, c->stream>>>(t);
+    }
     return cudaGetLastError();
 }

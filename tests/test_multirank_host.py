@@ -35,7 +35,7 @@ def _worker(rank, world, port, nbytes, q):
 def test_handle_gather_is_rank_ordered(world):
     m = svgf()
     nbytes = m.lib().svgf_ipc_handles_size()
-    assert nbytes == 15 * 64
+    assert nbytes == 18 * 64
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -60,3 +60,17 @@ def test_row_partition_covers_the_frame_once(H, world):
     assert all(rs[i] <= rs[i + 1] for i in range(world))
     sizes = [rs[i + 1] - rs[i] for i in range(world)]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_partition_equalises_cost():
+    m = svgf()
+    rs = m.row_partition(2160, 8)
+    # a cost profile that grows down the frame (more geometry in the lower rows)
+    cost = [1.0, 1.1, 1.4, 1.8, 2.2, 2.4, 2.0, 1.5]
+    new = m.balanced_partition(rs, cost)
+    assert new[0] == 0 and new[-1] == 2160 and all(new[i] < new[i + 1] for i in range(8))
+    dens = np.repeat(np.array(cost) / 270.0, 270)
+    per = [dens[new[r]:new[r + 1]].sum() for r in range(8)]
+    assert max(per) / min(per) < 1.03
+    # uniform cost keeps equal strips
+    assert m.balanced_partition(rs, [1.0] * 8) == rs
