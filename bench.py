@@ -225,6 +225,8 @@ def run_ours(args, wl, rank, world, local_rank):
     R.sync(); barrier()
     ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
     clk = clocks.stop()
+    if world > 1 and R.peer_error():
+        raise SystemExit("bench.py: a cross-rank wait timed out (a peer stopped making progress)")
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -140,7 +140,11 @@ struct SceneView {
 // glm::intersectRayTriangle (gtx/intersect.inl:37-74); same near-first order, same 64-entry stack
 // (overflow drops the subtree), same "first strictly smaller t wins".
 struct TriBest { float t, bx, by; int slot; };
-__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, TriBest &best) {
+// `t_bound`: hits at or beyond it cannot matter to the caller (it already holds a closer surface), so subtrees whose
+// slab entry lies beyond it -- or beyond the closest triangle found so far -- are skipped. The reference visits them
+// (no t-culling in AABBIntersect2) and then discards what it finds there: a triangle inside a node cannot be hit before
+// the ray enters the node's box, so with a conservative margin the closest triangle is the same.
+__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, float t_bound, TriBest &best) {
     if (sc.n_nodes == 0) return false;
     bool hit = false;
     const int neg[3] = {ray.direction.x < 0.f, ray.direction.y < 0.f, ray.direction.z < 0.f};
@@ -155,7 +159,8 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
         float tzMin = (a.z - ray.origin.z) * invdir.z, tzMax = (b.z - ray.origin.z) * invdir.z;
         float tmin = gmax(gmax(gmin(txMin, txMax), gmin(tyMin, tyMax)), gmin(tzMin, tzMax));
         float tmax = gmin(gmin(gmax(txMin, txMax), gmax(tyMin, tyMax)), gmax(tzMin, tzMax));
-        const bool box_hit = !(tmax < 0) && !(tmin > tmax);
+        const float t_cull = fminf(best.t, t_bound);
+        const bool box_hit = !(tmax < 0) && !(tmin > tmax) && !(tmin > t_cull * 1.0001f + 1e-4f);
         if (box_hit) {
             const int meta = __float_as_int(a.w), off = __float_as_int(b.w);
             const int count = meta & 0xffff;
@@ -228,13 +233,15 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
             const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             if (tf < tn || tf < 0.f) continue;      // the exact test would return -1 (no hit): t_min is unaffected
+            // the exact t is the world distance to a point inside these bounds, so it cannot undercut a closer hit already held
+            if (tn > t_min * 1.001f + 1e-3f) continue;
         }
         if (g.type == 1) t = boxIntersectionTest(g, ray, tmp_n);
         else if (g.type == 0) t = sphereIntersectionTest(g, ray, tmp_n);
         else {
             if (!mesh_done) {
                 mesh_done = true;
-                mesh_hit = intersectBVH(sc, ray, invdir, tb);
+                mesh_hit = intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb);
                 if (mesh_hit) tri_id = __float_as_int(__ldg(&sc.tri_hot[3 * tb.slot]).w);
             }
             t = -1.0f;
