@@ -150,8 +150,7 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
 static void shared_bufs(svgf_ctx *c, void **o) {
     int n = 0;
     for (int i = 0; i < 3; i++) o[n++] = c->cv[i];
-    for (int i = 0; i < 3; i++) o[n++] = c->lum[i];
-    for (int i = 0; i < 3; i++) o[n++] = c->varp[i];
+    for (int i = 0; i < 3; i++) o[n++] = c->lv[i];
     for (int i = 0; i < 2; i++) o[n++] = c->nrm[i];
     for (int i = 0; i < 2; i++) o[n++] = c->mom[i];
     for (int i = 0; i < 2; i++) o[n++] = c->hlen[i];
@@ -160,8 +159,7 @@ static void shared_bufs(svgf_ctx *c, void **o) {
 static void set_peer(svgf_ctx *c, int r, void *const *b) {
     int n = 0;
     for (int i = 0; i < 3; i++) c->p_cv[i].p[r] = (float4 *)b[n++];
-    for (int i = 0; i < 3; i++) c->p_lum[i].p[r] = (float *)b[n++];
-    for (int i = 0; i < 3; i++) c->p_varp[i].p[r] = (float *)b[n++];
+    for (int i = 0; i < 3; i++) c->p_lv[i].p[r] = (float2 *)b[n++];
     for (int i = 0; i < 2; i++) c->p_nrm[i].p[r] = (float4 *)b[n++];
     for (int i = 0; i < 2; i++) c->p_mom[i].p[r] = (float2 *)b[n++];
     for (int i = 0; i < 2; i++) c->p_hlen[i].p[r] = (int *)b[n++];
@@ -170,9 +168,15 @@ static void set_peer(svgf_ctx *c, int r, void *const *b) {
 
 static int alloc_frame_buffers(svgf_ctx *c) {
     const size_t px = c->px;
-    for (int i = 0; i < 3; i++) { CK(dalloc(&c->cv[i], px)); CK(dalloc(&c->lum[i], px)); CK(dalloc(&c->varp[i], px)); }
+    // planes the TMA tile loader addresses get SVGF_PAD_ROWS rows of (zeroed, never written) padding: lattice extents round up
+    const size_t ppx = px + (size_t)SVGF_PAD_ROWS * c->W;
+    for (int i = 0; i < 3; i++) {
+        CK(dalloc(&c->cv[i], ppx)); CK(dalloc(&c->lv[i], ppx));
+        CK(cudaMemset(c->cv[i], 0, ppx * sizeof(float4))); CK(cudaMemset(c->lv[i], 0, ppx * sizeof(float2)));
+    }
     for (int i = 0; i < 2; i++) { CK(dalloc(&c->nrm[i], px)); CK(dalloc(&c->mom[i], px)); CK(dalloc(&c->hlen[i], px)); }
-    CK(dalloc(&c->pos, px)); CK(dalloc(&c->alb, px)); CK(dalloc(&c->gnp, px)); CK(dalloc(&c->gzl, px));
+    CK(dalloc(&c->pos, px)); CK(dalloc(&c->alb, px)); CK(dalloc(&c->gnp, ppx)); CK(dalloc(&c->gzl, ppx));
+    CK(cudaMemset(c->gnp, 0, ppx * sizeof(float4))); CK(cudaMemset(c->gzl, 0, ppx * sizeof(float2)));
     CK(dalloc(&c->image, 3 * px)); CK(dalloc(&c->denoised, 3 * px)); CK(dalloc(&c->var_out, px));
     CK(dalloc(&c->stale_nm, px)); CK(dalloc(&c->stale_uv, px)); CK(dalloc(&c->kl, px));
     CK(cudaMalloc((void **)&c->pbo_own, px * 8));
@@ -184,6 +188,7 @@ static int alloc_frame_buffers(svgf_ctx *c) {
         c->rows.world = 1; c->rows.start[0] = 0; for (int r = 1; r <= SVGF_MAX_RANKS; r++) c->rows.start[r] = c->H;
     }
     CK(cudaMallocHost((void **)&c->pinned_image, px * 12));
+    atrous_build_tensor_maps(c);        // c->tma_ok = 0 (cp.async loader) when the driver entry point or the row pitch does not allow it
     return SVGF_OK;
 }
 
@@ -217,7 +222,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     c->device = device; c->W = scene->width; c->H = scene->height; c->px = (size_t)c->W * c->H;
     c->shard = svgf_shard{0, 1, 0, c->H};
     if (const char *v = getenv("SVGF_RT_VARIANT")) c->rt_variant = (!strcmp(v, "wavefront") || !strcmp(v, "1")) ? 1 : 0;
-    if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = atoi(v) == 1 ? 1 : 2;    // 1 = direct kernel (A/B testing)
+    if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3) ? atoi(v) : 2;    // A/B testing
     memset(c->view_matrix_prev, 0, sizeof(c->view_matrix_prev));
     c->view_matrix_prev[0] = c->view_matrix_prev[5] = c->view_matrix_prev[10] = c->view_matrix_prev[15] = 1.0f;   // glm::mat4()
     int rc = SVGF_OK;
@@ -239,7 +244,8 @@ int svgf_destroy(svgf_ctx *c) {
     DeviceScene &s = c->scene;
     cudaFree(s.geoms); cudaFree(s.materials); cudaFree(s.bvh); cudaFree(s.tri_hot); cudaFree(s.tri_cold); cudaFree(s.textures);
     for (unsigned char *p : s.tex_pixels) cudaFree(p);      // the reference leaks these (pathtrace.cu:136 vs 160-183)
-    for (int i = 0; i < 3; i++) { cudaFree(c->cv[i]); cudaFree(c->lum[i]); cudaFree(c->varp[i]); }
+    for (int i = 0; i < 3; i++) { cudaFree(c->cv[i]); cudaFree(c->lv[i]); }
+    free(c->tmaps);
     for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }
     cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->gnp); cudaFree(c->gzl); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
     cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl); cudaFree(c->flags); cudaFree(c->wf_mem);
@@ -262,8 +268,7 @@ int svgf_reset(svgf_ctx *c) {
     const size_t px = c->px;
     cudaStream_t st = c->stream;
     for (int i = 0; i < 3; i++) {
-        CK(cudaMemsetAsync(c->cv[i], 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->lum[i], 0, px * sizeof(float), st));
-        CK(cudaMemsetAsync(c->varp[i], 0, px * sizeof(float), st));
+        CK(cudaMemsetAsync(c->cv[i], 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->lv[i], 0, px * sizeof(float2), st));
     }
     for (int i = 0; i < 2; i++) {
         CK(cudaMemsetAsync(c->nrm[i], 0, px * sizeof(float4), st));
@@ -419,10 +424,10 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
     const float moment_alpha = P->temporal_enable ? P->moment_alpha : 1.0f;
     if (P->temporal_enable) {
         CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->p_nrm[c->cur_nrm ^ 1], c->pos, c->p_cv[c->hist_cv], c->p_mom[c->cur_mom],
-                           c->p_hlen[c->cur_hlen], acc, c->lum[acc_slot], c->varp[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1],
+                           c->p_hlen[c->cur_hlen], acc, c->lv[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1],
                            c->view_matrix_prev, color_alpha, moment_alpha));
     } else {
-        CK(launch_no_temporal(c, image, acc, c->lum[acc_slot], c->varp[acc_slot]));
+        CK(launch_no_temporal(c, image, acc, c->lv[acc_slot]));
     }
     CK(launch_signal(c, SVGF_STAGE_TEMPORAL));
     if (ev) CK(cudaEventRecord(ev[2], c->stream));
@@ -451,7 +456,7 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             a.src_slot = src;
             a.cv_in = c->cv[src];
             a.cv_out = (!last || is_hist) ? c->cv[dst] : nullptr;
-            a.lum_in = c->lum[src]; a.lum_out = c->lum[dst]; a.var_in = c->varp[src]; a.varp_out = c->varp[dst];
+            a.lv_in = c->lv[src]; a.lv_out = c->lv[dst]; a.dst_slot = dst;
             a.nrm = c->nrm[c->cur_nrm]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
             a.denoised_out = last ? c->denoised : nullptr; a.var_out = last ? c->var_out : nullptr;
             a.level = level; a.is_last = last; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
@@ -603,15 +608,15 @@ extern "C" int svgf_atrous_host(svgf_ctx *c, float *color_out, float *variance_o
     atrous_scales(P->sigman, P->sigmax, &kn, &kx);
     CK(launch_aos_to_soa(c, c->aos_g, c->nrm[0], c->pos, c->alb, kn, kx));
     {
-        std::vector<float> lm(px);
-        for (size_t i = 0; i < px; i++) lm[i] = (float)(0.2126 * color_in[3 * i] + 0.7152 * color_in[3 * i + 1] + 0.0722 * color_in[3 * i + 2]);
-        CK(cudaMemcpyAsync(c->lum[0], lm.data(), px * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->varp[0], variance_in, px * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        std::vector<float2> lm(px);
+        for (size_t i = 0; i < px; i++)
+            lm[i] = make_float2((float)(0.2126 * color_in[3 * i] + 0.7152 * color_in[3 * i + 1] + 0.0722 * color_in[3 * i + 2]), variance_in[i]);
+        CK(cudaMemcpyAsync(c->lv[0], lm.data(), px * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     AtrousArgs a;
     a.src_slot = 0;
-    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.lum_in = c->lum[0]; a.lum_out = c->lum[1]; a.var_in = c->varp[0]; a.varp_out = c->varp[1]; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
+    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.lv_in = c->lv[0]; a.lv_out = c->lv[1]; a.dst_slot = 1; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
     a.denoised_out = is_last ? c->denoised : nullptr; a.var_out = is_last ? c->var_out : nullptr;
     a.level = level; a.is_last = is_last != 0; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
     a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;

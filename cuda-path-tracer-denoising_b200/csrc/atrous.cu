@@ -14,6 +14,9 @@
 //     converges to when all reads win the race and is the only deterministic, shardable definition.
 #include "svgf_internal.h"
 
+#include <cuda.h>            // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cuda/barrier>
+
 namespace {
 
 __device__ __forceinline__ float lum_ref(float r, float g, float b) {
@@ -27,8 +30,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct AtrousK {
     const float4 *cv_in; float4 *cv_out;
-    const float *lum_in; float *lum_out;
-    float *varp_out;                            // dense copy of the output variance for the next level's 3x3 blur
+    const float2 *lv_in; float2 *lv_out;        // {luminance (fp64 formula), variance} per pixel
     const float4 *nrm, *pos, *alb;
     const float4 *gnp; const float2 *gzl;       // pre-scaled, interleaved G-buffer view (svgf_internal.h)
     float *denoised_out, *var_out;
@@ -104,68 +106,73 @@ atrous_direct_kernel(AtrousK k) {
         d[0] = o.x; d[1] = o.y; d[2] = o.z;
         k.var_out[p] = o.w;
     }
-    if (k.cv_out) { k.cv_out[p] = o; k.lum_out[p] = lum_ref(o.x, o.y, o.z); k.varp_out[p] = o.w; }
+    if (k.cv_out) { k.cv_out[p] = o; k.lv_out[p] = make_float2(lum_ref(o.x, o.y, o.z), o.w); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// v2: lattice-tiled kernel.
+// Lattice-tiled kernel.
 //
 // With step s the 5x5 dilated stencil only couples pixels of one residue class (x mod s, y mod s): on that
-// sub-lattice it is a DENSE 5x5 stencil. A block therefore owns a tile of LX x LY lattice points (x C adjacent
+// sub-lattice it is a DENSE 5x5 stencil. A block therefore owns a tile of LX x LY lattice points (x C = 2 adjacent
 // columns, so every global access is a full 32-byte sector) of one class, stages tile + 2-point apron once into
 // shared memory -- the same code and the same apron cost (1.4x) for step 2 and step 128 -- and every thread
 // computes a 2 x 4 patch of lattice points from a 6 x 8 window of taps held one at a time in registers, so each tap
 // is read from shared memory once per thread and reused for up to 8 centres (4.2 pair evaluations per 48-byte read).
-//   shared memory per tap: {r,g,b,var} {kn*n, lum} {kx*p, -}: normals/positions are pre-scaled by log2(e)/(sigma+1e-6)
-//   so the edge-stopping exponent is  |lq-lp|*kl + |n'q-n'p| + |p'q-p'p|  (2 sqrt.approx + 1 ex2.approx per pair).
-//   Out-of-image taps carry lum = 3e38: their exponent overflows and ex2(-inf) = 0 removes them without a branch.
-// Bank conflicts: a quarter-warp (8 lanes) reads 8 consecutive float4 (even/odd lattice columns are stored in
-// separate halves of a row because a thread's window starts at column 2*ap).
+//   per tap in shared memory: {r,g,b,var} {kn nx, kx px, kn ny, kx py} {kn nz, kx pz} {lum, var}. Normals/positions are
+//   pre-scaled by log2(e)/(sigma+1e-6), so the edge-stopping exponent is |lq-lp|*kl + |n'q-n'p| + |p'q-p'p|
+//   (2 sqrt.approx + 1 ex2.approx per pair). Out-of-image taps carry lum = 3e38: their exponent overflows and
+//   ex2(-inf) = 0 removes them without a branch.
+// Staging is done by the TMA: the strided lattice of one residue class is a plain 5-D box of the row-major plane --
+//   dims {floats of an s-pixel cell, column parity, column pair, row within cell, lattice row} -- so one thread issues
+//   8 cp.async.bulk.tensor copies (4 planes x 2 column parities) per block and nobody computes a single tap address.
+//   The two parities land in separate halves so that a quarter-warp reads 8 consecutive float4 (lane = (ap, c));
+//   out-of-range coordinates are zero-filled by the hardware and only border tiles run a fix-up pass (lum = 3e38).
+//   Tiles that need rows owned by another GPU (sharded frames) fall back to per-thread cp.async from the owner's memory.
 constexpr int AT_C = 2, AT_TX = 2, AT_TY = 4;
 // Tile shape <LX, LY> (lattice points per block, LX * LY = 512): 16x32 for fine levels, 32x16 when the lattice of a
 // residue class is short (coarse levels: 34 lattice rows at step 32 for 1080 rows; narrow strips of a sharded frame).
 template <int LX, int LY> struct AtShape {
     static constexpr int SW = LX + 4, SH = LY + 4;                  // staged lattice points (tile + 2-point apron)
     static constexpr int THREADS = (LX / AT_TX) * (LY / AT_TY) * AT_C;
-    static constexpr int TILE = SW * SH * AT_C;
-    static constexpr int PLANE = SW * SH + 4;                       // float4 per column plane; +4 so that the two planes land in
-                                                                    // different bank groups when a warp stages (c, ta) pairs
-    static constexpr int ARR = PLANE * AT_C;
-    static constexpr int SMEM = ARR * 48;
-    __device__ static __forceinline__ int idx(int c, int tb, int ta) { return c * PLANE + (tb * 2 + (ta & 1)) * (SW / 2) + (ta >> 1); }
+    static constexpr int TILE = SW * SH * AT_C;                     // taps
+    static constexpr int HALF = SH * (SW / 2) * AT_C;               // taps of one column parity = one TMA box
+    static constexpr int SMEM = TILE * 48 + 16;                     // + mbarrier
+    // [column parity][lattice row][column pair][c]  -- the order a TMA box arrives in
+    __device__ static __forceinline__ int idx(int c, int tb, int ta) { return (ta & 1) * HALF + (tb * (SW / 2) + (ta >> 1)) * AT_C + c; }
 };
+static_assert(AtShape<16, 32>::HALF * 8 % 128 == 0 && AtShape<32, 16>::HALF * 8 % 128 == 0, "TMA destinations must be 128-byte aligned");
+
 __device__ __forceinline__ float sqrt_approx(float x) {
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
 
 struct AtrousT {
     AtrousK k;
     RowOwner ro;                // multi-GPU: which rank owns a row, and that rank's base pointers
-    PeerPtr<const float4> p_cv; PeerPtr<const float> p_lum; PeerPtr<const float4> p_gnp; PeerPtr<const float2> p_gzl;
+    PeerPtr<const float4> p_cv; PeerPtr<const float2> p_lv; PeerPtr<const float4> p_gnp; PeerPtr<const float2> p_gzl;
+    int me;
     int b_first;        // first lattice row index covered by the grid (row_begin / step)
     int ncg;            // column groups per class row: step / C
+    int use_tma;
     const float *kl;    // per-pixel luminance-weight scale from atrous_kl_kernel
+    alignas(64) CUtensorMap tm_cv, tm_np, tm_zl, tm_lv;
 };
 
 // Pre-pass of a level: per-pixel luminance-weight scale  kl = log2(e) / (sqrt(max(blur3x3(variance), 0)) * sigma_l + 1e-6)
 // (denoise.cu:100-118,143). The 3x3 Gaussian lives in PIXEL space, i.e. across residue classes, so it is done here where
-// it is coalesced instead of per lattice point inside the tiled kernel. 4 B read (L1-shared) + 4 B written per pixel.
+// it is coalesced instead of per lattice point inside the tiled kernel. 8 B read (L1-shared) + 4 B written per pixel.
 __global__ void __launch_bounds__(256)
-atrous_kl_kernel(const __grid_constant__ PeerPtr<const float> varp, const __grid_constant__ RowOwner ro, float *__restrict__ kl,
+atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_constant__ RowOwner ro, float *__restrict__ kl,
                  int W, int H, int row_begin, int row_end, int blur_variance, float sigma_c) {
-    // one thread = 4 consecutive pixels of a row: 3 rows x (left neighbour, float4, right neighbour) from the dense plane
+    // one thread = 4 consecutive pixels of a row: 3 rows x (left neighbour, 4 pixels, right neighbour)
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     if (x0 >= W || y >= row_end) return;
@@ -178,11 +185,13 @@ atrous_kl_kernel(const __grid_constant__ PeerPtr<const float> varp, const __grid
 #pragma unroll
         for (int i = 0; i < 6; i++) v[r][i] = 0.f;
         if (rok[r]) {
-            const float *row = varp.p[owner_of(ro, ly)] + (size_t)ly * W;
-            if (((W & 3) == 0) && x0 + 3 < W) { const float4 m = __ldg(reinterpret_cast<const float4 *>(row + x0)); v[r][1] = m.x; v[r][2] = m.y; v[r][3] = m.z; v[r][4] = m.w; }
-            else for (int i = 0; i < 4; i++) if (x0 + i < W) v[r][1 + i] = __ldg(row + x0 + i);
-            if (x0 > 0) v[r][0] = __ldg(row + x0 - 1);
-            if (x0 + 4 < W) v[r][5] = __ldg(row + x0 + 4);
+            const float2 *row = lv.p[owner_of(ro, ly)] + (size_t)ly * W;
+            if (((W & 1) == 0) && x0 + 3 < W) {
+                const float4 m0 = __ldg(reinterpret_cast<const float4 *>(row + x0)), m1 = __ldg(reinterpret_cast<const float4 *>(row + x0 + 2));
+                v[r][1] = m0.y; v[r][2] = m0.w; v[r][3] = m1.y; v[r][4] = m1.w;
+            } else for (int i = 0; i < 4; i++) if (x0 + i < W) v[r][1 + i] = __ldg(&row[x0 + i].y);
+            if (x0 > 0) v[r][0] = __ldg(&row[x0 - 1].y);
+            if (x0 + 4 < W) v[r][5] = __ldg(&row[x0 + 4].y);
         }
     }
     float out[4];
@@ -243,17 +252,17 @@ __device__ __forceinline__ void at_pair(const AtTap &T, const AtCentre &C, AtAcc
 // One tap column (window column `tt` of the thread's 6) against the thread's 2 x 4 centres. DO0/DO1 select which of the
 // two centre columns the tap column reaches (|i| <= 2), so the edge columns are peeled without wasted work.
 template <class SH, bool DO0, bool DO1>
-__device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np, const float4 *s_zl, int c, int row0, int col,
+__device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np, const float2 *s_zl, const float2 *s_lv, int c, int row0, int col,
                                           const AtCentre (&C)[AT_TX][AT_TY], AtAcc (&A)[AT_TX][AT_TY], float hi0, float hi1) {
     // h = hi * hj with hj in {3/8, 1/4, 1/16} for |j| = 0, 1, 2
     const float h0[3] = {hi0 * 0.375f, hi0 * 0.25f, hi0 * 0.0625f}, h1[3] = {hi1 * 0.375f, hi1 * 0.25f, hi1 * 0.0625f};
 #pragma unroll
     for (int u = 0; u < AT_TY + 4; u++) {
         const int si = SH::idx(c, row0 + u, col);
-        const float4 np = s_np[si], zl = s_zl[si];
+        const float4 np = s_np[si];
         AtTap T;
         T.cv = s_cv[si];
-        T.nx_px = make_float2(np.x, np.y); T.ny_py = make_float2(np.z, np.w); T.nz_pz = make_float2(zl.x, zl.y); T.lum = zl.z;
+        T.nx_px = make_float2(np.x, np.y); T.ny_py = make_float2(np.z, np.w); T.nz_pz = s_zl[si]; T.lum = s_lv[si].x;
 #pragma unroll
         for (int cb = 0; cb < AT_TY; cb++) {
             const int j = u - 2 - cb, aj = j < 0 ? -j : j;
@@ -264,55 +273,96 @@ __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np
     }
 }
 
+namespace cde = cuda::device::experimental;
+
 template <int LX, int LY>
 __global__ void __launch_bounds__((AtShape<LX, LY>::THREADS), 3)
 atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     using SH = AtShape<LX, LY>;
-    constexpr int AT_LX = LX, AT_LY = LY, AT_SW = SH::SW, AT_SH = SH::SH, AT_ARR = SH::ARR, AT_THREADS = SH::THREADS;
-    extern __shared__ __align__(16) float4 at_smem[];
-    // per tap: {r,g,b,var}  {kn*nx, kx*px, kn*ny, kx*py}  {kn*nz, kx*pz, lum, -}  (the G-buffer part arrives pre-scaled)
-    float4 *s_cv = at_smem, *s_np = at_smem + AT_ARR, *s_zl = at_smem + 2 * AT_ARR;
+    constexpr int AT_LX = LX, AT_SW = SH::SW, AT_SH = SH::SH, AT_THREADS = SH::THREADS, TILE = SH::TILE, HALF = SH::HALF;
+    extern __shared__ __align__(128) unsigned char at_smem_raw[];
+    float4 *s_cv = reinterpret_cast<float4 *>(at_smem_raw), *s_np = s_cv + TILE;
+    float2 *s_zl = reinterpret_cast<float2 *>(s_np + TILE), *s_lv = s_zl + TILE;
+    using barrier_t = cuda::barrier<cuda::thread_scope_block>;
+    barrier_t &bar = *reinterpret_cast<barrier_t *>(at_smem_raw + TILE * 48);
     const AtrousK &k = t.k;
     const int W = k.W, H = k.H, step = k.step;
     const int cg = blockIdx.x % t.ncg, tile_x = blockIdx.x / t.ncg;
     const int yc = blockIdx.y % step, tile_y = blockIdx.y / step;
     const int X0 = cg * AT_C;
-    const int a0 = tile_x * AT_LX - 2, b0 = t.b_first + tile_y * AT_LY - 2;
+    const int a0 = tile_x * AT_LX - 2, b0 = t.b_first + tile_y * LY - 2;
     const int tid = threadIdx.x;
 
-    // ---- stage tile + apron with cp.async (LDGSTS): every thread queues all of its 16-byte copies back to back and
-    // none of the data passes through registers, so a block exposes ONE memory round trip instead of one per loop trip.
-    // Out-of-image taps: zero-filled colour/geometry and lum = 3e38 (exponent overflows, ex2(-inf) = 0). ----
-    // Each of the first 120 threads owns one (lattice column, sub-column) of the tile and walks down its 36 rows in
-    // steps of 3: everything that depends on x is computed once, per row there is one bounds test and one owner lookup.
-    constexpr int ST_STRIDE = AT_THREADS / (AT_SW * AT_C);      // rows advanced per trip (3 for 16x32, 1 for 32x16)
-    if (tid < ST_STRIDE * AT_SW * AT_C) {
-        const int slot = tid % (AT_SW * AT_C), r0 = tid / (AT_SW * AT_C);
-        const int c = slot % AT_C, ta = slot / AT_C;
-        const int x = X0 + (a0 + ta) * step + c;
-        const bool x_ok = a0 + ta >= 0 && x < W;
-        const int y_lo = max(0, k.row_begin - 2 * step), y_hi = min(H, k.row_end + 2 * step);
-#pragma unroll 4
-        for (int tb = r0; tb < AT_SH; tb += ST_STRIDE) {
-            const int y = yc + (b0 + tb) * step;
-            const int si = SH::idx(c, tb, ta);
-            // only rows a live centre of this strip can reach (strip +- 2 steps): a tile of a coarse level spans far more
-            // rows than the strip, and for a sharded frame those rows would be fetched from a peer for nothing
-            if (x_ok && b0 + tb >= 0 && y >= y_lo && y < y_hi) {
-                const int q = x + y * W, o = owner_of(t.ro, y);     // rows of other strips come straight from their owner
-                cp_async16(&s_cv[si], &t.p_cv.p[o][q]);
-                cp_async16(&s_np[si], &t.p_gnp.p[o][q]);
-                cp_async8(&s_zl[si], &t.p_gzl.p[o][q]);
-                cp_async4(&s_zl[si].z, &t.p_lum.p[o][q]);
-            } else {
-                s_cv[si] = make_float4(0.f, 0.f, 0.f, 0.f); s_np[si] = make_float4(0.f, 0.f, 0.f, 0.f);
-                s_zl[si] = make_float4(0.f, 0.f, 3e38f, 0.f);
+    // rows a live centre of this strip can reach (strip +- 2 steps); a coarse tile spans far more rows than the strip
+    const int y_lo = max(0, k.row_begin - 2 * step), y_hi = min(H, k.row_end + 2 * step);
+    // does the tile need rows owned by another rank? (first/last needed row of this tile)
+    const int yt0 = max(y_lo, yc + max(b0, 0) * step), yt1 = min(y_hi - 1, yc + (b0 + AT_SH - 1) * step);
+    const bool remote = t.ro.world > 1 && yt0 <= yt1 && (yt0 < t.ro.start[t.me] || yt1 >= t.ro.start[t.me + 1]);
+    const bool tma = t.use_tma && !remote;
+
+    if (tma) {
+        if (tid == 0) {
+            init(&bar, AT_THREADS);
+            cde::fence_proxy_async_shared_cta();
+        }
+        __syncthreads();
+        barrier_t::arrival_token token;
+        if (tid == 0) {
+#pragma unroll
+            for (int par = 0; par < 2; par++) {     // a0 is even: window column ta has parity ta & 1 and pair index a0/2 + ta/2
+                cde::cp_async_bulk_tensor_5d_global_to_shared(s_cv + par * HALF, &t.tm_cv, 4 * X0, par, a0 >> 1, yc, b0, bar);
+                cde::cp_async_bulk_tensor_5d_global_to_shared(s_np + par * HALF, &t.tm_np, 4 * X0, par, a0 >> 1, yc, b0, bar);
+                cde::cp_async_bulk_tensor_5d_global_to_shared(s_zl + par * HALF, &t.tm_zl, 2 * X0, par, a0 >> 1, yc, b0, bar);
+                cde::cp_async_bulk_tensor_5d_global_to_shared(s_lv + par * HALF, &t.tm_lv, 2 * X0, par, a0 >> 1, yc, b0, bar);
+            }
+            token = cuda::device::barrier_arrive_tx(bar, 1, TILE * 48);
+        } else {
+            token = bar.arrive();
+        }
+        bar.wait(std::move(token));
+        // border tiles: the hardware zero-filled what lies outside the tensor; taps outside the IMAGE (columns >= W inside
+        // the rounded-up lattice, padded rows >= H) get zeros too, and every invalid tap gets lum = 3e38
+        const bool border = a0 < 0 || X0 + (a0 + AT_SW - 1) * step + AT_C > W || b0 < 0 || yc + (b0 + AT_SH - 1) * step >= H;
+        if (border) {
+            for (int n = tid; n < TILE; n += AT_THREADS) {
+                const int c = n % AT_C, ta = (n / AT_C) % AT_SW, tb = n / (AT_C * AT_SW);
+                const int x = X0 + (a0 + ta) * step + c, y = yc + (b0 + tb) * step;
+                if (!(a0 + ta >= 0 && b0 + tb >= 0 && x < W && y < H)) {
+                    const int si = SH::idx(c, tb, ta);
+                    s_cv[si] = make_float4(0.f, 0.f, 0.f, 0.f); s_np[si] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    s_zl[si] = make_float2(0.f, 0.f); s_lv[si] = make_float2(3e38f, 0.f);
+                }
             }
         }
+    } else {
+        // per-thread cp.async (LDGSTS): rows of other strips come straight from their owner's memory over NVLink.
+        // Each of the first ST_STRIDE * 2 * SW threads owns one (lattice column, sub-column) and walks down the rows.
+        constexpr int ST_STRIDE = AT_THREADS / (AT_SW * AT_C);
+        if (tid < ST_STRIDE * AT_SW * AT_C) {
+            const int slot = tid % (AT_SW * AT_C), r0 = tid / (AT_SW * AT_C);
+            const int c = slot % AT_C, ta = slot / AT_C;
+            const int x = X0 + (a0 + ta) * step + c;
+            const bool x_ok = a0 + ta >= 0 && x < W;
+#pragma unroll 4
+            for (int tb = r0; tb < AT_SH; tb += ST_STRIDE) {
+                const int y = yc + (b0 + tb) * step;
+                const int si = SH::idx(c, tb, ta);
+                if (x_ok && b0 + tb >= 0 && y >= y_lo && y < y_hi) {
+                    const int q = x + y * W, o = owner_of(t.ro, y);
+                    cp_async16(&s_cv[si], &t.p_cv.p[o][q]);
+                    cp_async16(&s_np[si], &t.p_gnp.p[o][q]);
+                    cp_async8(&s_zl[si], &t.p_gzl.p[o][q]);
+                    cp_async8(&s_lv[si], &t.p_lv.p[o][q]);
+                } else {
+                    s_cv[si] = make_float4(0.f, 0.f, 0.f, 0.f); s_np[si] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    s_zl[si] = make_float2(0.f, 0.f); s_lv[si] = make_float2(3e38f, 0.f);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
 
-    const int ap = tid % (AT_LX / 2), c = (tid / (AT_LX / 2)) & 1, bq = tid / AT_LX;
+    const int c = tid & 1, ap = (tid >> 1) % (AT_LX / 2), bq = tid / AT_LX;
     // centres' kl from the pre-pass plane, issued before the barrier
     float c_kl[AT_TX][AT_TY];
     bool live = false;
@@ -325,7 +375,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
             live |= ok;
             c_kl[ca][cb] = ok ? __ldg(&t.kl[x + y * W]) : 0.f;
         }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (!live) return;
 
@@ -336,9 +386,9 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
 #pragma unroll
         for (int cb = 0; cb < AT_TY; cb++) {
             const int si = SH::idx(c, 4 * bq + cb + 2, 2 * ap + ca + 2);
-            const float4 np = s_np[si], zl = s_zl[si];
+            const float4 np = s_np[si]; const float2 zl = s_zl[si];
             C[ca][cb].nx_px = make_float2(-np.x, -np.y); C[ca][cb].ny_py = make_float2(-np.z, -np.w);
-            C[ca][cb].nz_pz = make_float2(-zl.x, -zl.y); C[ca][cb].lum = zl.z; C[ca][cb].kl = c_kl[ca][cb];
+            C[ca][cb].nz_pz = make_float2(-zl.x, -zl.y); C[ca][cb].lum = s_lv[si].x; C[ca][cb].kl = c_kl[ca][cb];
             A[ca][cb].w_w2 = make_float2(0.f, 0.f); A[ca][cb].b_v = make_float2(0.f, 0.f); A[ca][cb].r = 0.f; A[ca][cb].g = 0.f;
         }
 
@@ -347,15 +397,15 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     // columns 0 and 5 reach one centre column each and are peeled. The centre tap takes the generic path: all
     // differences are 0, sqrt(0) = 0, ex2(-0) = 1 exactly. ----
     const int row0 = 4 * bq, col0 = 2 * ap;
-    at_column<SH, true, false>(s_cv, s_np, s_zl, c, row0, col0 + 0, C, A, 0.0625f, 0.f);        // i = -2 for centre column 0
+    at_column<SH, true, false>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + 0, C, A, 0.0625f, 0.f);        // i = -2 for centre column 0
 #pragma unroll 1
     for (int tt = 1; tt <= 4; tt++) {
         const int i0 = tt - 2, i1 = tt - 3;
         const float hi0 = i0 == 0 ? 0.375f : ((i0 == 1 || i0 == -1) ? 0.25f : 0.0625f);
         const float hi1 = i1 == 0 ? 0.375f : ((i1 == 1 || i1 == -1) ? 0.25f : 0.0625f);
-        at_column<SH, true, true>(s_cv, s_np, s_zl, c, row0, col0 + tt, C, A, hi0, hi1);
+        at_column<SH, true, true>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + tt, C, A, hi0, hi1);
     }
-    at_column<SH, false, true>(s_cv, s_np, s_zl, c, row0, col0 + 5, C, A, 0.f, 0.0625f);        // i = +2 for centre column 1
+    at_column<SH, false, true>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + 5, C, A, 0.f, 0.0625f);        // i = +2 for centre column 1
 
     // ---- outputs: all 8 results (incl. the fp64 luminance of the new colour, a long dependent chain) are computed as
     // straight-line code first, then stored under predicates, so the 8 chains overlap ----
@@ -397,7 +447,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
                 d[0] = o[ca][cb].x; d[1] = o[ca][cb].y; d[2] = o[ca][cb].z;
                 k.var_out[p] = o[ca][cb].w;
             }
-            if (k.cv_out) { k.cv_out[p] = o[ca][cb]; k.lum_out[p] = ol[ca][cb]; k.varp_out[p] = o[ca][cb].w; }
+            if (k.cv_out) { k.cv_out[p] = o[ca][cb]; k.lv_out[p] = make_float2(ol[ca][cb], o[ca][cb].w); }
         }
 }
 
@@ -410,11 +460,57 @@ void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx) {
     *kx = (float)(log2e / ((double)sigma_x + 1e-6));
 }
 
+// ---- TMA descriptors ------------------------------------------------------------------------------------------------
+// The lattice of residue class (., yc) with sub-columns [X0, X0+2) of a row-major plane with `fpp` floats per pixel is
+// the 5-D tensor  {j: fpp*s floats of one s-pixel cell | parity of the cell | cell pair | row inside the s-row band | band}
+// with byte strides {-, fpp*4*s, fpp*4*2s, fpp*4*W, fpp*4*s*W}; a tile is the box {fpp*2, 1, SW/2, 1, SH}.
+// Extents round up, so addresses may run past the image: columns >= W alias the next row (fixed up in the kernel),
+// rows >= H fall into SVGF_PAD_ROWS rows of zeroed padding behind every plane.
+typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+enum { TM_PLANES = 8, TM_LEVELS = SVGF_MAX_LEVELS + 1, TM_SHAPES = 2 };
+static inline CUtensorMap *tmap_at(svgf_ctx *c, int plane, int level, int shape) {
+    return static_cast<CUtensorMap *>(c->tmaps) + ((plane * TM_LEVELS + level) * TM_SHAPES + shape);
+}
+
+int atrous_build_tensor_maps(svgf_ctx *c) {
+    c->tma_ok = 0;
+    if (c->W & 1) return 0;         // 8 B/pixel planes need a 16-byte row pitch; odd widths use the cp.async loader
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    encode_fn_t encode = reinterpret_cast<encode_fn_t>(fn);
+    if (!c->tmaps) c->tmaps = aligned_alloc(64, sizeof(CUtensorMap) * TM_PLANES * TM_LEVELS * TM_SHAPES);
+    if (!c->tmaps) return 0;
+    void *planes[TM_PLANES] = {c->cv[0], c->cv[1], c->cv[2], c->lv[0], c->lv[1], c->lv[2], c->gnp, c->gzl};
+    const int fpp[TM_PLANES] = {4, 4, 4, 2, 2, 2, 4, 2};
+    const int sw[TM_SHAPES] = {AtShape<16, 32>::SW, AtShape<32, 16>::SW}, sh[TM_SHAPES] = {AtShape<16, 32>::SH, AtShape<32, 16>::SH};
+    for (int pl = 0; pl < TM_PLANES; pl++)
+        for (int level = 1; level <= SVGF_MAX_LEVELS; level++)
+            for (int shp = 0; shp < TM_SHAPES; shp++) {
+                const cuuint64_t s = 1ull << level, W = c->W, H = c->H, f = fpp[pl];
+                const cuuint64_t dims[5] = {f * s, 2, (W + 2 * s - 1) / (2 * s), s, (H + s - 1) / s};
+                const cuuint64_t strides[4] = {f * 4 * s, f * 4 * 2 * s, f * 4 * W, f * 4 * s * W};
+                const cuuint32_t box[5] = {(cuuint32_t)(f * AT_C), 1, (cuuint32_t)(sw[shp] / 2), 1, (cuuint32_t)sh[shp]};
+                const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                CUresult r = encode(tmap_at(c, pl, level, shp), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, planes[pl], dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return 0;
+            }
+    c->tma_ok = 1;
+    return 1;
+}
+
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     AtrousK k;
-    k.cv_in = a.cv_in; k.cv_out = a.cv_out; k.lum_in = a.lum_in; k.lum_out = a.lum_out; k.varp_out = a.varp_out;
+    k.cv_in = a.cv_in; k.cv_out = a.cv_out; k.lv_in = a.lv_in; k.lv_out = a.lv_out;
     k.nrm = a.nrm; k.pos = a.pos; k.alb = a.alb;
     k.gnp = a.gnp; k.gzl = a.gzl;
     k.denoised_out = a.denoised_out; k.var_out = a.var_out;
@@ -428,15 +524,15 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
         return cudaGetLastError();
     }
     AtrousT t;
-    t.k = k; t.kl = c->kl; t.ro = c->rows;
+    t.k = k; t.kl = c->kl; t.ro = c->rows; t.me = c->shard.rank;
+    PeerPtr<const float2> pv;
     for (int r = 0; r < SVGF_MAX_RANKS; r++) {
         const bool peer = r < c->shard.world && a.src_slot >= 0;
-        t.p_cv.p[r] = peer ? c->p_cv[a.src_slot].p[r] : a.cv_in; t.p_lum.p[r] = peer ? c->p_lum[a.src_slot].p[r] : a.lum_in;
+        t.p_cv.p[r] = peer ? c->p_cv[a.src_slot].p[r] : a.cv_in; t.p_lv.p[r] = peer ? c->p_lv[a.src_slot].p[r] : a.lv_in;
         t.p_gnp.p[r] = peer ? c->p_gnp.p[r] : a.gnp; t.p_gzl.p[r] = peer ? c->p_gzl.p[r] : a.gzl;
+        pv.p[r] = t.p_lv.p[r];
     }
     {
-        PeerPtr<const float> pv;
-        for (int r = 0; r < SVGF_MAX_RANKS; r++) pv.p[r] = (r < c->shard.world && a.src_slot >= 0) ? c->p_varp[a.src_slot].p[r] : a.var_in;
         dim3 b(32, 8), g(((c->W + 3) / 4 + 31) / 32, (rows + 7) / 8);
         atrous_kl_kernel<<<g, b, 0, c->stream>>>(pv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c);
     }
@@ -449,13 +545,22 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     auto padded = [&](int lx, int ly, int wy) {
         return (double)(((lat_w + lx - 1) / lx) * lx) * (((lat_rows + wy - 1) / wy) * wy) + 0.15 * (double)(((lat_w + lx - 1) / lx) * lx) * (((lat_rows + ly - 1) / ly) * ly);
     };
+    const int shape = padded(16, 32, 8) <= padded(32, 16, 4) ? 0 : 1;
+    t.use_tma = c->tma_ok && a.src_slot >= 0 && c->atrous_variant != 3;
+    if (t.use_tma) {
+        t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, 3 + a.src_slot, a.level, shape);
+        t.tm_np = *tmap_at(c, 6, a.level, shape); t.tm_zl = *tmap_at(c, 7, a.level, shape);
+    } else {
+        memset(&t.tm_cv, 0, sizeof(CUtensorMap)); memset(&t.tm_lv, 0, sizeof(CUtensorMap));
+        memset(&t.tm_np, 0, sizeof(CUtensorMap)); memset(&t.tm_zl, 0, sizeof(CUtensorMap));
+    }
     if (!c->atrous_attr_set) {      // per context (= per device)
         cudaError_t e = cudaFuncSetAttribute(atrous_tiled_kernel<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtShape<16, 32>::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(atrous_tiled_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtShape<32, 16>::SMEM);
         if (e != cudaSuccess) return e;
         c->atrous_attr_set = true;
     }
-    if (padded(16, 32, 8) <= padded(32, 16, 4)) {
+    if (shape == 0) {
         dim3 g(((lat_w + 15) / 16) * t.ncg, ((lat_rows + 31) / 32) * step);
         atrous_tiled_kernel<16, 32><<<g, AtShape<16, 32>::THREADS, AtShape<16, 32>::SMEM, c->stream>>>(t);
     } else {

@@ -42,7 +42,7 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
                 const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
                 const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,
                 const __grid_constant__ PeerPtr<int> hlen_tab, const __grid_constant__ RowOwner ro, int me,
-                float4 *__restrict__ acc_cv, float *__restrict__ acc_lum, float *__restrict__ acc_var, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
+                float4 *__restrict__ acc_cv, float2 *__restrict__ acc_lv, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
                 float color_alpha_min, float moment_alpha_min) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
@@ -127,29 +127,27 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
             const float ar = sr * color_alpha + pr * (1.0f - color_alpha), ag = sg * color_alpha + pg * (1.0f - color_alpha),
                         ab = sb * color_alpha + pb * (1.0f - color_alpha);
             acc_cv[p] = make_float4(ar, ag, ab, variance > 0.0f ? variance : 0.0f);
-            acc_var[p] = variance > 0.0f ? variance : 0.0f;
-            acc_lum[p] = (float)(0.2126 * ar + 0.7152 * ag + 0.0722 * ab);      // what the a-trous taps will read (denoise.cu:121,138)
+            // luminance as the a-trous taps will read it (denoise.cu:121,138), and the variance once more for the 3x3 blur
+            acc_lv[p] = make_float2((float)(0.2126 * ar + 0.7152 * ag + 0.0722 * ab), variance > 0.0f ? variance : 0.0f);
             return;
         }
     }
     hlen_out[p] = 1;
     mom_acc[p] = make_float2(luminance, luminance * luminance);
     acc_cv[p] = make_float4(sr, sg, sb, 100.0f);
-    acc_var[p] = 100.0f;
-    acc_lum[p] = luminance;
+    acc_lv[p] = make_float2(luminance, 100.0f);
 }
 
 __global__ void __launch_bounds__(256)
 no_temporal_kernel(int W, int row_begin, int row_end, const float *__restrict__ image, float4 *__restrict__ acc_cv,
-                   float *__restrict__ acc_lum, float *__restrict__ acc_var) {
+                   float2 *__restrict__ acc_lv) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= row_end) return;
     const size_t p = x + (size_t)y * W;
     const float r = image[3 * p], g = image[3 * p + 1], b = image[3 * p + 2];
     acc_cv[p] = make_float4(r, g, b, 10.0f);
-    acc_var[p] = 10.0f;
-    acc_lum[p] = (float)(0.2126 * r + 0.7152 * g + 0.0722 * b);
+    acc_lv[p] = make_float2((float)(0.2126 * r + 0.7152 * g + 0.0722 * b), 10.0f);
 }
 
 // clamp((int)(v * 255.0), 0, 255) with the reference's DOUBLE product (pathtrace.cu:60-62), evaluated in fp32:
@@ -254,23 +252,23 @@ inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (
 
 cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const PeerPtr<float4> &nrm_prev,
                             const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
-                            const PeerPtr<int> &hlen_in, float4 *acc_cv, float *acc_lum, float *acc_var, float2 *mom_acc, int *hlen_out,
+                            const PeerPtr<int> &hlen_in, float4 *acc_cv, float2 *acc_lv, float2 *mom_acc, int *hlen_out,
                             const float *prev_viewmat, float color_alpha, float moment_alpha) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     Mat4 vm; for (int i = 0; i < 16; i++) vm.m[i] = prev_viewmat[i];
     dim3 b(32, 8);
     temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
-                                                                 nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lum, acc_var, mom_acc,
+                                                                 nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lv, mom_acc,
                                                                  hlen_out, vm, color_alpha, moment_alpha);
     return cudaGetLastError();
 }
 
-cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float *acc_lum, float *acc_var) {
+cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float2 *acc_lv) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     dim3 b(32, 8);
-    no_temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->shard.row_begin, c->shard.row_end, image, acc_cv, acc_lum, acc_var);
+    no_temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->shard.row_begin, c->shard.row_end, image, acc_cv, acc_lv);
     return cudaGetLastError();
 }
 

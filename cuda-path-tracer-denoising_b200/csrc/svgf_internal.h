@@ -66,7 +66,8 @@ __host__ __device__ inline int owner_of(const RowOwner &ro, int y) {
     return r;
 }
 enum { SVGF_STAGE_RT = 0, SVGF_STAGE_TEMPORAL = 1, SVGF_STAGE_LEVEL0 = 1 /* + level */, SVGF_STAGE_FRAME = 9, SVGF_NUM_STAGES = 10 };
-enum { SVGF_IPC_NBUF = 18 };    // cv[3] lum[3] varp[3] nrm[2] mom[2] hlen[2] gnp gzl flags
+enum { SVGF_IPC_NBUF = 15 };    // cv[3] lv[3] nrm[2] mom[2] hlen[2] gnp gzl flags
+enum { SVGF_PAD_ROWS = 130 };   // rows of zeroed padding behind the planes the TMA tile loads address (lattice dims round up)
 
 struct svgf_ctx {
     int device = 0;
@@ -79,16 +80,19 @@ struct svgf_ctx {
     svgf_shard shard{0, 1, 0, 0};
     RowOwner rows{1, {0}};
     // peer views of every plane another rank may read (index [rank]; [shard.rank] is this context's own pointer)
-    PeerPtr<float4> p_cv[3]; PeerPtr<float> p_lum[3]; PeerPtr<float> p_varp[3]; PeerPtr<float4> p_nrm[2]; PeerPtr<float2> p_mom[2]; PeerPtr<int> p_hlen[2];
+    PeerPtr<float4> p_cv[3]; PeerPtr<float2> p_lv[3]; PeerPtr<float4> p_nrm[2]; PeerPtr<float2> p_mom[2]; PeerPtr<int> p_hlen[2];
     PeerPtr<float4> p_gnp; PeerPtr<float2> p_gzl; PeerPtr<unsigned> p_flags;
     unsigned *flags = nullptr;          // [SVGF_MAX_RANKS][SVGF_NUM_STAGES] sequence numbers written by the peers, + 1 error word
     unsigned seq = 0;                   // frame sequence number (identical on all ranks)
     std::vector<void *> ipc_opened;
 
     float4 *cv[3] = {nullptr, nullptr, nullptr};
-    float *lum[3] = {nullptr, nullptr, nullptr};    // luminance of cv[i].rgb, the reference's fp64 formula (denoise.cu:121)
-    float *varp[3] = {nullptr, nullptr, nullptr};   // copy of cv[i].w as a dense float plane: the 3x3 variance blur reads 4 B/px, coalesced
-    int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled
+    // {luminance of cv[i].rgb in the reference's fp64 formula (denoise.cu:121), copy of cv[i].w}: what a tap needs besides
+    // colour, and what the 3x3 variance blur reads (8 B/px, coalesced)
+    float2 *lv[3] = {nullptr, nullptr, nullptr};
+    // TMA descriptors (CUtensorMap, 128 B each) for the lattice tiles of cv[3], lv[3], gnp, gzl: [plane 8][level 1..7][shape 2]
+    void *tmaps = nullptr; int tma_ok = 0;
+    int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled (TMA tile loads), 3 = lattice-tiled (cp.async)
     bool atrous_attr_set = false;
     int rt_variant = 0;                 // 0 = state-machine kernel, 1 = wavefront (stage kernels + ballot-compacted queues)
     void *wf_mem = nullptr;             // wavefront ray/hit/queue buffers (allocated on first use)
@@ -152,16 +156,16 @@ void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx);
 cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out);
 cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const PeerPtr<float4> &nrm_prev,
                             const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
-                            const PeerPtr<int> &hlen_in, float4 *acc_cv, float *acc_lum, float *acc_var, float2 *mom_acc, int *hlen_out,
+                            const PeerPtr<int> &hlen_in, float4 *acc_cv, float2 *acc_lv, float2 *mom_acc, int *hlen_out,
                             const float *prev_viewmat, float color_alpha, float moment_alpha);
 cudaError_t launch_signal(svgf_ctx *c, int stage);
 cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq);
-cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float *acc_lum, float *acc_var);
+cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float2 *acc_lv);
 struct AtrousArgs {
     int src_slot;                                   // cv/lum input = c->p_cv[src_slot] / c->p_lum[src_slot] (peer-readable)
     const float4 *cv_in; float4 *cv_out;            // cv_out may be null on the last level
-    const float *lum_in; float *lum_out;
-    const float *var_in; float *varp_out;           // dense variance planes (var_in only used when there are no peers)
+    const float2 *lv_in; float2 *lv_out;            // {luminance, variance} planes; slot numbers select the TMA descriptors
+    int dst_slot;
     const float4 *nrm, *pos, *alb;
     const float4 *gnp; const float2 *gzl;
     float *denoised_out; float *var_out;            // last level only (AoS vec3 + float plane)
@@ -176,4 +180,5 @@ cudaError_t launch_aos_to_soa(svgf_ctx *c, const svgf_gbuffer_texel *g, float4 *
 cudaError_t launch_soa_to_aos(svgf_ctx *c, const float4 *nrm, const float4 *pos, const float4 *alb, svgf_gbuffer_texel *g);
 cudaError_t launch_copy_f3(svgf_ctx *c, float *dst, const float *src);
 
+int atrous_build_tensor_maps(svgf_ctx *c);
 void svgf_view_matrix(const svgf_camera *cam, float *out16);
