@@ -75,8 +75,9 @@ __device__ __forceinline__ F3 getPointOnRay(const Ray &r, float t) {   // inters
     return r.origin + (t - .0001f) * normalize(r.direction);
 }
 
-// intersections.h:50-92
-__device__ float boxIntersectionTest(const GeomD &box, const Ray &r, F3 &normal) {
+// intersections.h:50-92. Returns the reference's t (world-space distance to the pulled-back hit point); the face normal
+// is only computed for the winning geom (box_normal), from the axis/sign recorded here.
+__device__ float boxIntersectionTest(const GeomD &box, const Ray &r, int &axis, float &sign) {
     Ray q;
     q.origin = multiplyMV(box.inverseTransform, r.origin, 1.0f);
     q.direction = normalize(multiplyMV(box.inverseTransform, r.direction, 0.0f));
@@ -97,15 +98,18 @@ __device__ float boxIntersectionTest(const GeomD &box, const Ray &r, F3 &normal)
     if (tmax >= tmin && tmax > 0) {
         if (tmin <= 0) { tmin = tmax; tmin_axis = tmax_axis; tmin_s = tmax_s; }
         F3 ip = multiplyMV(box.transform, getPointOnRay(q, tmin), 1.0f);
-        F3 n = mk(tmin_axis == 0 ? tmin_s : 0.f, tmin_axis == 1 ? tmin_s : 0.f, tmin_axis == 2 ? tmin_s : 0.f);
-        normal = normalize(multiplyMV(box.transform, n, 0.0f));
+        axis = tmin_axis; sign = tmin_s;
         return length(r.origin - ip);
     }
     return -1;
 }
+__device__ __forceinline__ F3 box_normal(const GeomD &box, int axis, float sign) {      // intersections.h:67-68,90
+    const F3 n = mk(axis == 0 ? sign : 0.f, axis == 1 ? sign : 0.f, axis == 2 ? sign : 0.f);
+    return normalize(multiplyMV(box.transform, n, 0.0f));
+}
 
-// intersections.h:104-146
-__device__ float sphereIntersectionTest(const GeomD &sphere, const Ray &r, F3 &normal) {
+// intersections.h:104-146; the normal is deferred like the box's (sphere_normal from the object-space hit point)
+__device__ float sphereIntersectionTest(const GeomD &sphere, const Ray &r, F3 &osi, bool &outside) {
     Ray rt;
     rt.origin = multiplyMV(sphere.inverseTransform, r.origin, 1.0f);
     rt.direction = normalize(multiplyMV(sphere.inverseTransform, r.direction, 0.0f));
@@ -117,15 +121,16 @@ __device__ float sphereIntersectionTest(const GeomD &sphere, const Ray &r, F3 &n
     float t1 = firstTerm + squareRoot;
     float t2 = firstTerm - squareRoot;
     float t = 0;
-    bool outside;
     if (t1 < 0 && t2 < 0) return -1;
     else if (t1 > 0 && t2 > 0) { t = fminf(t1, t2); outside = true; }
     else { t = fmaxf(t1, t2); outside = false; }
-    F3 osi = getPointOnRay(rt, t);
+    osi = getPointOnRay(rt, t);
     F3 ip = multiplyMV(sphere.transform, osi, 1.f);
-    normal = normalize(multiplyMV(sphere.invTranspose, osi, 0.f));
-    if (!outside) normal = -normal;
     return length(r.origin - ip);
+}
+__device__ __forceinline__ F3 sphere_normal(const GeomD &sphere, F3 osi, bool outside) {    // intersections.h:140-143
+    F3 n = normalize(multiplyMV(sphere.invTranspose, osi, 0.f));
+    return outside ? n : -n;
 }
 
 struct SceneView {
@@ -206,24 +211,28 @@ struct Isect {      // the live part of ShadeableIntersection (sceneStructs.h:10
     float t; F3 n; int materialId, geomId; float u, v;
 };
 
-// computeIntersection, pathtrace.cu:210-281. On a miss only t and geomId change (267-271).
+// computeIntersection, pathtrace.cu:210-281: the closest t > 0 over all geoms, ties going to the lowest geom index
+// (the reference loops in index order with a strict `<`). On a miss only t and geomId change (267-271).
+//
+// Evaluation order is re-designed for SIMT: the reference's loop makes all 32 lanes visit geom i together, and only the
+// lanes whose ray can reach it do any work in the expensive exact test. Here each lane first collects the cubes and
+// spheres its own ray can reach (slab test against conservative world bounds), then pops them one by one, so in every trip
+// of the exact-test loops all lanes are busy -- each with a different geom. The tie rule is applied explicitly, so the
+// winner is the reference's. Normals are computed for the winner only.
 __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &is) {
     float t_min = FLT_MAX;
     int hit_geom = -1;
-    F3 normal = mk(0, 0, 0);
-    float uu = 0.f, vv = 0.f;
-    // tmp_uv is only ever written by mesh hits and carried across loop iterations (pathtrace.cu:226,251,263)
-    float tmp_u = 0.f, tmp_v = 0.f;
-    bool mesh_done = false, mesh_hit = false;
-    TriBest tb; tb.t = FLT_MAX; tb.slot = -1; tb.bx = tb.by = 0.f;
-    int tri_id = -1;
+    // what the winner's deferred normal needs
+    int w_axis = 0; float w_sign = 0.f; F3 w_osi = mk(0, 0, 0); bool w_outside = true; int w_kind = -1;   // 1 cube, 0 sphere, 2 mesh
     // 1 / direction exactly as IntersectBVH forms it (intersections.h:276); also feeds the conservative bounds pre-test
     const F3 invdir = mk(1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z);
-    for (int i = 0; i < sc.n_geoms; i++) {
-        const GeomD &g = sc.geoms[i];
-        float t;
-        F3 tmp_n = mk(0, 0, 0);
-        if (g.type != 2) {
+    bool any_mesh = false;
+    for (int base = 0; base < sc.n_geoms; base += 32) {
+        unsigned cubes = 0, spheres = 0;
+        const int n = min(32, sc.n_geoms - base);
+        for (int j = 0; j < n; j++) {
+            const GeomD &g = sc.geoms[base + j];
+            if (g.type == 2) { any_mesh = true; continue; }
             // Slab test against the inflated world bounds. A NaN direction keeps every term NaN (no reject: the exact test
             // then runs as in the reference); 0 * inf only arises for a ray lying IN an inflated face plane, which is
             // >= 1e-3 outside the real surface, so dropping that NaN (fminf/fmaxf) can only reject true misses.
@@ -232,37 +241,58 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
             const float az = (g.aabb_min[2] - ray.origin.z) * invdir.z, bz = (g.aabb_max[2] - ray.origin.z) * invdir.z;
             const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-            if (tf < tn || tf < 0.f) continue;      // the exact test would return -1 (no hit): t_min is unaffected
-            // the exact t is the world distance to a point inside these bounds, so it cannot undercut a closer hit already held
-            if (tn > t_min * 1.001f + 1e-3f) continue;
+            if (tf < tn || tf < 0.f) continue;      // the exact test would return -1 (no hit)
+            if (g.type == 1) cubes |= 1u << j; else spheres |= 1u << j;
         }
-        if (g.type == 1) t = boxIntersectionTest(g, ray, tmp_n);
-        else if (g.type == 0) t = sphereIntersectionTest(g, ray, tmp_n);
-        else {
-            if (!mesh_done) {
-                mesh_done = true;
-                mesh_hit = intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb);
-                if (mesh_hit) tri_id = __float_as_int(__ldg(&sc.tri_hot[3 * tb.slot]).w);
-            }
-            t = -1.0f;
-            if (mesh_hit && tri_id >= g.tri_begin && tri_id < g.tri_end) {
-                t = tb.t;
-                // deferred Triangle::Intersect shading (sceneStructs.h:160-172): uv in the correct barycentric
-                // order, normal in the reference's permuted order -- both kept
-                const float4 c0 = __ldg(&sc.tri_cold[4 * tb.slot]), c1 = __ldg(&sc.tri_cold[4 * tb.slot + 1]);
-                const float4 c2 = __ldg(&sc.tri_cold[4 * tb.slot + 2]), c3 = __ldg(&sc.tri_cold[4 * tb.slot + 3]);
-                const float w0 = 1.0f - tb.bx - tb.by;
-                tmp_u = (c0.w * w0 + c2.w * tb.bx) + c3.y * tb.by;
-                tmp_v = (c1.w * w0 + c3.x * tb.bx) + c3.z * tb.by;
-                const float wn = 1.f - tb.bx - tb.by;
-                F3 n = (mk(c0.x, c0.y, c0.z) * tb.bx + mk(c1.x, c1.y, c1.z) * tb.by) + mk(c2.x, c2.y, c2.z) * wn;
-                tmp_n = normalize(n);
-            }
+        while (cubes) {
+            const int i = base + __ffs(cubes) - 1; cubes &= cubes - 1;
+            int axis = 0; float sign = 0.f;
+            const float t = boxIntersectionTest(sc.geoms[i], ray, axis, sign);
+            if (t > 0.0f && (t < t_min || (t == t_min && i < hit_geom))) { t_min = t; hit_geom = i; w_kind = 1; w_axis = axis; w_sign = sign; }
         }
-        if (t > 0.0f && t < t_min) { t_min = t; hit_geom = i; normal = tmp_n; uu = tmp_u; vv = tmp_v; }
+        while (spheres) {
+            const int i = base + __ffs(spheres) - 1; spheres &= spheres - 1;
+            F3 osi = mk(0, 0, 0); bool outside = true;
+            const float t = sphereIntersectionTest(sc.geoms[i], ray, osi, outside);
+            if (t > 0.0f && (t < t_min || (t == t_min && i < hit_geom))) { t_min = t; hit_geom = i; w_kind = 0; w_osi = osi; w_outside = outside; }
+        }
+    }
+    // Meshes: every MESH geom runs the same traversal of the one global BVH and accepts the closest triangle only if its id is
+    // in the geom's range (pathtrace.cu:244-255), so one traversal serves them all. Triangles at or beyond the closest cube/
+    // sphere cannot win (margin for the tie rule), which bounds the traversal.
+    float mesh_u = 0.f, mesh_v = 0.f; int mesh_owner = -1;
+    TriBest tb; tb.t = FLT_MAX; tb.slot = -1; tb.bx = tb.by = 0.f;
+    if (any_mesh && intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb)) {
+        const int tri_id = __float_as_int(__ldg(&sc.tri_hot[3 * tb.slot]).w);
+        for (int i = 0; i < sc.n_geoms && mesh_owner < 0; i++) {
+            const GeomD &g = sc.geoms[i];
+            if (g.type == 2 && tri_id >= g.tri_begin && tri_id < g.tri_end) mesh_owner = i;
+        }
+        if (mesh_owner >= 0) {
+            // uv in the correct barycentric order (sceneStructs.h:162-164); the reference's tmp_uv keeps this value for later geoms
+            const float4 c0 = __ldg(&sc.tri_cold[4 * tb.slot]), c1 = __ldg(&sc.tri_cold[4 * tb.slot + 1]);
+            const float4 c2 = __ldg(&sc.tri_cold[4 * tb.slot + 2]), c3 = __ldg(&sc.tri_cold[4 * tb.slot + 3]);
+            const float w0 = 1.0f - tb.bx - tb.by;
+            mesh_u = (c0.w * w0 + c2.w * tb.bx) + c3.y * tb.by;
+            mesh_v = (c1.w * w0 + c3.x * tb.bx) + c3.z * tb.by;
+            const float t = tb.t;
+            if (t > 0.0f && (t < t_min || (t == t_min && mesh_owner < hit_geom))) { t_min = t; hit_geom = mesh_owner; w_kind = 2; }
+        }
     }
     if (hit_geom == -1) { is.t = -1.0f; is.geomId = -1; return false; }
-    is.t = t_min; is.materialId = sc.geoms[hit_geom].materialid; is.n = normal; is.u = uu; is.v = vv; is.geomId = hit_geom;
+    F3 normal;
+    if (w_kind == 1) normal = box_normal(sc.geoms[hit_geom], w_axis, w_sign);
+    else if (w_kind == 0) normal = sphere_normal(sc.geoms[hit_geom], w_osi, w_outside);
+    else {      // Triangle::Intersect's normal, in the reference's permuted barycentric order (sceneStructs.h:168-172)
+        const float4 c0 = __ldg(&sc.tri_cold[4 * tb.slot]), c1 = __ldg(&sc.tri_cold[4 * tb.slot + 1]), c2 = __ldg(&sc.tri_cold[4 * tb.slot + 2]);
+        const float wn = 1.f - tb.bx - tb.by;
+        normal = normalize((mk(c0.x, c0.y, c0.z) * tb.bx + mk(c1.x, c1.y, c1.z) * tb.by) + mk(c2.x, c2.y, c2.z) * wn);
+    }
+    is.t = t_min; is.materialId = sc.geoms[hit_geom].materialid; is.n = normal; is.geomId = hit_geom;
+    // uv: a mesh hit's own; for a cube/sphere the reference hands over its stale tmp_uv (pathtrace.cu:226,251,263) = the uv of a
+    // mesh candidate processed EARLIER in index order, else nothing (uninitialised there, 0 here)
+    const bool uv_from_mesh = mesh_owner >= 0 && mesh_owner <= hit_geom;
+    is.u = uv_from_mesh ? mesh_u : 0.f; is.v = uv_from_mesh ? mesh_v : 0.f;
     return true;
 }
 
