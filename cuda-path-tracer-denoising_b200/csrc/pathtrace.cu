@@ -15,6 +15,7 @@
 //   * the G-buffer is written as float4 SoA planes, the persistent per-pixel intersection record is reduced to
 //     the 24 bytes that can be observed (stale normal/material/uv on a primary miss, pathtrace.cu:316-322).
 #include "svgf_internal.h"
+#include <algorithm>
 #include <cfloat>
 
 namespace {
@@ -537,6 +538,156 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// Persistent variant of the state machine (SVGF_RT_VARIANT=persistent, A/B only): paths have different lengths (a mirror
+// bounce skips the shadow query, a path that reaches the light or leaves the scene stops), so in the one-pixel-per-thread
+// kernel a quarter of the lanes of a warp sit idle waiting for the longest path. Here a lane that finishes its pixel
+// immediately takes the next unrendered pixel (warp-aggregated atomic on a work counter, pixels enumerated tile by tile) and
+// joins the others at the single closest-hit call site with its primary ray. Which lane renders a pixel cannot change the
+// pixel (everything is keyed by the pixel index; tests check bit-equality). MEASURED ON B200: 20-25 % SLOWER than the plain
+// state machine (C2 1.58 vs 1.25 ms, C3 4.71 vs 4.04 ms): once lanes of a warp are at different depths of different
+// pixels their rays stop being coherent, and the extra divergence inside the intersection and shading code costs more
+// than the idle lanes did. Kept as a documented negative result.
+__global__ void __launch_bounds__(128, 4)
+rt_persistent_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf_material *__restrict__ g_materials,
+                     int n_materials, const float4 *__restrict__ bvh, int n_nodes, const float4 *__restrict__ tri_hot,
+                     const float4 *__restrict__ tri_cold, const TexD *__restrict__ textures,
+                     float4 *__restrict__ nrm_out, float4 *__restrict__ pos_out, float4 *__restrict__ alb_out,
+                     float *__restrict__ image, float4 *__restrict__ stale_nm, float2 *__restrict__ stale_uv,
+                     float4 *__restrict__ gnp_out, float2 *__restrict__ gzl_out, unsigned int *__restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    GeomD *s_geoms = reinterpret_cast<GeomD *>(smem);
+    svgf_material *s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomD) * n_geoms);
+    {
+        const int gw = sizeof(GeomD) / 4 * n_geoms, mw = sizeof(svgf_material) / 4 * n_materials;
+        const int *src = reinterpret_cast<const int *>(g_geoms); int *dst = reinterpret_cast<int *>(s_geoms);
+        for (int i = threadIdx.x; i < gw; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const int *>(g_materials); dst = reinterpret_cast<int *>(s_mats);
+        for (int i = threadIdx.x; i < mw; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    SceneView sc;
+    sc.geoms = s_geoms; sc.n_geoms = n_geoms; sc.materials = s_mats; sc.bvh = bvh; sc.n_nodes = n_nodes;
+    sc.tri_hot = tri_hot; sc.tri_cold = tri_cold; sc.textures = textures;
+    const svgf_camera &cam = P.cam;
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = (P.W + 7) >> 3, tiles_y = (P.row_end - P.row_begin + 3) >> 2;
+    const unsigned int n_items = (unsigned int)tiles_x * (unsigned int)tiles_y * 32u;       // 8x4-pixel tiles, 32 slots each
+
+    bool active = false, exhausted = false;
+    int idx = 0;
+    PathState seg; seg.ray.origin = seg.ray.direction = seg.color = mk(0, 0, 0); seg.diffuse = false;
+    Isect is; is.t = 0.f; is.n = mk(0, 0, 0); is.materialId = 0; is.geomId = 0; is.u = is.v = 0.f;
+    bool any_hit = false;
+    F3 acc = mk(0, 0, 0);
+    int depth = 0, kind = Q_PATH;
+    Ray cur = seg.ray;
+    unsigned int seed = 0; F3 ipos = mk(0, 0, 0), inrm = mk(0, 0, 0); float expectDist = 0.f;
+
+    while (true) {
+        // ---- idle lanes take new pixels (warp-synchronous) ----
+        if (!exhausted) {
+            const unsigned need = __ballot_sync(0xffffffffu, !active);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                unsigned int base = 0;
+                if (lane == leader) base = atomicAdd(work_counter, (unsigned int)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (base >= n_items) exhausted = true;
+                if (!active) {
+                    const unsigned int n = base + __popc(need & ((1u << lane) - 1u));
+                    const unsigned int tile = n >> 5, w = n & 31u;
+                    const int x = (int)(tile % (unsigned int)tiles_x) * 8 + (int)(w & 7u);
+                    const int y = P.row_begin + (int)(tile / (unsigned int)tiles_x) * 4 + (int)(w >> 3);
+                    if (n < n_items && x < P.W && y < P.row_end) {
+                        active = true; idx = x + y * P.W;
+                        // generateRayFromCamera, pathtrace.cu:187-208
+                        seg.ray.origin = mk(cam.position[0], cam.position[1], cam.position[2]);
+                        seg.color = mk(1.0f, 1.0f, 1.0f);
+                        seg.ray.direction = normalize(mk(cam.view[0], cam.view[1], cam.view[2])
+                            - mk(cam.right[0], cam.right[1], cam.right[2]) * cam.pixelLength[0] * ((float)x - (float)(P.W * 0.5f - 0.5f))
+                            - mk(cam.up[0], cam.up[1], cam.up[2]) * cam.pixelLength[1] * ((float)y - (float)(P.H * 0.5f - 0.5f)));
+                        seg.diffuse = false;
+                        any_hit = false; acc = mk(0, 0, 0); depth = 0; kind = Q_PATH; cur = seg.ray;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) { if (exhausted) break; else continue; }
+        if (!active) continue;
+
+        // ---- one step of the path's state machine: intersect the current ray, act on the result ----
+        Isect res; res.geomId = -2; res.materialId = 0; res.t = 0.f; res.n = mk(0, 0, 0); res.u = res.v = 0.f;
+        const bool hit = computeIntersection(sc, cur, res);      // <- the only closest-hit call site
+        bool finished = false, bounce = false;
+        if (kind == Q_SHADOW) {
+            if (res.geomId == 0) {                               // pathtrace.cu:374-384 (lightIdx == 0)
+                const svgf_material &sm = sc.materials[res.materialId];
+                if (sm.emittance > 0.0f) acc = add_direct_light(acc, seg.color, sm, P.sintensity, expectDist, cur.direction, inrm);
+            }
+            bounce = true;
+        } else {
+            if (hit) { is = res; any_hit = true; }
+            else {
+                is.t = -1.0f; is.geomId = -1;
+                if (depth == 0) {                                // stale record of earlier frames (pathtrace.cu:119-120,316-322)
+                    const float4 s4 = stale_nm[idx]; const float2 suv = stale_uv[idx];
+                    is.n = mk(s4.x, s4.y, s4.z); is.materialId = __float_as_int(s4.w); is.u = suv.x; is.v = suv.y;
+                }
+            }
+            if (depth == 0) {                                    // G-buffer from the primary hit, pathtrace.cu:316-323
+                const svgf_material &material = sc.materials[is.materialId];
+                const F3 p = hit_point(seg.ray.origin, seg.ray.direction, is.t);
+                const F3 a = materialAlbedo(sc, material, is.u, is.v);
+                nrm_out[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.geomId));
+                pos_out[idx] = make_float4(p.x, p.y, p.z, 0.f);
+                alb_out[idx] = make_float4(a.x, a.y, a.z, 0.f);
+                gnp_out[idx] = make_float4(is.n.x * P.kn, p.x * P.kx, is.n.y * P.kn, p.y * P.kx);
+                gzl_out[idx] = make_float2(is.n.z * P.kn, p.z * P.kx);
+            }
+            depth++;
+            if (depth > P.max_depth || !hit) finished = true;    // top of the reference's bounce loop (pathtrace.cu:325-326)
+            else {
+                seed = initRand(idx, P.frame + depth);
+                const svgf_material &material = sc.materials[is.materialId];
+                if (material.emittance > 0.0f) {
+                    if (!P.trace_shadowray || !P.reduce_var || !seg.diffuse) acc = add_emission(acc, seg.color, material);
+                    finished = true;
+                } else {
+                    ipos = hit_point(seg.ray.origin, seg.ray.direction, is.t);
+                    inrm = is.n;
+                    const bool materialIsDiffuse = material.hasReflective < 1e-6 && material.hasRefractive < 1e-6;
+                    if (!(P.denoise && P.sepcolor) || depth > 1) seg.color = seg.color * materialAlbedo(sc, material, is.u, is.v);
+                    if (P.trace_shadowray && materialIsDiffuse) {        // pathtrace.cu:358-371
+                        const GeomD &light = sc.geoms[0];
+                        computeShadowRay(cur, ipos, inrm, mk(light.translation[0], light.translation[1], light.translation[2]),
+                                         P.lightradius, expectDist, seed);
+                        kind = Q_SHADOW;
+                    } else bounce = true;
+                }
+            }
+        }
+        if (bounce) {                                            // pathtrace.cu:387-392
+            if (depth >= P.max_depth) finished = true;
+            else { scatterRay(seg, ipos, inrm, sc.materials[is.materialId], seed); cur = seg.ray; kind = Q_PATH; }
+        }
+        if (finished) {
+            float *img = image + 3 * (size_t)idx;
+            if (P.denoise) { img[0] = acc.x; img[1] = acc.y; img[2] = acc.z; }
+            else {          // running mean, pathtrace.cu:398
+                const float f = (float)P.frame, f1 = (float)(P.frame + 1);
+                const F3 nw = mk(img[0], img[1], img[2]) * f / f1 + acc / f1;
+                img[0] = nw.x; img[1] = nw.y; img[2] = nw.z;
+            }
+            if (any_hit) {
+                stale_nm[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.materialId));
+                stale_uv[idx] = make_float2(is.u, is.v);
+            }
+            active = false;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Wavefront variant (SVGF_RT_VARIANT=wavefront): the same per-ray functions, split into stages with SoA ray/hit
 // buffers in HBM and queues of live paths compacted with a warp ballot. One "slot" per pixel holds a path's state;
 // queues hold slot indices, so compaction moves 4 bytes per path, never the state. Stage kernels are launched for the
@@ -803,6 +954,28 @@ static cudaError_t launch_pathtrace_wavefront(svgf_ctx *c, const RtParams &p, fl
 cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
     if (c->rt_variant == 1) return launch_pathtrace_wavefront(c, p, nrm_out);
     const DeviceScene &s = c->scene;
+    if (c->rt_variant == 2) {       // persistent state machine with work refill (A/B; slower: see the kernel's comment)
+        const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(rt_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        if (p.row_end <= p.row_begin) return cudaSuccess;
+        if (!c->rt_counter) {
+            cudaError_t e = cudaMalloc((void **)&c->rt_counter, sizeof(unsigned int));
+            if (e != cudaSuccess) return e;
+            int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            c->rt_blocks = sms * 4;
+        }
+        cudaError_t e = cudaMemsetAsync(c->rt_counter, 0, sizeof(unsigned int), c->stream);
+        if (e != cudaSuccess) return e;
+        const long long items = (long long)((p.W + 7) / 8) * ((p.row_end - p.row_begin + 3) / 4);   // tiles of 32 pixels = one warp's first fetch
+        const int blocks = (int)std::min<long long>(c->rt_blocks, (items + 3) / 4);
+        rt_persistent_kernel<<<blocks, 128, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes,
+                                                               s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, c->alb, c->image,
+                                                               c->stale_nm, c->stale_uv, c->gnp, c->gzl, c->rt_counter);
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

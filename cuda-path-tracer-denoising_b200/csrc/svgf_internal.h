@@ -94,7 +94,9 @@ struct svgf_ctx {
     void *tmaps = nullptr; int tma_ok = 0;
     int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled (TMA tile loads), 3 = lattice-tiled (cp.async)
     bool atrous_attr_set = false;
-    int rt_variant = 0;                 // 0 = state-machine kernel, 1 = wavefront (stage kernels + ballot-compacted queues)
+    int rt_variant = 0;                 // 0 = state machine, one pixel per thread (default), 1 = wavefront (stage kernels +
+                                        // ballot-compacted queues), 2 = persistent state machine with work refill
+    unsigned int *rt_counter = nullptr; int rt_blocks = 0;
     void *wf_mem = nullptr;             // wavefront ray/hit/queue buffers (allocated on first use)
     int hist_cv = -1;                   // which cv[] holds the colour history for the next frame (-1: none yet)
     float4 *nrm[2] = {nullptr, nullptr};
