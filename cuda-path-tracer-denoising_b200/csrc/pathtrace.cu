@@ -59,7 +59,7 @@ struct Ray { F3 origin, direction; };
 // interactions.h:10-30
 __device__ __forceinline__ unsigned int initRand(unsigned int val0, unsigned int val1) {
     unsigned int v0 = val0, v1 = val1, s0 = 0;
-#pragma unroll 4
+#pragma unroll 1
     for (unsigned int n = 0; n < 16; n++) {
         s0 += 0x9e3779b9;
         v0 += ((v1 << 4) + 0xa341316c) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4);
@@ -231,6 +231,7 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
     for (int base = 0; base < sc.n_geoms; base += 32) {
         unsigned cubes = 0, spheres = 0;
         const int n = min(32, sc.n_geoms - base);
+#pragma unroll 1
         for (int j = 0; j < n; j++) {
             const GeomD &g = sc.geoms[base + j];
             if (g.type == 2) { any_mesh = true; continue; }
@@ -265,6 +266,7 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
     TriBest tb; tb.t = FLT_MAX; tb.slot = -1; tb.bx = tb.by = 0.f;
     if (any_mesh && intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb)) {
         const int tri_id = __float_as_int(__ldg(&sc.tri_hot[3 * tb.slot]).w);
+#pragma unroll 1
         for (int i = 0; i < sc.n_geoms && mesh_owner < 0; i++) {
             const GeomD &g = sc.geoms[i];
             if (g.type == 2 && tri_id >= g.tri_begin && tri_id < g.tri_end) mesh_owner = i;
@@ -336,7 +338,8 @@ __device__ __noinline__ void computeShadowRay(Ray &sr, F3 ipos, F3 inrm, F3 ligh
         qw = s * 0.5f; qv = mk(axis.x * invs, axis.y * invs, axis.z * invs);
     }
     float theta = 2 * PI_F * nextRand(seed);
-    F3 v = mk(cosf(theta), sinf(theta), 0.0f);
+    float st, ct; sincosf(theta, &st, &ct);
+    F3 v = mk(ct, st, 0.0f);
     F3 uv = cross(qv, v);
     F3 uuv = cross(qv, uv);
     F3 sampleDirection = v + ((uv * qw) + uuv) * 2.0f;
@@ -358,7 +361,8 @@ __device__ F3 calculateRandomDirectionInHemisphere(F3 normal, unsigned int &seed
     else notNormal = mk(0, 0, 1);
     F3 p1 = normalize(cross(normal, notNormal));
     F3 p2 = normalize(cross(normal, p1));
-    return (up * normal + cosf(around) * over * p1) + sinf(around) * over * p2;
+    float sa, ca; sincosf(around, &sa, &ca);
+    return (up * normal + ca * over * p1) + sa * over * p2;
 }
 
 struct PathState { Ray ray; F3 color; bool diffuse; };
@@ -371,8 +375,11 @@ __device__ __noinline__ void scatterRay(PathState &ps, F3 intersect, F3 normal, 
         float eta = 1.0f / m.indexOfRefraction;
         float unit_projection = dot(ps.ray.direction, normal);
         if (unit_projection > 0) eta = 1.0f / eta;
-        float R0 = powf((1.0f - eta) / (1.0f + eta), 2.0f);
-        float R = R0 + (1 - R0) * powf(1 - gabs(unit_projection), 5.0f);
+        // powf(x, 2) and powf(x, 5) as products: <= 2 ulp from libdevice's powf, far inside the parity budget, and ~300
+        // instructions less code in a kernel whose instruction-cache footprint matters
+        const float r0 = (1.0f - eta) / (1.0f + eta), c1 = 1 - gabs(unit_projection), c2 = c1 * c1;
+        float R0 = r0 * r0;
+        float R = R0 + (1 - R0) * (c2 * c2 * c1);
         if (R < nextRand(seed)) {
             F3 I = ps.ray.direction, N = normal;        // glm::refract, detail/func_geometric.inl:189-198
             float dotValue = dot(N, I);
@@ -398,7 +405,7 @@ __device__ __noinline__ void scatterRay(PathState &ps, F3 intersect, F3 normal, 
 __device__ __noinline__ F3 add_direct_light(F3 acc, F3 throughput, const svgf_material &light, float sintensity, float expectDist,
                                             F3 shadow_dir, F3 normal) {        // pathtrace.cu:377-382
     const float diffuse = gmax(0.0f, dot(shadow_dir, normal));
-    const float shadowIntensity = sintensity / powf(expectDist, 2.0f);
+    const float shadowIntensity = sintensity / (expectDist * expectDist);    // pow(d, 2.0f): x*x is the correctly rounded square
     return acc + throughput * light.emittance * mk(light.color[0], light.color[1], light.color[2]) * shadowIntensity * diffuse;
 }
 __device__ __noinline__ F3 add_emission(F3 acc, F3 throughput, const svgf_material &m) {       // pathtrace.cu:333
