@@ -11,6 +11,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -75,7 +76,13 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
                 }
             }
             const double diag = sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
-            const double pad = 0.01 * diag + 1e-3;
+            // Padding: the exact tests work in fp32 object space, whose rounding moves a silhouette by a few ulps of the world
+            // coordinates (~1e-6 at |x| ~ 10), so ~50 ulps are ample. It must stay well below the 1e-4 by which bounce and
+            // shadow rays are lifted off the surface they leave (pathtrace.cu:366, interactions.h:103): then a ray leaving a
+            // wall starts OUTSIDE the wall's bounds and is rejected by the slab test instead of costing an exact test.
+            double maxabs = 0.0;
+            for (int i = 0; i < 3; i++) { maxabs = std::max(maxabs, fabs(lo[i])); maxabs = std::max(maxabs, fabs(hi[i])); }
+            const double pad = 2e-6 * (1.0 + maxabs + diag);
             for (int i = 0; i < 3; i++) { o.aabb_min[i] = (float)(lo[i] - pad); o.aabb_max[i] = (float)(hi[i] + pad); }
             if (!(diag == diag) || g.type == 2) for (int i = 0; i < 3; i++) { o.aabb_min[i] = -3e38f; o.aabb_max[i] = 3e38f; }
         }

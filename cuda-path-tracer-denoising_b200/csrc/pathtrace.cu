@@ -76,12 +76,10 @@ __device__ __forceinline__ F3 getPointOnRay(const Ray &r, float t) {   // inters
     return r.origin + (t - .0001f) * normalize(r.direction);
 }
 
-// intersections.h:50-92. Returns the reference's t (world-space distance to the pulled-back hit point); the face normal
-// is only computed for the winning geom (box_normal), from the axis/sign recorded here.
-__device__ float boxIntersectionTest(const GeomD &box, const Ray &r, int &axis, float &sign) {
-    Ray q;
-    q.origin = multiplyMV(box.inverseTransform, r.origin, 1.0f);
-    q.direction = normalize(multiplyMV(box.inverseTransform, r.direction, 0.0f));
+// intersections.h:50-92, the slab part: object-space ray q against the unit cube. Yields the object-space t of the hit
+// and the face (axis, sign) the deferred normal is made from; the shared head (ray into object space) and tail (hit point
+// back to world space, distance) live in computeIntersection, common to cubes and spheres.
+__device__ __forceinline__ bool box_slabs(const Ray &q, float &tobj, int &axis, float &sign) {
     float tmin = -1e38f, tmax = 1e38f;
     int tmin_axis = -1, tmax_axis = -1; float tmin_s = 0.f, tmax_s = 0.f;   // normal = sign on one axis, zero elsewhere
     const float qo[3] = {q.origin.x, q.origin.y, q.origin.z}, qd[3] = {q.direction.x, q.direction.y, q.direction.z};
@@ -98,36 +96,29 @@ __device__ float boxIntersectionTest(const GeomD &box, const Ray &r, int &axis, 
     }
     if (tmax >= tmin && tmax > 0) {
         if (tmin <= 0) { tmin = tmax; tmin_axis = tmax_axis; tmin_s = tmax_s; }
-        F3 ip = multiplyMV(box.transform, getPointOnRay(q, tmin), 1.0f);
-        axis = tmin_axis; sign = tmin_s;
-        return length(r.origin - ip);
+        tobj = tmin; axis = tmin_axis; sign = tmin_s;
+        return true;
     }
-    return -1;
+    return false;
 }
 __device__ __forceinline__ F3 box_normal(const GeomD &box, int axis, float sign) {      // intersections.h:67-68,90
     const F3 n = mk(axis == 0 ? sign : 0.f, axis == 1 ? sign : 0.f, axis == 2 ? sign : 0.f);
     return normalize(multiplyMV(box.transform, n, 0.0f));
 }
 
-// intersections.h:104-146; the normal is deferred like the box's (sphere_normal from the object-space hit point)
-__device__ float sphereIntersectionTest(const GeomD &sphere, const Ray &r, F3 &osi, bool &outside) {
-    Ray rt;
-    rt.origin = multiplyMV(sphere.inverseTransform, r.origin, 1.0f);
-    rt.direction = normalize(multiplyMV(sphere.inverseTransform, r.direction, 0.0f));
+// intersections.h:104-131, the quadratic: object-space ray against the sphere of radius 0.5
+__device__ __forceinline__ bool sphere_roots(const Ray &rt, float &tobj, bool &outside) {
     float vDotDirection = dot(rt.origin, rt.direction);
     float radicand = vDotDirection * vDotDirection - (dot(rt.origin, rt.origin) - 0.25f);
-    if (radicand < 0) return -1;
+    if (radicand < 0) return false;
     float squareRoot = sqrtf(radicand);
     float firstTerm = -vDotDirection;
     float t1 = firstTerm + squareRoot;
     float t2 = firstTerm - squareRoot;
-    float t = 0;
-    if (t1 < 0 && t2 < 0) return -1;
-    else if (t1 > 0 && t2 > 0) { t = fminf(t1, t2); outside = true; }
-    else { t = fmaxf(t1, t2); outside = false; }
-    osi = getPointOnRay(rt, t);
-    F3 ip = multiplyMV(sphere.transform, osi, 1.f);
-    return length(r.origin - ip);
+    if (t1 < 0 && t2 < 0) return false;
+    else if (t1 > 0 && t2 > 0) { tobj = fminf(t1, t2); outside = true; }
+    else { tobj = fmaxf(t1, t2); outside = false; }
+    return true;
 }
 __device__ __forceinline__ F3 sphere_normal(const GeomD &sphere, F3 osi, bool outside) {    // intersections.h:140-143
     F3 n = normalize(multiplyMV(sphere.invTranspose, osi, 0.f));
@@ -228,16 +219,20 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
     // 1 / direction exactly as IntersectBVH forms it (intersections.h:276); also feeds the conservative bounds pre-test
     const F3 invdir = mk(1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z);
     bool any_mesh = false;
+    // |direction| turns the slab parameter of the bounds pre-test into a distance comparable with the reference's t
+    const float dlen = length(ray.direction);
     for (int base = 0; base < sc.n_geoms; base += 32) {
         unsigned cubes = 0, spheres = 0;
+        float near_tn = FLT_MAX; int near_j = -1;       // candidate whose bounds the ray enters first
         const int n = min(32, sc.n_geoms - base);
 #pragma unroll 1
         for (int j = 0; j < n; j++) {
             const GeomD &g = sc.geoms[base + j];
             if (g.type == 2) { any_mesh = true; continue; }
             // Slab test against the inflated world bounds. A NaN direction keeps every term NaN (no reject: the exact test
-            // then runs as in the reference); 0 * inf only arises for a ray lying IN an inflated face plane, which is
-            // >= 1e-3 outside the real surface, so dropping that NaN (fminf/fmaxf) can only reject true misses.
+            // then runs as in the reference); 0 * inf only arises for a ray lying IN a padded face plane, which is outside
+            // the real surface by ~50x the rounding of the exact test, so dropping that NaN (fminf/fmaxf) can only reject
+            // true misses.
             const float ax = (g.aabb_min[0] - ray.origin.x) * invdir.x, bx = (g.aabb_max[0] - ray.origin.x) * invdir.x;
             const float ay = (g.aabb_min[1] - ray.origin.y) * invdir.y, by = (g.aabb_max[1] - ray.origin.y) * invdir.y;
             const float az = (g.aabb_min[2] - ray.origin.z) * invdir.z, bz = (g.aabb_max[2] - ray.origin.z) * invdir.z;
@@ -245,18 +240,49 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
             if (tf < tn || tf < 0.f) continue;      // the exact test would return -1 (no hit)
             if (g.type == 1) cubes |= 1u << j; else spheres |= 1u << j;
+            if (tn < near_tn) { near_tn = tn; near_j = j; }
         }
-        while (cubes) {
-            const int i = base + __ffs(cubes) - 1; cubes &= cubes - 1;
-            int axis = 0; float sign = 0.f;
-            const float t = boxIntersectionTest(sc.geoms[i], ray, axis, sign);
-            if (t > 0.0f && (t < t_min || (t == t_min && i < hit_geom))) { t_min = t; hit_geom = i; w_kind = 1; w_axis = axis; w_sign = sign; }
-        }
-        while (spheres) {
-            const int i = base + __ffs(spheres) - 1; spheres &= spheres - 1;
-            F3 osi = mk(0, 0, 0); bool outside = true;
-            const float t = sphereIntersectionTest(sc.geoms[i], ray, osi, outside);
-            if (t > 0.0f && (t < t_min || (t == t_min && i < hit_geom))) { t_min = t; hit_geom = i; w_kind = 0; w_osi = osi; w_outside = outside; }
+        // One loop for both primitive kinds: head (ray into object space) and tail (hit point back to world space, distance
+        // along the ray: intersections.h:52-55,86-91 / 106-111,133-146) are the same code, only the middle differs, so a lane
+        // holding a sphere works in the same trips as the lanes holding cubes.
+        // Order: the candidate entered first, then index order; once a hit is known, candidates whose bounds the ray enters
+        // beyond it are dropped without the exact test -- their hit point lies inside the bounds, so its distance could
+        // neither beat nor tie t_min (margin far above rounding). The reference tests them and discards the result; the
+        // explicit tie rule below makes the winner independent of the order.
+        unsigned cand = cubes | spheres;
+        while (true) {
+            int j = -1;
+            while (cand) {      // next candidate that can still matter (cheap; lanes reconverge before the exact test)
+                int jj = near_j >= 0 ? near_j : __ffs(cand) - 1;
+                near_j = -1;
+                cand &= ~(1u << jj);
+                if (t_min < FLT_MAX) {
+                    const GeomD &g = sc.geoms[base + jj];
+                    const float ax = (g.aabb_min[0] - ray.origin.x) * invdir.x, bx = (g.aabb_max[0] - ray.origin.x) * invdir.x;
+                    const float ay = (g.aabb_min[1] - ray.origin.y) * invdir.y, by = (g.aabb_max[1] - ray.origin.y) * invdir.y;
+                    const float az = (g.aabb_min[2] - ray.origin.z) * invdir.z, bz = (g.aabb_max[2] - ray.origin.z) * invdir.z;
+                    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+                    if (tn * dlen > t_min * 1.0001f + 1e-4f) continue;
+                }
+                j = jj;
+                break;
+            }
+            if (j < 0) break;
+            const int i = base + j;
+            const GeomD &g = sc.geoms[i];
+            Ray q;
+            q.origin = multiplyMV(g.inverseTransform, ray.origin, 1.0f);
+            q.direction = normalize(multiplyMV(g.inverseTransform, ray.direction, 0.0f));
+            const bool is_cube = (cubes >> j) & 1u;
+            float tobj = 0.f; int axis = 0; float sign = 0.f; bool outside = true;
+            const bool ok = is_cube ? box_slabs(q, tobj, axis, sign) : sphere_roots(q, tobj, outside);
+            if (!ok) continue;
+            const F3 osi = getPointOnRay(q, tobj);
+            const F3 ip = multiplyMV(g.transform, osi, 1.0f);
+            const float t = length(ray.origin - ip);
+            if (t > 0.0f && (t < t_min || (t == t_min && i < hit_geom))) {
+                t_min = t; hit_geom = i; w_kind = is_cube ? 1 : 0; w_axis = axis; w_sign = sign; w_osi = osi; w_outside = outside;
+            }
         }
     }
     // Meshes: every MESH geom runs the same traversal of the one global BVH and accepts the closest triangle only if its id is
