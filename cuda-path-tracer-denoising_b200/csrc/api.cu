@@ -229,6 +229,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     c->device = device; c->W = scene->width; c->H = scene->height; c->px = (size_t)c->W * c->H;
     c->shard = svgf_shard{0, 1, 0, c->H};
     if (const char *v = getenv("SVGF_RT_VARIANT")) c->rt_variant = (!strcmp(v, "wavefront") || !strcmp(v, "1")) ? 1 : ((!strcmp(v, "persistent") || !strcmp(v, "2")) ? 2 : 0);
+    if (const char *v = getenv("SVGF_HALO")) c->halo_push = strcmp(v, "pull") != 0;      // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3) ? atoi(v) : 2;    // A/B testing
     memset(c->view_matrix_prev, 0, sizeof(c->view_matrix_prev));
     c->view_matrix_prev[0] = c->view_matrix_prev[5] = c->view_matrix_prev[10] = c->view_matrix_prev[15] = 1.0f;   // glm::mat4()
@@ -424,9 +425,25 @@ int svgf_sync(svgf_ctx *c) {
 
 // ---- the denoise driver on SoA planes (denoise.cu:349-402) -------------------------------------------
 // Inputs: c->image (1-spp colour), c->nrm[cur_nrm], c->pos, c->alb. Output: c->denoised, c->var_out.
+template <class T> static HaloPlane halo_plane(const T *local, const PeerPtr<T> &peers) {
+    HaloPlane h; h.local = local; h.esz = (int)sizeof(T);
+    for (int r = 0; r < SVGF_MAX_RANKS; r++) h.peer[r] = peers.p[r];
+    return h;
+}
+
 static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, const svgf_params *P, cudaEvent_t *ev) {
     const int acc_slot = (c->hist_cv + 1) % 3;          // any buffer that is not the current history
     float4 *acc = c->cv[acc_slot];
+    // Sharded frames, push mode: a level taps rows up to 2*step beyond the strip. Instead of reading them from their owners
+    // in place (32-byte gathers over NVLink, every coarse tile), each stage's producer copies the rows its neighbours will
+    // tap into THEIR copy of the plane right after producing them (dense stores, nobody waits on them), and the levels read
+    // local memory only. The G-buffer view travels once per frame, for the coarsest level's reach.
+    const bool filter = P->right_view_option == 0 && P->atrous_nlevel > 0 && P->spatial_enable;
+    const bool push = c->halo_push && c->shard.world > 1 && filter;
+    if (push) {
+        const HaloPlane g[2] = {halo_plane(c->gnp, c->p_gnp), halo_plane(c->gzl, c->p_gzl)};
+        CK(launch_halo_push(c, 2 << P->atrous_nlevel, g, 2));
+    }
     const float color_alpha = P->temporal_enable ? P->color_alpha : 1.0f;
     const float moment_alpha = P->temporal_enable ? P->moment_alpha : 1.0f;
     if (P->temporal_enable) {
@@ -435,6 +452,10 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
                            c->view_matrix_prev, color_alpha, moment_alpha));
     } else {
         CK(launch_no_temporal(c, image, acc, c->lv[acc_slot]));
+    }
+    if (push) {     // level 1 (step 2) taps +-4 rows
+        const HaloPlane h[2] = {halo_plane(c->cv[acc_slot], c->p_cv[acc_slot]), halo_plane(c->lv[acc_slot], c->p_lv[acc_slot])};
+        CK(launch_halo_push(c, 4, h, 2));
     }
     CK(launch_signal(c, SVGF_STAGE_TEMPORAL));
     if (ev) CK(cudaEventRecord(ev[2], c->stream));
@@ -469,6 +490,10 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             a.level = level; a.is_last = last; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
             a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;
             CK(launch_atrous(c, a));
+            if (push && !last) {        // the next level (step 2^(level+1)) taps +-2 steps
+                const HaloPlane h[2] = {halo_plane(c->cv[dst], c->p_cv[dst]), halo_plane(c->lv[dst], c->p_lv[dst])};
+                CK(launch_halo_push(c, 4 << level, h, 2));
+            }
             CK(launch_signal(c, SVGF_STAGE_LEVEL0 + level));
             if (ev && level <= SVGF_MAX_LEVELS) CK(cudaEventRecord(ev[2 + level], c->stream));
             if (is_hist) new_hist = dst;     // denoise.cu:391: colour history := this level's output

@@ -525,9 +525,12 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     }
     AtrousT t;
     t.k = k; t.kl = c->kl; t.ro = c->rows; t.me = c->shard.rank;
+    // push mode: the neighbours' rows this level taps were copied into this rank's planes by their producers (api.cu)
+    const bool local_only = c->halo_push || c->shard.world <= 1;
+    if (local_only) { t.ro.world = 1; t.me = 0; }
     PeerPtr<const float2> pv;
     for (int r = 0; r < SVGF_MAX_RANKS; r++) {
-        const bool peer = r < c->shard.world && a.src_slot >= 0;
+        const bool peer = !local_only && r < c->shard.world && a.src_slot >= 0;
         t.p_cv.p[r] = peer ? c->p_cv[a.src_slot].p[r] : a.cv_in; t.p_lv.p[r] = peer ? c->p_lv[a.src_slot].p[r] : a.lv_in;
         t.p_gnp.p[r] = peer ? c->p_gnp.p[r] : a.gnp; t.p_gzl.p[r] = peer ? c->p_gzl.p[r] : a.gzl;
         pv.p[r] = t.p_lv.p[r];

@@ -10,6 +10,8 @@
 // The a-trous filter itself lives in atrous.cu.
 #include "svgf_internal.h"
 
+#include <algorithm>
+
 namespace {
 
 __device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, float by, float bz) {
@@ -246,6 +248,23 @@ __global__ void wait_kernel(unsigned *flags, int world, int stage, unsigned seq)
     __threadfence_system();
 }
 
+// ---- halo push: whole rows of a row-major plane are contiguous, so "my rows that rank r will tap" is one memcpy-shaped
+// segment per (plane, peer). One launch moves all segments of a stage (blockIdx.y = segment) with 16-byte stores that
+// travel over NVLink as full packets; the stage's sequence flag follows in stream order (signal_kernel).
+struct PushSeg { const void *src; void *dst; unsigned long long bytes; };
+enum { SVGF_PUSH_MAXSEG = 4 * SVGF_MAX_RANKS };
+struct PushArgs { PushSeg seg[SVGF_PUSH_MAXSEG]; };
+
+template <class V>
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const __grid_constant__ PushArgs a) {
+    const PushSeg &s = a.seg[blockIdx.y];
+    const V *__restrict__ src = static_cast<const V *>(s.src);
+    V *__restrict__ dst = static_cast<V *>(s.dst);
+    const size_t n = s.bytes / sizeof(V), stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
 inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (rows + b.y - 1) / b.y); }
 
 }  // namespace
@@ -278,6 +297,36 @@ cudaError_t launch_pack_pbo(svgf_ctx *c, unsigned char *pbo, const float *left, 
     dim3 b(32, 8);
     pack_pbo_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->shard.row_begin, c->shard.row_end,
                                                                  reinterpret_cast<uchar4 *>(pbo), left, right);
+    return cudaGetLastError();
+}
+
+// Copies this rank's rows that lie within `halo_rows` of another rank's strip into that rank's copy of the plane(s).
+cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes) {
+    if (c->shard.world <= 1 || halo_rows <= 0) return cudaSuccess;
+    PushArgs a; int nseg = 0; unsigned long long longest = 0; bool v16 = true;
+    const int b = c->shard.row_begin, e = c->shard.row_end;
+    for (int r = 0; r < c->shard.world; r++) {
+        if (r == c->shard.rank) continue;
+        const int lo = std::max(b, c->rows.start[r] - halo_rows), hi = std::min(e, c->rows.start[r + 1] + halo_rows);
+        if (lo >= hi || c->rows.start[r] >= c->rows.start[r + 1]) continue;       // nothing of mine in reach / empty strip
+        for (int p = 0; p < nplanes; p++) {
+            if (!planes[p].peer[r] || planes[p].peer[r] == planes[p].local) continue;     // not connected (yet): own plane
+            if (nseg == SVGF_PUSH_MAXSEG) return cudaErrorInvalidValue;
+            const size_t off = (size_t)lo * c->W * planes[p].esz, bytes = (size_t)(hi - lo) * c->W * planes[p].esz;
+            a.seg[nseg].src = static_cast<const char *>(planes[p].local) + off;
+            a.seg[nseg].dst = static_cast<char *>(planes[p].peer[r]) + off;
+            a.seg[nseg].bytes = bytes;
+            v16 = v16 && (off % 16 == 0) && (bytes % 16 == 0);
+            longest = std::max<unsigned long long>(longest, bytes);
+            nseg++;
+        }
+    }
+    if (nseg == 0) return cudaSuccess;
+    const unsigned long long per_block = 256ull * (v16 ? 16 : 8) * 4;        // ~4 vectors per thread
+    const unsigned gx = (unsigned)std::min<unsigned long long>((longest + per_block - 1) / per_block, 1024ull);
+    dim3 g(gx ? gx : 1, nseg);
+    if (v16) halo_push_kernel<uint4><<<g, 256, 0, c->stream>>>(a);
+    else halo_push_kernel<uint2><<<g, 256, 0, c->stream>>>(a);
     return cudaGetLastError();
 }
 

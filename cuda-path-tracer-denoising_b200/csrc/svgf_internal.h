@@ -92,6 +92,9 @@ struct svgf_ctx {
     float2 *lv[3] = {nullptr, nullptr, nullptr};
     // TMA descriptors (CUtensorMap, 128 B each) for the lattice tiles of cv[3], lv[3], gnp, gzl: [plane 8][level 1..7][shape 2]
     void *tmaps = nullptr; int tma_ok = 0;
+    // sharded frames: 1 = every stage pushes the rows its neighbours will tap into their copy of the plane, levels read local
+    // memory only (TMA tiles everywhere); 0 = levels read neighbours' rows in place over NVLink (SVGF_HALO=pull, A/B)
+    int halo_push = 1;
     int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled (TMA tile loads), 3 = lattice-tiled (cp.async)
     bool atrous_attr_set = false;
     int rt_variant = 0;                 // 0 = state machine, one pixel per thread (default), 1 = wavefront (stage kernels +
@@ -160,6 +163,8 @@ cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_c
                             const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
                             const PeerPtr<int> &hlen_in, float4 *acc_cv, float2 *acc_lv, float2 *mom_acc, int *hlen_out,
                             const float *prev_viewmat, float color_alpha, float moment_alpha);
+struct HaloPlane { const void *local; void *peer[SVGF_MAX_RANKS]; int esz; };     // esz = bytes per pixel (multiple of 8)
+cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes);
 cudaError_t launch_signal(svgf_ctx *c, int stage);
 cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq);
 cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float2 *acc_lv);
