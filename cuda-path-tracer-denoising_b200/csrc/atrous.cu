@@ -28,6 +28,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct AtrousK {
     const float4 *cv_in; float4 *cv_out;
     const float2 *lv_in; float2 *lv_out;        // {luminance (fp64 formula), variance} per pixel
@@ -142,11 +148,6 @@ template <int LX, int LY> struct AtShape {
 };
 static_assert(AtShape<16, 32>::HALF * 8 % 128 == 0 && AtShape<32, 16>::HALF * 8 % 128 == 0, "TMA destinations must be 128-byte aligned");
 
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -195,11 +196,21 @@ atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_
         }
     }
     float out[4];
+    // interior threads (all 18 taps inside the image): the weights sum to exactly 1, so the renormalising divide is an
+    // identity and the bounds tests fold away; same products, same order, same bits
+    const bool interior = blur_variance && rok[0] && rok[2] && x0 > 0 && x0 + 4 < W;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int x = x0 + i;
         float var;
-        if (blur_variance) {        // same tap order as the reference: rows outer, columns inner (denoise.cu:105-114)
+        if (interior) {
+            float sum = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) sum += ((dx == 0 ? 0.5f : 0.25f) * (r == 1 ? 0.5f : 0.25f)) * v[r][1 + i + dx];
+            var = sum;
+        } else if (blur_variance) {        // same tap order as the reference: rows outer, columns inner (denoise.cu:105-114)
             float sum = 0.0f, sumw = 0.0f;
 #pragma unroll
             for (int r = 0; r < 3; r++)
@@ -218,7 +229,8 @@ atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_
         }
         var = fmaxf(var, 0.0f);
         // fp32: the reference's fp64 add/divide here (denoise.cu:143) only has to be matched to ~1e-7 relative
-        out[i] = 1.4426950408889634f / (sqrtf(var) * sigma_c + 1e-6f);
+        // (sqrt.approx and an approximate divide: 2-3 ulp on kl, i.e. < 1e-6 relative on any exponent that matters)
+        out[i] = __fdividef(1.4426950408889634f, fmaf(sqrt_approx(var), sigma_c, 1e-6f));
     }
     float *dst = kl + (size_t)y * W + x0;
     if (((W & 3) == 0) && x0 + 3 < W) *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);

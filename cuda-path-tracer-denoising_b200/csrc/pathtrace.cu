@@ -17,6 +17,7 @@
 #include "svgf_internal.h"
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 namespace {
 
@@ -451,7 +452,8 @@ __device__ __noinline__ F3 hit_point(F3 origin, F3 direction, float t) { return 
 constexpr int RT_BX = 8, RT_BY = 16;
 enum { Q_PATH = 0, Q_SHADOW = 1 };
 
-__global__ void __launch_bounds__(RT_BX *RT_BY, 4)
+template <int MINB>
+__global__ void __launch_bounds__(RT_BX *RT_BY, MINB)
 rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf_material *__restrict__ g_materials,
           int n_materials, const float4 *__restrict__ bvh, int n_nodes, const float4 *__restrict__ tri_hot,
           const float4 *__restrict__ tri_cold, const TexD *__restrict__ textures,
@@ -1010,15 +1012,24 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
         return cudaGetLastError();
     }
     const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
     const int rows = p.row_end - p.row_begin;
     if (rows <= 0) return cudaSuccess;
     dim3 block(RT_BX, RT_BY), grid((p.W + RT_BX - 1) / RT_BX, (rows + RT_BY - 1) / RT_BY);
-    rt_kernel<<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes,
-                                                s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, c->alb, c->image,
-                                                c->stale_nm, c->stale_uv, c->gnp, c->gzl);
+#define RT_LAUNCH(MINB)                                                                                                          \
+    do {                                                                                                                         \
+        if (smem > 48 * 1024) {                                                                                                  \
+            cudaError_t e = cudaFuncSetAttribute(rt_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+            if (e != cudaSuccess) return e;                                                                                      \
+        }                                                                                                                        \
+        rt_kernel<MINB><<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes,   \
+                                                          s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, c->alb, c->image,  \
+                                                          c->stale_nm, c->stale_uv, c->gnp, c->gzl);                             \
+    } while (0)
+    // Occupancy beats registers here: the kernel waits on dependent fp32 chains and BVH loads, so 8 blocks/SM (64 registers,
+    // 84 B of spills) run 15-30 % faster than 4 blocks/SM (110 registers, none); 10 and 12 were slower again (measured on
+    // B200: C2 0.93/0.80/0.86/0.89 ms, C3 3.73/2.82/2.85/2.92 ms for 4/8/10/12). SVGF_RT_MINBLOCKS=4 keeps the A/B.
+    static const int minb = getenv("SVGF_RT_MINBLOCKS") ? atoi(getenv("SVGF_RT_MINBLOCKS")) : 8;
+    if (minb == 4) RT_LAUNCH(4); else RT_LAUNCH(8);
+#undef RT_LAUNCH
     return cudaGetLastError();
 }
