@@ -12,8 +12,11 @@ Prints ONE JSON line (rank 0). Keys follow the driver's contract; see DESIGN.md 
 
   value     frames/s with everything resident on the device (no host image requested), CUDA events on the
             library's own stream around exactly K frames, after W warm-up frames.
-  e2e       frames/s through the public C-ABI call a user makes, svgf_render(..., host_image): per frame the
-            camera+parameter structs go in (kernel arguments) and the W*H*3 float image comes back to host memory.
+  e2e       frames/s through the public C-ABI calls a user makes with HOST buffers: per frame the camera+parameter structs
+            go in (kernel arguments) and the W*H*3 float image comes back to (page-locked) host memory. `value` uses the
+            pipelined pair svgf_render_async / svgf_wait_image (frame N's image is consumed while frame N+1 renders: one
+            frame in flight, every image waited for inside the timed region); `blocking` is the reference-shaped call
+            svgf_render(..., host_image), which returns with the image in place (pathtrace.cu:450).
   roofline  the a-trous level kernel(s): algorithmic bytes (56 B/pixel, 68 B/pixel on the last level) / CUDA-event
             duration of each level launch, averaged over the timed frames, against the measured HBM copy peak.
   cpu_baseline  the CPU oracle (port of the reference path, OpenMP) timed on this box's host cores, bounded sample.
@@ -190,6 +193,8 @@ def run_ours(args, wl, rank, world, local_rank):
     stream = torch.cuda.ExternalStream(R.stream(), device=torch.device("cuda", local_rank))
     host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
     host_np = host.numpy()
+    host2 = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    bufs = [host_np, host2.numpy()]
     frame = 0
 
     def barrier():
@@ -200,6 +205,9 @@ def run_ours(args, wl, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         R.pathtrace(drv.step(), P, frame, host_image=host_np); frame += 1
+    for i in range(3):      # sets up the copy stream and the second output buffer of the pipelined path
+        R.pathtrace_async(drv.step(), P, frame, bufs[i & 1]); frame += 1
+    R.wait_image(None)
 
     # ---- device-resident throughput (value) + per-stage events over the same timed region ----
     clocks = ClockSampler(local_rank); clocks.start()
@@ -223,20 +231,32 @@ def run_ours(args, wl, rank, world, local_rank):
         R.pathtrace(drv.step(), P, frame, host_image=host_np); frame += 1
     e3.record(stream)
     R.sync(); barrier()
-    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+    ms_blk = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+    # ---- end to end, pipelined: the image of frame N is waited for (= consumed) while frame N+1 renders ----
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        R.pathtrace_async(drv.step(), P, frame, bufs[i & 1]); frame += 1
+        if i >= 1:
+            R.wait_image(bufs[(i - 1) & 1])
+    R.wait_image(bufs[(args.steps - 1) & 1])
+    R.sync()
+    ms_e2e = (time.perf_counter() - t0) * 1e3      # host clock: the last image has landed
+    barrier()
     clk = clocks.stop()
     if world > 1 and R.peer_error():
         raise SystemExit("bench.py: a cross-rank wait timed out (a peer stopped making progress)")
     if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_dev, ms_e2e, ms_blk], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = t.tolist()
+        ms_dev, ms_e2e, ms_blk = t.tolist()
     if rank != 0:
         return
     px = W * H
     # strong scaling: all ranks together render ONE frame per step (row strips)
     fps_dev = args.steps * 1000.0 / ms_dev
     fps_e2e = args.steps * 1000.0 / ms_e2e
+    fps_blk = args.steps * 1000.0 / ms_blk
     peak, peak_src = measured_peak()
     lv_ms = [float(stage[2 + l]) for l in range(nl)]
     strip_px = W * (rows[rank + 1] - rows[rank]) if world > 1 else px       # rank 0's launches cover its strip
@@ -259,8 +279,11 @@ def run_ours(args, wl, rank, world, local_rank):
                    "l2": "per-frame working set %.0f MB > 126 MB L2 (no flush needed)" % (px * 196 / 1e6)},
         "e2e": {"value": fps_e2e * px / 1e6, "unit": "Mpixels/sec", "fps": fps_e2e, "h2d_bytes_per_step": (84 + 80) * world,
                 "d2h_bytes_per_step": px * 12, "ms_per_step": ms_e2e / args.steps,
+                "api": "svgf_render_async + svgf_wait_image (one frame in flight, every image waited for; host clock)",
+                "blocking": {"value": fps_blk * px / 1e6, "fps": fps_blk, "ms_per_step": ms_blk / args.steps,
+                             "api": "svgf_render(..., host_image): returns with the image in place, like the reference's pathtrace()"},
                 "note": "every rank copies its own strip of the image to its host buffer each frame" if world > 1 else "whole image to host each frame"},
-        "gpu_launches": launches_per_frame * args.steps * 2 * world,
+        "gpu_launches": launches_per_frame * args.steps * 3 * world,
         "roofline": {"bound": "hbm", "kernel": "atrous level (all %d levels)" % nl, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "per_level_us": [t * 1e3 for t in lv_ms], "per_level_gbs": lv_gbs, "per_level_frac": [g / peak for g in lv_gbs],

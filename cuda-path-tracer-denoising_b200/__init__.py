@@ -82,7 +82,8 @@ class Shard(ctypes.Structure):
 EXPORTS = ["svgf_params_default", "svgf_create", "svgf_destroy", "svgf_reset", "svgf_render", "svgf_denoise", "svgf_sync",
            "svgf_denoise_host", "svgf_atrous_host", "svgf_fetch", "svgf_last_error", "svgf_abi_version", "svgf_stage_times",
            "svgf_set_profiling", "svgf_stream", "svgf_set_shard", "svgf_ipc_handles_size", "svgf_ipc_export",
-           "svgf_ipc_connect", "svgf_peer_connect_local", "svgf_peer_error", "svgf_camera_init", "svgf_camera_step"]
+           "svgf_ipc_connect", "svgf_peer_connect_local", "svgf_peer_error", "svgf_camera_init", "svgf_camera_step",
+           "svgf_render_async", "svgf_wait_image"]
 
 _lib = None
 
@@ -105,6 +106,8 @@ def lib():
         L.svgf_destroy.argtypes = [vp]
         L.svgf_reset.argtypes = [vp]
         L.svgf_render.argtypes = [vp, ctypes.POINTER(Camera), ctypes.POINTER(Params), ci, vp, vp]
+        L.svgf_render_async.argtypes = [vp, ctypes.POINTER(Camera), ctypes.POINTER(Params), ci, vp, vp]
+        L.svgf_wait_image.argtypes = [vp, vp]
         L.svgf_denoise.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Camera), ctypes.POINTER(Params)]
         L.svgf_denoise_host.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Camera), ctypes.POINTER(Params)]
         L.svgf_atrous_host.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ctypes.POINTER(Params)]
@@ -227,6 +230,15 @@ class Renderer:
         """== pathtrace(pbo, frame). host_image: (H, W, 3) float32 numpy array to fill (scene->state.image), or None."""
         hp = host_image.ctypes.data if host_image is not None else None
         self._ck(lib().svgf_render(self.h, ctypes.byref(cam), ctypes.byref(params), frame, pbo_dev, hp), "svgf_render")
+
+    def pathtrace_async(self, cam, params, frame, host_image, pbo_dev=None):
+        """Pipelined pathtrace(): queues the frame and the copy of its image into `host_image` and returns; the image is
+        complete after wait_image(host_image). Alternate between two host arrays to keep one frame in flight."""
+        self._ck(lib().svgf_render_async(self.h, ctypes.byref(cam), ctypes.byref(params), frame, pbo_dev, host_image.ctypes.data),
+                 "svgf_render_async")
+
+    def wait_image(self, host_image=None):
+        self._ck(lib().svgf_wait_image(self.h, host_image.ctypes.data if host_image is not None else None), "svgf_wait_image")
 
     def sync(self):
         self._ck(lib().svgf_sync(self.h), "svgf_sync")

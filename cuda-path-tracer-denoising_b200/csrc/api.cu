@@ -231,6 +231,15 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     if (const char *v = getenv("SVGF_RT_VARIANT")) c->rt_variant = (!strcmp(v, "wavefront") || !strcmp(v, "1")) ? 1 : ((!strcmp(v, "persistent") || !strcmp(v, "2")) ? 2 : 0);
     if (const char *v = getenv("SVGF_HALO")) c->halo_push = strcmp(v, "pull") != 0;      // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3) ? atoi(v) : 2;    // A/B testing
+    if (const char *v = getenv("SVGF_ATROUS_SHAPE")) c->atrous_shape = atoi(v);
+    if (const char *v = getenv("SVGF_ATROUS_SHAPES")) {      // "a,b,c,...": shape of level 1, 2, 3, ...
+        int level = 1;
+        for (const char *q = v; *q && level <= SVGF_MAX_LEVELS; level++) {
+            c->atrous_shape_level[level] = atoi(q);
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+    }
     memset(c->view_matrix_prev, 0, sizeof(c->view_matrix_prev));
     c->view_matrix_prev[0] = c->view_matrix_prev[5] = c->view_matrix_prev[10] = c->view_matrix_prev[15] = 1.0f;   // glm::mat4()
     int rc = SVGF_OK;
@@ -260,6 +269,10 @@ int svgf_destroy(svgf_ctx *c) {
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->aos_in); cudaFree(c->aos_out); cudaFree(c->aos_g);
     if (c->pinned_image) cudaFreeHost(c->pinned_image);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->frame_done);
+        cudaEventDestroy(c->copy_done[0]); cudaEventDestroy(c->copy_done[1]); cudaFree(c->denoised_alt);
+    }
     for (auto &pf : c->prof_pool) for (int i = 0; i < 12; i++) cudaEventDestroy(pf.ev[i]);
     for (auto &r : c->registered_hosts) cudaHostUnregister(r.first);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -287,6 +300,11 @@ int svgf_reset(svgf_ctx *c) {
     CK(cudaMemsetAsync(c->gnp, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->gzl, 0, px * sizeof(float2), st));
     CK(cudaMemsetAsync(c->image, 0, px * 12, st)); CK(cudaMemsetAsync(c->denoised, 0, px * 12, st));
     CK(cudaMemsetAsync(c->var_out, 0, px * 4, st));
+    if (c->copy_stream) {       // images still in flight belong to the history being discarded
+        CK(cudaStreamSynchronize(c->copy_stream));
+        c->copy_pending[0] = c->copy_pending[1] = 0;
+        CK(cudaMemsetAsync(c->denoised_alt, 0, px * 12, st));
+    }
     CK(cudaMemsetAsync(c->stale_nm, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->stale_uv, 0, px * sizeof(float2), st));
     CK(cudaMemsetAsync(c->pbo_own, 0, px * 8, st));
     c->hist_cv = 0; c->cur_nrm = 0; c->cur_mom = 0; c->cur_hlen = 0;
@@ -418,6 +436,7 @@ void *svgf_stream(svgf_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int svgf_sync(svgf_ctx *c) {
     if (!c) return SVGF_ERR_INVALID;
     CK(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
     return SVGF_OK;
 }
 
@@ -536,11 +555,41 @@ static bool host_is_registered(svgf_ctx *c, void *p, size_t bytes) {
     return false;
 }
 
-extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, float *host_image) {
+// Pipelined readback: the frame's image leaves through a second stream while the next frame renders, so the final colour
+// needs two buffers (the copy of frame N reads one while frame N+1's last level writes the other).
+static int async_setup(svgf_ctx *c) {
+    if (c->copy_stream) return SVGF_OK;
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->frame_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming));
+    CK(dalloc(&c->denoised_alt, 3 * c->px));
+    CK(cudaMemsetAsync(c->denoised_alt, 0, c->px * 12, c->stream));
+    return SVGF_OK;
+}
+
+// Work that writes `denoised` outside the async rotation must not overtake an image copy still reading it.
+static int order_after_copies(svgf_ctx *c) {
+    for (int i = 0; i < 2; i++) if (c->copy_pending[i]) CK(cudaStreamWaitEvent(c->stream, c->copy_done[i], 0));
+    return SVGF_OK;
+}
+
+static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, float *host_image, bool async) {
     if (!c || !cam || !P) return SVGF_ERR_INVALID;
     if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_render: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
     if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS || P->tracedepth < 0) { c->err = "svgf_render: parameter out of range"; return SVGF_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
+    if (async && host_image) {
+        int rc = async_setup(c);
+        if (rc != SVGF_OK) return rc;
+        if (!host_is_registered(c, host_image, c->px * 12)) { c->err = "svgf_render_async: host_image cannot be page-locked"; return SVGF_ERR_INVALID; }
+        // this frame writes the buffer whose copy was queued two frames ago: that copy must have drained
+        std::swap(c->denoised, c->denoised_alt);
+        c->copy_slot ^= 1;
+        if (c->copy_pending[c->copy_slot]) CK(cudaStreamWaitEvent(c->stream, c->copy_done[c->copy_slot], 0));
+    } else {
+        int rc = order_after_copies(c);
+        if (rc != SVGF_OK) return rc;
+    }
     cudaEvent_t *ev = prof_begin(c, P);
     c->seq++;
     // before this frame overwrites planes that peers read in place, they must have finished the previous frame
@@ -566,8 +615,15 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     unsigned char *pbo = pbo_dev ? static_cast<unsigned char *>(pbo_dev) : c->pbo_own;
     CK(launch_pack_pbo(c, pbo, c->image, c->denoised));
     if (ev) CK(cudaEventRecord(ev[10], c->stream));
-    if (host_image) {   // pathtrace.cu:450 (scene->state.image): synchronous like the reference, but a pinned DMA
-        const size_t off = (size_t)c->shard.row_begin * c->W * 3, n = (size_t)(c->shard.row_end - c->shard.row_begin) * c->W * 3;
+    const size_t off = (size_t)c->shard.row_begin * c->W * 3, n = (size_t)(c->shard.row_end - c->shard.row_begin) * c->W * 3;
+    if (host_image && async) {
+        if (ev) CK(cudaEventRecord(ev[11], c->stream));
+        CK(cudaEventRecord(c->frame_done, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->frame_done, 0));
+        CK(cudaMemcpyAsync(host_image + off, c->denoised + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaEventRecord(c->copy_done[c->copy_slot], c->copy_stream));
+        c->copy_pending[c->copy_slot] = 1; c->copy_host[c->copy_slot] = host_image;
+    } else if (host_image) {   // pathtrace.cu:450 (scene->state.image): synchronous like the reference, but a pinned DMA
         if (host_is_registered(c, host_image, c->px * 12)) {
             CK(cudaMemcpyAsync(host_image + off, c->denoised + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
             if (ev) CK(cudaEventRecord(ev[11], c->stream));
@@ -584,6 +640,26 @@ extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_param
     return SVGF_OK;
 }
 
+extern "C" int svgf_render(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, float *host_image) {
+    return render_impl(c, cam, P, frame, pbo_dev, host_image, false);
+}
+
+extern "C" int svgf_render_async(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, float *host_image) {
+    return render_impl(c, cam, P, frame, pbo_dev, host_image, true);
+}
+
+// Blocks until the image most recently queued into `host_image` by svgf_render_async has arrived (NULL: all of them).
+extern "C" int svgf_wait_image(svgf_ctx *c, const float *host_image) {
+    if (!c) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < 2; i++)
+        if (c->copy_pending[i] && (!host_image || c->copy_host[i] == host_image)) {
+            CK(cudaEventSynchronize(c->copy_done[i]));
+            c->copy_pending[i] = 0;
+        }
+    return SVGF_OK;
+}
+
 extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_dev, const svgf_gbuffer_texel *gbuffer_dev,
                             const svgf_camera *cam, const svgf_params *P) {
     if (!c || !output_dev || !input_dev || !gbuffer_dev || !cam || !P) return SVGF_ERR_INVALID;
@@ -591,6 +667,7 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS) { c->err = "svgf_denoise: atrous_nlevel out of range"; return SVGF_ERR_INVALID; }
     if (c->shard.world > 1) { c->err = "svgf_denoise: the AoS entry point is single-GPU; sharded frames go through svgf_render"; return SVGF_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
+    { int rc = order_after_copies(c); if (rc != SVGF_OK) return rc; }
     cudaEvent_t *ev = prof_begin(c, P);
     if (ev) { CK(cudaEventRecord(ev[0], c->stream)); CK(cudaEventRecord(ev[1], c->stream)); }
     float kn, kx;

@@ -16,6 +16,8 @@
 
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda/barrier>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -134,19 +136,26 @@ atrous_direct_kernel(AtrousK k) {
 //   The two parities land in separate halves so that a quarter-warp reads 8 consecutive float4 (lane = (ap, c));
 //   out-of-range coordinates are zero-filled by the hardware and only border tiles run a fix-up pass (lum = 3e38).
 //   Tiles that need rows owned by another GPU (sharded frames) fall back to per-thread cp.async from the owner's memory.
-constexpr int AT_C = 2, AT_TX = 2, AT_TY = 4;
-// Tile shape <LX, LY> (lattice points per block, LX * LY = 512): 16x32 for fine levels, 32x16 when the lattice of a
-// residue class is short (coarse levels: 34 lattice rows at step 32 for 1080 rows; narrow strips of a sharded frame).
-template <int LX, int LY> struct AtShape {
+constexpr int AT_C = 2, AT_TX = 2;
+// Tile shape <LX, LY, TY>: LX x LY lattice points (x 2 columns) per block, every thread a 2 x TY patch of them.
+//   TY = 4: 128 threads per 512 points, 168 registers, 69 KB -> 3 blocks (12 warps) per SM; 4.2 pair evaluations per tap read.
+//   TY = 2: twice the threads per point at half the registers (more warps to hide the MUFU/LDS latencies, 2.8 pairs per tap
+//           read), and 16 x 16 tiles of 38 KB so that 5 blocks per SM overlap their tile loads with each other's arithmetic.
+// 16x32 suits fine levels, 32x16 / 32x12 lattices that are short (coarse levels: 34 lattice rows at step 32 for 1080 rows;
+// narrow strips of a sharded frame). launch_atrous() picks per level; SVGF_ATROUS_SHAPE=<id> forces one (A/B runs).
+template <int LX, int LY, int TY_> struct AtShape {
+    static constexpr int TY = TY_;
     static constexpr int SW = LX + 4, SH = LY + 4;                  // staged lattice points (tile + 2-point apron)
-    static constexpr int THREADS = (LX / AT_TX) * (LY / AT_TY) * AT_C;
+    static constexpr int THREADS = (LX / AT_TX) * (LY / TY) * AT_C;
     static constexpr int TILE = SW * SH * AT_C;                     // taps
     static constexpr int HALF = SH * (SW / 2) * AT_C;               // taps of one column parity = one TMA box
     static constexpr int SMEM = TILE * 48 + 16;                     // + mbarrier
+    // TMA destinations (every plane, and the second parity half of every plane) must be 128-byte aligned
+    static constexpr bool OK = HALF * 8 % 128 == 0 && TILE * 8 % 128 == 0 && THREADS % 32 == 0 && LX % 2 == 0 && LY % TY == 0;
     // [column parity][lattice row][column pair][c]  -- the order a TMA box arrives in
     __device__ static __forceinline__ int idx(int c, int tb, int ta) { return (ta & 1) * HALF + (tb * (SW / 2) + (ta >> 1)) * AT_C + c; }
 };
-static_assert(AtShape<16, 32>::HALF * 8 % 128 == 0 && AtShape<32, 16>::HALF * 8 % 128 == 0, "TMA destinations must be 128-byte aligned");
+
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -265,18 +274,18 @@ __device__ __forceinline__ void at_pair(const AtTap &T, const AtCentre &C, AtAcc
 // two centre columns the tap column reaches (|i| <= 2), so the edge columns are peeled without wasted work.
 template <class SH, bool DO0, bool DO1>
 __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np, const float2 *s_zl, const float2 *s_lv, int c, int row0, int col,
-                                          const AtCentre (&C)[AT_TX][AT_TY], AtAcc (&A)[AT_TX][AT_TY], float hi0, float hi1) {
+                                          const AtCentre (&C)[AT_TX][SH::TY], AtAcc (&A)[AT_TX][SH::TY], float hi0, float hi1) {
     // h = hi * hj with hj in {3/8, 1/4, 1/16} for |j| = 0, 1, 2
     const float h0[3] = {hi0 * 0.375f, hi0 * 0.25f, hi0 * 0.0625f}, h1[3] = {hi1 * 0.375f, hi1 * 0.25f, hi1 * 0.0625f};
 #pragma unroll
-    for (int u = 0; u < AT_TY + 4; u++) {
+    for (int u = 0; u < SH::TY + 4; u++) {
         const int si = SH::idx(c, row0 + u, col);
         const float4 np = s_np[si];
         AtTap T;
         T.cv = s_cv[si];
         T.nx_px = make_float2(np.x, np.y); T.ny_py = make_float2(np.z, np.w); T.nz_pz = s_zl[si]; T.lum = s_lv[si].x;
 #pragma unroll
-        for (int cb = 0; cb < AT_TY; cb++) {
+        for (int cb = 0; cb < SH::TY; cb++) {
             const int j = u - 2 - cb, aj = j < 0 ? -j : j;
             if (aj > 2) continue;       // compile-time
             if (DO0) at_pair(T, C[0][cb], A[0][cb], h0[aj]);
@@ -287,10 +296,11 @@ __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np
 
 namespace cde = cuda::device::experimental;
 
-template <int LX, int LY>
-__global__ void __launch_bounds__((AtShape<LX, LY>::THREADS), 3)
+template <int LX, int LY, int AT_TY, int MINB>
+__global__ void __launch_bounds__((AtShape<LX, LY, AT_TY>::THREADS), MINB)
 atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
-    using SH = AtShape<LX, LY>;
+    using SH = AtShape<LX, LY, AT_TY>;
+    static_assert(SH::OK, "tile shape");
     constexpr int AT_LX = LX, AT_SW = SH::SW, AT_SH = SH::SH, AT_THREADS = SH::THREADS, TILE = SH::TILE, HALF = SH::HALF;
     extern __shared__ __align__(128) unsigned char at_smem_raw[];
     float4 *s_cv = reinterpret_cast<float4 *>(at_smem_raw), *s_np = s_cv + TILE;
@@ -382,7 +392,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     for (int ca = 0; ca < AT_TX; ca++)
 #pragma unroll
         for (int cb = 0; cb < AT_TY; cb++) {
-            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + 4 * bq + cb + 2) * step;
+            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + AT_TY * bq + cb + 2) * step;
             const bool ok = x < W && y >= k.row_begin && y < k.row_end;
             live |= ok;
             c_kl[ca][cb] = ok ? __ldg(&t.kl[x + y * W]) : 0.f;
@@ -397,7 +407,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     for (int ca = 0; ca < AT_TX; ca++)
 #pragma unroll
         for (int cb = 0; cb < AT_TY; cb++) {
-            const int si = SH::idx(c, 4 * bq + cb + 2, 2 * ap + ca + 2);
+            const int si = SH::idx(c, AT_TY * bq + cb + 2, 2 * ap + ca + 2);
             const float4 np = s_np[si]; const float2 zl = s_zl[si];
             C[ca][cb].nx_px = make_float2(-np.x, -np.y); C[ca][cb].ny_py = make_float2(-np.z, -np.w);
             C[ca][cb].nz_pz = make_float2(-zl.x, -zl.y); C[ca][cb].lum = s_lv[si].x; C[ca][cb].kl = c_kl[ca][cb];
@@ -408,7 +418,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     // large basic block (8 taps, 40 independent pair evaluations: plenty of ILP for 12 warps/SM, 13 KB of SASS);
     // columns 0 and 5 reach one centre column each and are peeled. The centre tap takes the generic path: all
     // differences are 0, sqrt(0) = 0, ex2(-0) = 1 exactly. ----
-    const int row0 = 4 * bq, col0 = 2 * ap;
+    const int row0 = AT_TY * bq, col0 = 2 * ap;
     at_column<SH, true, false>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + 0, C, A, 0.0625f, 0.f);        // i = -2 for centre column 0
 #pragma unroll 1
     for (int tt = 1; tt <= 4; tt++) {
@@ -426,7 +436,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     for (int ca = 0; ca < AT_TX; ca++)
 #pragma unroll
         for (int cb = 0; cb < AT_TY; cb++) {
-            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + 4 * bq + cb + 2) * step;
+            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + AT_TY * bq + cb + 2) * step;
             op[ca][cb] = (x < W && y >= k.row_begin && y < k.row_end) ? x + y * W : -1;
             // weights_sum >= 9/64 always (the centre tap), so the reference's `else` branch (denoise.cu:162-164) is dead
             const AtAcc &a = A[ca][cb];
@@ -472,6 +482,35 @@ void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx) {
     *kx = (float)(log2e / ((double)sigma_x + 1e-6));
 }
 
+// ---- tile shapes ------------------------------------------------------------------------------------------------------
+// One entry per instantiation of the tiled kernel. `warp_rows` = lattice rows one warp covers (work is issued per warp, and a
+// warp whose patches all lie outside the strip exits right after the tile has landed).
+struct AtShapeInfo {
+    int lx, ly, ty, threads, smem, warp_rows;
+    const void *fn;
+    void (*launch)(dim3 grid, cudaStream_t st, const AtrousT &t);
+};
+template <int LX, int LY, int TY, int MINB> static void at_launch(dim3 grid, cudaStream_t st, const AtrousT &t) {
+    using SH = AtShape<LX, LY, TY>;
+    atrous_tiled_kernel<LX, LY, TY, MINB><<<grid, SH::THREADS, SH::SMEM, st>>>(t);
+}
+template <int LX, int LY, int TY, int MINB> static AtShapeInfo at_info() {
+    using SH = AtShape<LX, LY, TY>;
+    return AtShapeInfo{LX, LY, TY, SH::THREADS, SH::SMEM, (32 / LX > 0 ? 32 / LX : 1) * TY,
+                       (const void *)atrous_tiled_kernel<LX, LY, TY, MINB>, at_launch<LX, LY, TY, MINB>};
+}
+enum { AT_NSHAPES = 8 };
+static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
+    at_info<16, 32, 4, 3>(),    // 0: 128 threads, 69 KB, 3 blocks/SM
+    at_info<32, 16, 4, 3>(),    // 1: 128 threads, 69 KB, 3 blocks/SM
+    at_info<16, 16, 2, 5>(),    // 2: 128 threads, 38 KB, 5 blocks/SM (20 warps)
+    at_info<16, 32, 2, 2>(),    // 3: 256 threads, 69 KB, 2-3 blocks/SM (16-24 warps)
+    at_info<32, 16, 2, 2>(),    // 4: 256 threads, 69 KB
+    at_info<16, 24, 4, 4>(),    // 5:  96 threads, 54 KB, 4 blocks/SM
+    at_info<32, 12, 4, 4>(),    // 6:  96 threads, 55 KB, 4 blocks/SM (34 lattice rows = 3 tiles)
+    at_info<16, 32, 2, 3>(),    // 7: 256 threads, 69 KB, 3 blocks/SM (24 warps, 80 registers)
+};
+
 // ---- TMA descriptors ------------------------------------------------------------------------------------------------
 // The lattice of residue class (., yc) with sub-columns [X0, X0+2) of a row-major plane with `fpp` floats per pixel is
 // the 5-D tensor  {j: fpp*s floats of one s-pixel cell | parity of the cell | cell pair | row inside the s-row band | band}
@@ -481,7 +520,7 @@ void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx) {
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-enum { TM_PLANES = 8, TM_LEVELS = SVGF_MAX_LEVELS + 1, TM_SHAPES = 2 };
+enum { TM_PLANES = 8, TM_LEVELS = SVGF_MAX_LEVELS + 1, TM_SHAPES = AT_NSHAPES };
 static inline CUtensorMap *tmap_at(svgf_ctx *c, int plane, int level, int shape) {
     return static_cast<CUtensorMap *>(c->tmaps) + ((plane * TM_LEVELS + level) * TM_SHAPES + shape);
 }
@@ -498,24 +537,44 @@ int atrous_build_tensor_maps(svgf_ctx *c) {
     encode_fn_t encode = reinterpret_cast<encode_fn_t>(fn);
     if (!c->tmaps) c->tmaps = aligned_alloc(64, sizeof(CUtensorMap) * TM_PLANES * TM_LEVELS * TM_SHAPES);
     if (!c->tmaps) return 0;
+    // L2 promotion: a tile row is one 32-byte sector per (lattice point, plane); the sectors next to it belong to the column
+    // groups that the neighbouring blocks (adjacent blockIdx.x) load at about the same time. SVGF_TMA_L2PROMO=0..3 (A/B runs).
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    if (const char *v = getenv("SVGF_TMA_L2PROMO")) {
+        const int q = atoi(v);
+        promo = q == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : q == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : q == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo;
+    }
     void *planes[TM_PLANES] = {c->cv[0], c->cv[1], c->cv[2], c->lv[0], c->lv[1], c->lv[2], c->gnp, c->gzl};
     const int fpp[TM_PLANES] = {4, 4, 4, 2, 2, 2, 4, 2};
-    const int sw[TM_SHAPES] = {AtShape<16, 32>::SW, AtShape<32, 16>::SW}, sh[TM_SHAPES] = {AtShape<16, 32>::SH, AtShape<32, 16>::SH};
     for (int pl = 0; pl < TM_PLANES; pl++)
         for (int level = 1; level <= SVGF_MAX_LEVELS; level++)
             for (int shp = 0; shp < TM_SHAPES; shp++) {
+                const int sw = g_at_shapes[shp].lx + 4, sh = g_at_shapes[shp].ly + 4;
                 const cuuint64_t s = 1ull << level, W = c->W, H = c->H, f = fpp[pl];
                 const cuuint64_t dims[5] = {f * s, 2, (W + 2 * s - 1) / (2 * s), s, (H + s - 1) / s};
                 const cuuint64_t strides[4] = {f * 4 * s, f * 4 * 2 * s, f * 4 * W, f * 4 * s * W};
-                const cuuint32_t box[5] = {(cuuint32_t)(f * AT_C), 1, (cuuint32_t)(sw[shp] / 2), 1, (cuuint32_t)sh[shp]};
+                const cuuint32_t box[5] = {(cuuint32_t)(f * AT_C), 1, (cuuint32_t)(sw / 2), 1, (cuuint32_t)sh};
                 const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
                 CUresult r = encode(tmap_at(c, pl, level, shp), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, planes[pl], dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) return 0;
             }
     c->tma_ok = 1;
     return 1;
+}
+
+// Which tile shape for a lattice of lat_w x lat_rows points per residue class. Cost model: blocks are charged for the
+// tile they stage (every block loads its whole tile, live or not) and warps for the patches they compute.
+static int at_pick_shape(const svgf_ctx *c, int level, int lat_w, int lat_rows) {
+    if (c->atrous_shape >= 0 && c->atrous_shape < AT_NSHAPES) return c->atrous_shape;
+    if (c->atrous_shape_level[level] >= 0 && c->atrous_shape_level[level] < AT_NSHAPES) return c->atrous_shape_level[level];
+    auto up = [](int n, int m) { return (double)(((n + m - 1) / m) * m); };
+    auto padded = [&](int s) {
+        const AtShapeInfo &i = g_at_shapes[s];
+        return up(lat_w, i.lx) * up(lat_rows, i.warp_rows) + 0.15 * up(lat_w, i.lx) * up(lat_rows, i.ly);
+    };
+    return padded(0) <= padded(1) ? 0 : 1;
 }
 
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
@@ -556,11 +615,8 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     t.ncg = step / AT_C;
     const int lat_w = (c->W + step - 1) / step;                                 // lattice columns per class
     const int lat_rows = (k.row_end - 1) / step - t.b_first + 1;                // lattice rows touching the strip
-    // pick the tile shape that wastes fewer lattice points (work is issued per warp: 16 x 8 resp. 32 x 4 points)
-    auto padded = [&](int lx, int ly, int wy) {
-        return (double)(((lat_w + lx - 1) / lx) * lx) * (((lat_rows + wy - 1) / wy) * wy) + 0.15 * (double)(((lat_w + lx - 1) / lx) * lx) * (((lat_rows + ly - 1) / ly) * ly);
-    };
-    const int shape = padded(16, 32, 8) <= padded(32, 16, 4) ? 0 : 1;
+    const int shape = at_pick_shape(c, a.level, lat_w, lat_rows);
+    const AtShapeInfo &si = g_at_shapes[shape];
     t.use_tma = c->tma_ok && a.src_slot >= 0 && c->atrous_variant != 3;
     if (t.use_tma) {
         t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, 3 + a.src_slot, a.level, shape);
@@ -570,17 +626,14 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
         memset(&t.tm_np, 0, sizeof(CUtensorMap)); memset(&t.tm_zl, 0, sizeof(CUtensorMap));
     }
     if (!c->atrous_attr_set) {      // per context (= per device)
-        cudaError_t e = cudaFuncSetAttribute(atrous_tiled_kernel<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtShape<16, 32>::SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(atrous_tiled_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtShape<32, 16>::SMEM);
-        if (e != cudaSuccess) return e;
+        for (int s = 0; s < AT_NSHAPES; s++) {
+            cudaError_t e = cudaFuncSetAttribute(g_at_shapes[s].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_at_shapes[s].smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(g_at_shapes[s].fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
         c->atrous_attr_set = true;
     }
-    if (shape == 0) {
-        dim3 g(((lat_w + 15) / 16) * t.ncg, ((lat_rows + 31) / 32) * step);
-        atrous_tiled_kernel<16, 32><<<g, AtShape<16, 32>::THREADS, AtShape<16, 32>::SMEM, c->stream>>>(t);
-    } else {
-        dim3 g(((lat_w + 31) / 32) * t.ncg, ((lat_rows + 15) / 16) * step);
-        atrous_tiled_kernel<32, 16><<<g, AtShape<32, 16>::THREADS, AtShape<32, 16>::SMEM, c->stream>>>(t);
-    }
+    dim3 g(((lat_w + si.lx - 1) / si.lx) * t.ncg, ((lat_rows + si.ly - 1) / si.ly) * step);
+    si.launch(g, c->stream, t);
     return cudaGetLastError();
 }

@@ -97,6 +97,9 @@ struct svgf_ctx {
     int halo_push = 1;
     int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled (TMA tile loads), 3 = lattice-tiled (cp.async)
     bool atrous_attr_set = false;
+    // tile shape of the lattice-tiled kernel (index into atrous.cu's table): -1 = chosen per level by the cost model;
+    // SVGF_ATROUS_SHAPE=<id> forces one for every level, SVGF_ATROUS_SHAPES=<id>,<id>,... one per level (A/B runs)
+    int atrous_shape = -1, atrous_shape_level[SVGF_MAX_LEVELS + 1] = {-1, -1, -1, -1, -1, -1, -1, -1};
     int rt_variant = 0;                 // 0 = state machine, one pixel per thread (default), 1 = wavefront (stage kernels +
                                         // ballot-compacted queues), 2 = persistent state machine with work refill
     unsigned int *rt_counter = nullptr; int rt_blocks = 0;
@@ -120,6 +123,13 @@ struct svgf_ctx {
     // scratch for the AoS entry point svgf_denoise() and the host conveniences
     float *aos_in = nullptr, *aos_out = nullptr; svgf_gbuffer_texel *aos_g = nullptr;
     float *pinned_image = nullptr;      // W*H*3 pinned staging for the per-frame D2H
+    // svgf_render_async: the image of frame N is copied out on copy_stream while frame N+1 renders; `denoised` and
+    // `denoised_alt` swap every async frame, copy_done[slot] gates the reuse of a buffer two frames later
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t frame_done = nullptr, copy_done[2] = {nullptr, nullptr};
+    float *denoised_alt = nullptr;
+    int copy_slot = 0, copy_pending[2] = {0, 0};
+    const float *copy_host[2] = {nullptr, nullptr};
 
     float view_matrix_prev[16];         // denoise.cu:15; identity until the first denoise (glm::mat4())
     int last_variance_valid = 0;        // var_out holds the final variance of the last frame

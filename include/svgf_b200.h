@@ -160,6 +160,15 @@ int svgf_reset(svgf_ctx *ctx);
  * given; otherwise work is left queued on the context's stream (svgf_sync to wait). */
 int svgf_render(svgf_ctx *ctx, const svgf_camera *cam, const svgf_params *params, int frame,
                 void *pbo_dev, float *host_image);
+/* Pipelined form of svgf_render (the reference blocks on a pageable D2H every frame,
+ * pathtrace.cu:450). Queues the frame AND the copy of its image into `host_image` (page-locked by the library on first
+ * sight) and returns; the copy runs on a second stream while the next frame renders. `host_image` holds the frame once
+ * svgf_wait_image(ctx, host_image) (or svgf_sync) has returned; alternate between two host buffers to keep one frame in
+ * flight. Results are bit-identical to svgf_render. */
+int svgf_render_async(svgf_ctx *ctx, const svgf_camera *cam, const svgf_params *params, int frame,
+                      void *pbo_dev, float *host_image);
+/* Blocks until the image most recently queued into `host_image` has arrived (NULL: every queued image). */
+int svgf_wait_image(svgf_ctx *ctx, const float *host_image);
 /* == denoise(output, input, gbuffer), denoise.cu:349-402, on caller-owned DEVICE buffers in the reference's
  * AoS layouts (vec3 colour, 52-byte texels). */
 int svgf_denoise(svgf_ctx *ctx, float *output_dev, const float *input_dev, const svgf_gbuffer_texel *gbuffer_dev,

@@ -30,6 +30,46 @@ def test_level_matches_oracle(level, size):
     R.close()
 
 
+@pytest.mark.parametrize("shape", range(8))
+def test_every_tile_shape_matches_oracle(shape, monkeypatch):
+    """The lattice-tiled kernel is instantiated for several tile shapes / patch heights (csrc/atrous.cu, g_at_shapes);
+    launch_atrous picks one per level. Force each of them (SVGF_ATROUS_SHAPE is read at svgf_create) and check it against
+    the oracle on a ragged size, at a fine and a coarse level, with the last-level albedo modulation on the coarse one."""
+    monkeypatch.setenv("SVGF_ATROUS_SHAPE", str(shape))
+    W, H = 334, 141
+    m, R = ctx_for(W, H)
+    color, var, g = synthetic_planes(W, H, seed=40 + shape)
+    for level, last in ((1, False), (4, True)):
+        co, vo = R.atrous_level(color, var, g, level, last, m.default_params())
+        oc, ov = orc.atrous_level(color, var, g, level, last, orc.default_params())
+        assert_close(co, oc, COLOR_FLOOR, "shape %d colour L%d" % (shape, level))
+        assert_close(vo, ov, VAR_FLOOR, "shape %d variance L%d" % (shape, level))
+    R.close()
+
+
+@pytest.mark.parametrize("shape", [2, 6])
+def test_tile_shapes_in_the_frame_path(shape, monkeypatch):
+    """Whole frames with a forced tile shape equal the default shape choice bit for bit (same arithmetic per pixel; only
+    the tiling differs), odd width included (cp.async loader instead of TMA)."""
+    out = []
+    for forced in (None, shape):
+        if forced is None:
+            monkeypatch.delenv("SVGF_ATROUS_SHAPE", raising=False)
+        else:
+            monkeypatch.setenv("SVGF_ATROUS_SHAPE", str(forced))
+        m = svgf()
+        blob, R = m.open_scene("cornell", 131, 77)
+        P = m.default_params(atrous_nlevel=5)
+        drv = blob.camera_driver(131, 77)
+        host = np.zeros((77, 131, 3), np.float32)
+        for f in range(3):
+            R.pathtrace(drv.step(), P, f, host_image=host)
+        out.append((host.copy(), R.fetch("variance")))
+        R.close()
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
+
+
 @pytest.mark.parametrize("over", [{}, {"blurvariance": 0}, {"addcolor": 0}, {"sigmal": 2.0, "sigman": 1.0, "sigmax": 1.0},
                                   {"sigmal": 0.01, "sigman": 0.01, "sigmax": 0.01}])
 def test_last_level_and_parameter_variants(over):
