@@ -232,6 +232,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     if (const char *v = getenv("SVGF_HALO")) c->halo_push = strcmp(v, "pull") != 0;      // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3) ? atoi(v) : 2;    // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_SHAPE")) c->atrous_shape = atoi(v);
+    if (const char *v = getenv("SVGF_ATROUS_PROBE")) c->atrous_probe = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_SHAPES")) {      // "a,b,c,...": shape of level 1, 2, 3, ...
         int level = 1;
         for (const char *q = v; *q && level <= SVGF_MAX_LEVELS; level++) {

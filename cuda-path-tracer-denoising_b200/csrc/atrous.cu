@@ -172,6 +172,7 @@ struct AtrousT {
     int b_first;        // first lattice row index covered by the grid (row_begin / step)
     int ncg;            // column groups per class row: step / C
     int use_tma;
+    int probe;          // timing probes (SVGF_ATROUS_PROBE, never set in production): 1 = skip the tile load, 2 = skip the arithmetic
     const float *kl;    // per-pixel luminance-weight scale from atrous_kl_kernel
     alignas(64) CUtensorMap tm_cv, tm_np, tm_zl, tm_lv;
 };
@@ -322,7 +323,9 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     const bool remote = t.ro.world > 1 && yt0 <= yt1 && (yt0 < t.ro.start[t.me] || yt1 >= t.ro.start[t.me + 1]);
     const bool tma = t.use_tma && !remote;
 
-    if (tma) {
+    if (t.probe == 1) {
+        // timing probe: arithmetic on whatever shared memory holds
+    } else if (tma) {
         if (tid == 0) {
             init(&bar, AT_THREADS);
             cde::fence_proxy_async_shared_cta();
@@ -400,6 +403,10 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     if (!tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (!live) return;
+    if (t.probe == 2) {     // timing probe: tile load + kl only; one store keeps the loads alive
+        if (c_kl[0][0] == 123.456f) k.var_out[0] = s_cv[tid].x;
+        return;
+    }
 
     AtCentre C[AT_TX][AT_TY];
     AtAcc A[AT_TX][AT_TY];
@@ -499,7 +506,7 @@ template <int LX, int LY, int TY, int MINB> static AtShapeInfo at_info() {
     return AtShapeInfo{LX, LY, TY, SH::THREADS, SH::SMEM, (32 / LX > 0 ? 32 / LX : 1) * TY,
                        (const void *)atrous_tiled_kernel<LX, LY, TY, MINB>, at_launch<LX, LY, TY, MINB>};
 }
-enum { AT_NSHAPES = 8 };
+enum { AT_NSHAPES = 11 };
 static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
     at_info<16, 32, 4, 3>(),    // 0: 128 threads, 69 KB, 3 blocks/SM
     at_info<32, 16, 4, 3>(),    // 1: 128 threads, 69 KB, 3 blocks/SM
@@ -509,6 +516,9 @@ static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
     at_info<16, 24, 4, 4>(),    // 5:  96 threads, 54 KB, 4 blocks/SM
     at_info<32, 12, 4, 4>(),    // 6:  96 threads, 55 KB, 4 blocks/SM (34 lattice rows = 3 tiles)
     at_info<16, 32, 2, 3>(),    // 7: 256 threads, 69 KB, 3 blocks/SM (24 warps, 80 registers)
+    at_info<32, 8, 2, 5>(),     // 8: 128 threads, 41 KB, 5 blocks/SM (lattices of a few rows: strips of a sharded frame)
+    at_info<16, 12, 2, 6>(),    // 9:  96 threads, 31 KB, 6-7 blocks/SM
+    at_info<32, 12, 2, 3>(),    // 10: 192 threads, 55 KB, 3 blocks/SM
 };
 
 // ---- TMA descriptors ------------------------------------------------------------------------------------------------
@@ -564,17 +574,18 @@ int atrous_build_tensor_maps(svgf_ctx *c) {
     return 1;
 }
 
-// Which tile shape for a lattice of lat_w x lat_rows points per residue class. Cost model: blocks are charged for the
-// tile they stage (every block loads its whole tile, live or not) and warps for the patches they compute.
+// Which tile shape for a lattice of lat_w x lat_rows points per residue class. Measured on B200 (tools/ab_atrous.py, us per
+// level, cornell): every block stages its whole tile, live or not, and a warp with no live patch exits, so what counts is
+// how many blocks are mostly dead and how many warps per SM stay busy.
+//   1080p, whole frame (lattice rows 540/270/135/68/34):  shape 2: 88 89 93 101 132 | shape 9: 91 93 94  99 118 | shape 0: 93 98 105 126 173
+//   4K, strip of 270 rows  (lattice rows 135/68/34/17/9):  shape 2: 54 54 60  71  82 | shape 9: 55 54 56  62  73 | shape 0: 59 61  68  84  91
+// 2 x 2 patches (20 warps/SM) beat 2 x 4 patches (12 warps/SM) at every level; 16 x 16 tiles win while the lattice is tall,
+// 16 x 12 tiles (6-7 blocks/SM, 3 tiles for 34 rows) once it is short.
 static int at_pick_shape(const svgf_ctx *c, int level, int lat_w, int lat_rows) {
     if (c->atrous_shape >= 0 && c->atrous_shape < AT_NSHAPES) return c->atrous_shape;
     if (c->atrous_shape_level[level] >= 0 && c->atrous_shape_level[level] < AT_NSHAPES) return c->atrous_shape_level[level];
-    auto up = [](int n, int m) { return (double)(((n + m - 1) / m) * m); };
-    auto padded = [&](int s) {
-        const AtShapeInfo &i = g_at_shapes[s];
-        return up(lat_w, i.lx) * up(lat_rows, i.warp_rows) + 0.15 * up(lat_w, i.lx) * up(lat_rows, i.ly);
-    };
-    return padded(0) <= padded(1) ? 0 : 1;
+    (void)lat_w;
+    return lat_rows >= 100 ? 2 : 9;
 }
 
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
@@ -618,6 +629,7 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     const int shape = at_pick_shape(c, a.level, lat_w, lat_rows);
     const AtShapeInfo &si = g_at_shapes[shape];
     t.use_tma = c->tma_ok && a.src_slot >= 0 && c->atrous_variant != 3;
+    t.probe = c->atrous_probe;
     if (t.use_tma) {
         t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, 3 + a.src_slot, a.level, shape);
         t.tm_np = *tmap_at(c, 6, a.level, shape); t.tm_zl = *tmap_at(c, 7, a.level, shape);

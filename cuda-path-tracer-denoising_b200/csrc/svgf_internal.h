@@ -99,6 +99,7 @@ struct svgf_ctx {
     bool atrous_attr_set = false;
     // tile shape of the lattice-tiled kernel (index into atrous.cu's table): -1 = chosen per level by the cost model;
     // SVGF_ATROUS_SHAPE=<id> forces one for every level, SVGF_ATROUS_SHAPES=<id>,<id>,... one per level (A/B runs)
+    int atrous_probe = 0;               // SVGF_ATROUS_PROBE: timing probes of the tiled kernel (results are garbage)
     int atrous_shape = -1, atrous_shape_level[SVGF_MAX_LEVELS + 1] = {-1, -1, -1, -1, -1, -1, -1, -1};
     int rt_variant = 0;                 // 0 = state machine, one pixel per thread (default), 1 = wavefront (stage kernels +
                                         // ballot-compacted queues), 2 = persistent state machine with work refill

@@ -16,12 +16,17 @@ sys.path.insert(0, ROOT)
 from bench import WORKLOADS, C5_SPEEDS  # noqa: E402
 
 
+STRIP = None
+
+
 def run(m, wl, frames, env):
     for k in ("SVGF_ATROUS_SHAPE", "SVGF_ATROUS_SHAPES", "SVGF_TMA_L2PROMO", "SVGF_ATROUS_VARIANT"):
         os.environ.pop(k, None)
     os.environ.update(env)
     W, H, nl = wl["W"], wl["H"], wl["nlevel"]
     blob, R = m.open_scene(wl["scene"], W, H)
+    if STRIP:       # one rank's share of a sharded frame (taps outside the strip read this context's own planes)
+        R.set_shard(0, 1, STRIP[0], STRIP[1])
     P = m.default_params(atrous_nlevel=nl)
     drv = blob.camera_driver(W, H, automate=wl["moving"])
     f = 0
@@ -34,7 +39,7 @@ def run(m, wl, frames, env):
     R.set_profiling(False)
     R.close()
     lv = [round(float(st[2 + l]) * 1e3, 2) for l in range(nl)]
-    return {"env": env, "workload": wl["name"], "rt_us": round(float(st[0]) * 1e3, 1), "temporal_us": round(float(st[1]) * 1e3, 1),
+    return {"env": env, "workload": wl["name"], "strip": STRIP, "rt_us": round(float(st[0]) * 1e3, 1), "temporal_us": round(float(st[1]) * 1e3, 1),
             "level_us": lv, "atrous_us": round(sum(lv), 1), "frame_us": round(float(st[10]) * 1e3, 1)}
 
 
@@ -44,8 +49,12 @@ def main():
     ap.add_argument("--frames", type=int, default=30)
     ap.add_argument("--shapes", default="0,1,2,3,4,5,6,7")
     ap.add_argument("--promo", default="")
-    ap.add_argument("--extra", default="", help="semicolon-separated KEY=VAL,KEY=VAL configurations")
+    ap.add_argument("--extra", default="", help="semicolon-separated KEY=VAL+KEY=VAL configurations")
+    ap.add_argument("--strip", default="", help="row_begin,row_end: render only this strip (emulates one rank of a sharded frame)")
     a = ap.parse_args()
+    global STRIP
+    if a.strip:
+        STRIP = tuple(int(v) for v in a.strip.split(","))
     m = importlib.import_module("cuda-path-tracer-denoising_b200")
     wl = WORKLOADS[a.workload]
     cfgs = [{}]
@@ -56,7 +65,7 @@ def main():
             cfgs += [{"SVGF_TMA_L2PROMO": q, "SVGF_ATROUS_SHAPE": s} for s in a.shapes.split(",") if s != ""]
     for e in a.extra.split(";"):
         if e:
-            cfgs.append(dict(kv.split("=") for kv in e.split(",")))
+            cfgs.append(dict(kv.split("=") for kv in e.split("+")))
     for env in cfgs:
         try:
             print(json.dumps(run(m, wl, a.frames, env)), flush=True)
