@@ -247,37 +247,64 @@ atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_
     else for (int i = 0; i < 4; i++) if (x0 + i < W) dst[i] = out[i];
 }
 
-// Edge-stopping weight and accumulation of ONE (tap, centre) pair, written for Blackwell's packed fp32 pipe
-// (FADD2/FMUL2/FFMA2, sm_100+): normal and position differences travel as float2 {n, p} lanes, so the two squared
-// distances cost 6 packed instructions instead of 12, and {sum w, sum w^2} / {b, var} accumulate as pairs.
-struct AtCentre {           // negated so that tap + centre = difference
-    float2 nx_px, ny_py, nz_pz;     // {-kn*n, -kx*p} per component
-    float lum, kl;
+// Edge-stopping weights and accumulation, written for Blackwell's packed fp32 pipe (FADD2/FMUL2/FFMA2, sm_100+).
+//   * distances: normal and position differences travel as float2 {n, p} lanes, so the two squared distances of a pair cost
+//     6 packed instructions instead of 12;
+//   * everything after the square roots is packed ACROSS THE TWO CENTRES of a patch row (ca = 0, 1), which meet the same tap
+//     in tap columns 1..4: {e0, e1} = |{lq, lq} - {l0, l1}| * {kl0, kl1} + {dn0, dn1} + {dp0, dp1}, w = ex2(-e) * {h0, h1}, and
+//     the six sums of both centres advance with six packed instructions. The tap's colour enters as a broadcast operand
+//     (`R.F32` in SASS) and |.| is an operand modifier, so no instruction is spent on forming pairs.
+// Why this matters (tools/pipe_probe.cu on B200, cycles per trip per SM sub-partition): 3 MUFU + 18 scalar FFMA take 36.5
+// cycles although neither pipe needs more than 24 -- MUFU and scalar FMA issue get in each other's way -- while
+// 3 MUFU + 8 FFMA2 + 8 integer adds take 25.0. Per pair the kernel needs 3 MUFU (24 XU cycles) and ~23 FMA-pipe cycles either
+// way; issued as ~12 packed instructions instead of 8 packed + 7 scalar they overlap.
+struct AtCentre2 {          // the two centres of one patch row; G-buffer terms negated so that tap + centre = difference
+    float2 nx_px[AT_TX], ny_py[AT_TX], nz_pz[AT_TX];    // {-kn*n, -kx*p} per component, per centre
+    float2 lum, kl;                                     // {centre 0, centre 1}
 };
-struct AtAcc { float2 w_w2, b_v; float r, g; };
+struct AtAcc2 { float2 w, w2, r, g, b, v; };           // {centre 0, centre 1}: sum w, sum w^2, sum w*rgb, sum w^2*var
 struct AtTap { float4 cv; float2 nx_px, ny_py, nz_pz; float lum; };
 
-__device__ __forceinline__ void at_pair(const AtTap &T, const AtCentre &C, AtAcc &A, float h) {
-    const float2 dx = __fadd2_rn(T.nx_px, C.nx_px), dy = __fadd2_rn(T.ny_py, C.ny_py), dz = __fadd2_rn(T.nz_pz, C.nz_pz);
-    const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));       // {|dn|^2, |dp|^2}
-    const float dn = sqrt_approx(d2.x), dp = sqrt_approx(d2.y);
-    const float e = fmaf(fabsf(T.lum - C.lum), C.kl, dn) + dp;
-    float2 ww;
-    ww.x = h * ex2_approx(-e);
-    ww.y = ww.x * ww.x;
-    A.w_w2 = __fadd2_rn(A.w_w2, ww);
-    A.b_v = __ffma2_rn(make_float2(T.cv.z, T.cv.w), ww, A.b_v);
-    A.r = fmaf(T.cv.x, ww.x, A.r);
-    A.g = fmaf(T.cv.y, ww.x, A.g);
+__device__ __forceinline__ float2 at_dist2(const AtTap &T, float2 cx, float2 cy, float2 cz) {       // {|dn|^2, |dp|^2}
+    const float2 dx = __fadd2_rn(T.nx_px, cx), dy = __fadd2_rn(T.ny_py, cy), dz = __fadd2_rn(T.nz_pz, cz);
+    return __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
 }
 
-// One tap column (window column `tt` of the thread's 6) against the thread's 2 x 4 centres. DO0/DO1 select which of the
+// one tap against both centres of a patch row; h = {h of centre 0, h of centre 1}
+__device__ __forceinline__ void at_twin(const AtTap &T, const AtCentre2 &C, AtAcc2 &A, float2 h) {
+    const float2 d0 = at_dist2(T, C.nx_px[0], C.ny_py[0], C.nz_pz[0]), d1 = at_dist2(T, C.nx_px[1], C.ny_py[1], C.nz_pz[1]);
+    const float2 dn = make_float2(sqrt_approx(d0.x), sqrt_approx(d1.x)), dp = make_float2(sqrt_approx(d0.y), sqrt_approx(d1.y));
+    const float2 dl = __fadd2_rn(make_float2(T.lum, T.lum), make_float2(-C.lum.x, -C.lum.y));
+    const float2 e = __fadd2_rn(__ffma2_rn(make_float2(fabsf(dl.x), fabsf(dl.y)), C.kl, dn), dp);
+    const float2 w = __fmul2_rn(make_float2(ex2_approx(-e.x), ex2_approx(-e.y)), h);
+    const float2 w2 = __fmul2_rn(w, w);
+    A.w = __fadd2_rn(A.w, w);
+    A.w2 = __fadd2_rn(A.w2, w2);
+    A.r = __ffma2_rn(make_float2(T.cv.x, T.cv.x), w, A.r);
+    A.g = __ffma2_rn(make_float2(T.cv.y, T.cv.y), w, A.g);
+    A.b = __ffma2_rn(make_float2(T.cv.z, T.cv.z), w, A.b);
+    A.v = __ffma2_rn(make_float2(T.cv.w, T.cv.w), w2, A.v);
+}
+
+// one tap against ONE centre of the row (tap columns 0 and 5 reach one centre column only): same operations per lane
+template <int CA>
+__device__ __forceinline__ void at_single(const AtTap &T, const AtCentre2 &C, AtAcc2 &A, float h) {
+    const float2 d2 = at_dist2(T, C.nx_px[CA], C.ny_py[CA], C.nz_pz[CA]);
+    const float dn = sqrt_approx(d2.x), dp = sqrt_approx(d2.y);
+    const float lum = CA ? C.lum.y : C.lum.x, kl = CA ? C.kl.y : C.kl.x;
+    const float e = fmaf(fabsf(T.lum - lum), kl, dn) + dp;
+    const float w = ex2_approx(-e) * h, w2 = w * w;
+    if (CA) { A.w.y += w; A.w2.y += w2; A.r.y = fmaf(T.cv.x, w, A.r.y); A.g.y = fmaf(T.cv.y, w, A.g.y); A.b.y = fmaf(T.cv.z, w, A.b.y); A.v.y = fmaf(T.cv.w, w2, A.v.y); }
+    else { A.w.x += w; A.w2.x += w2; A.r.x = fmaf(T.cv.x, w, A.r.x); A.g.x = fmaf(T.cv.y, w, A.g.x); A.b.x = fmaf(T.cv.z, w, A.b.x); A.v.x = fmaf(T.cv.w, w2, A.v.x); }
+}
+
+// One tap column (window column `tt` of the thread's 6) against the thread's 2 x TY centres. DO0/DO1 select which of the
 // two centre columns the tap column reaches (|i| <= 2), so the edge columns are peeled without wasted work.
 template <class SH, bool DO0, bool DO1>
 __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np, const float2 *s_zl, const float2 *s_lv, int c, int row0, int col,
-                                          const AtCentre (&C)[AT_TX][SH::TY], AtAcc (&A)[AT_TX][SH::TY], float hi0, float hi1) {
+                                          const AtCentre2 (&C)[SH::TY], AtAcc2 (&A)[SH::TY], float hi0, float hi1) {
     // h = hi * hj with hj in {3/8, 1/4, 1/16} for |j| = 0, 1, 2
-    const float h0[3] = {hi0 * 0.375f, hi0 * 0.25f, hi0 * 0.0625f}, h1[3] = {hi1 * 0.375f, hi1 * 0.25f, hi1 * 0.0625f};
+    const float2 hh[3] = {make_float2(hi0 * 0.375f, hi1 * 0.375f), make_float2(hi0 * 0.25f, hi1 * 0.25f), make_float2(hi0 * 0.0625f, hi1 * 0.0625f)};
 #pragma unroll
     for (int u = 0; u < SH::TY + 4; u++) {
         const int si = SH::idx(c, row0 + u, col);
@@ -289,8 +316,9 @@ __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np
         for (int cb = 0; cb < SH::TY; cb++) {
             const int j = u - 2 - cb, aj = j < 0 ? -j : j;
             if (aj > 2) continue;       // compile-time
-            if (DO0) at_pair(T, C[0][cb], A[0][cb], h0[aj]);
-            if (DO1) at_pair(T, C[1][cb], A[1][cb], h1[aj]);
+            if (DO0 && DO1) at_twin(T, C[cb], A[cb], hh[aj]);
+            else if (DO0) at_single<0>(T, C[cb], A[cb], hh[aj].x);
+            else at_single<1>(T, C[cb], A[cb], hh[aj].y);
         }
     }
 }
@@ -408,18 +436,22 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
         return;
     }
 
-    AtCentre C[AT_TX][AT_TY];
-    AtAcc A[AT_TX][AT_TY];
+    AtCentre2 C[AT_TY];
+    AtAcc2 A[AT_TY];
 #pragma unroll
-    for (int ca = 0; ca < AT_TX; ca++)
+    for (int cb = 0; cb < AT_TY; cb++) {
+        float cl[AT_TX];
 #pragma unroll
-        for (int cb = 0; cb < AT_TY; cb++) {
+        for (int ca = 0; ca < AT_TX; ca++) {
             const int si = SH::idx(c, AT_TY * bq + cb + 2, 2 * ap + ca + 2);
             const float4 np = s_np[si]; const float2 zl = s_zl[si];
-            C[ca][cb].nx_px = make_float2(-np.x, -np.y); C[ca][cb].ny_py = make_float2(-np.z, -np.w);
-            C[ca][cb].nz_pz = make_float2(-zl.x, -zl.y); C[ca][cb].lum = s_lv[si].x; C[ca][cb].kl = c_kl[ca][cb];
-            A[ca][cb].w_w2 = make_float2(0.f, 0.f); A[ca][cb].b_v = make_float2(0.f, 0.f); A[ca][cb].r = 0.f; A[ca][cb].g = 0.f;
+            C[cb].nx_px[ca] = make_float2(-np.x, -np.y); C[cb].ny_py[ca] = make_float2(-np.z, -np.w);
+            C[cb].nz_pz[ca] = make_float2(-zl.x, -zl.y); cl[ca] = s_lv[si].x;
         }
+        C[cb].lum = make_float2(cl[0], cl[1]); C[cb].kl = make_float2(c_kl[0][cb], c_kl[1][cb]);
+        const float2 z = make_float2(0.f, 0.f);
+        A[cb].w = z; A[cb].w2 = z; A[cb].r = z; A[cb].g = z; A[cb].b = z; A[cb].v = z;
+    }
 
     // ---- 6 tap columns x 8 tap rows. Columns 1..4 reach both centre columns and run as a rolled loop whose body is one
     // large basic block (8 taps, 40 independent pair evaluations: plenty of ILP for 12 warps/SM, 13 KB of SASS);
@@ -446,9 +478,10 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
             const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + AT_TY * bq + cb + 2) * step;
             op[ca][cb] = (x < W && y >= k.row_begin && y < k.row_end) ? x + y * W : -1;
             // weights_sum >= 9/64 always (the centre tap), so the reference's `else` branch (denoise.cu:162-164) is dead
-            const AtAcc &a = A[ca][cb];
-            const float rw = __frcp_rn(a.w_w2.x);
-            o[ca][cb] = make_float4(a.r * rw, a.g * rw, a.b_v.x * rw, __fdividef(a.b_v.y, a.w_w2.y));
+            const AtAcc2 &a = A[cb];
+            const float rw = __frcp_rn(ca ? a.w.y : a.w.x);
+            o[ca][cb] = make_float4((ca ? a.r.y : a.r.x) * rw, (ca ? a.g.y : a.g.x) * rw, (ca ? a.b.y : a.b.x) * rw,
+                                    __fdividef(ca ? a.v.y : a.v.x, ca ? a.w2.y : a.w2.x));
         }
     if (k.is_last && k.addcolor) {
 #pragma unroll
