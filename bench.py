@@ -272,7 +272,7 @@ def run_ours(args, wl, rank, world, local_rank):
     achieved = sum(lv_bytes) / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "atrous_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1 and (W, H) == (1920, 1080):     # the capture is of C2; other workloads report null
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     cb = cpu_baseline(wl, 2) if world == 1 and not args.no_cpu_baseline else None
     launches_per_frame = 1 + 1 + 2 * nl + 1 + (0 if world == 1 else 3 + 2 * nl)     # rt, temporal, (kl + tiled) x levels, pack [+ signal/wait]
