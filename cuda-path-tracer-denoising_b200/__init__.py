@@ -83,7 +83,8 @@ EXPORTS = ["svgf_params_default", "svgf_create", "svgf_destroy", "svgf_reset", "
            "svgf_denoise_host", "svgf_atrous_host", "svgf_fetch", "svgf_last_error", "svgf_abi_version", "svgf_stage_times",
            "svgf_set_profiling", "svgf_stream", "svgf_set_shard", "svgf_ipc_handles_size", "svgf_ipc_export",
            "svgf_ipc_connect", "svgf_peer_connect_local", "svgf_peer_error", "svgf_camera_init", "svgf_camera_step",
-           "svgf_render_async", "svgf_wait_image"]
+           "svgf_render_async", "svgf_wait_image", "svgf_scene_load", "svgf_scene_free", "svgf_scene_error", "svgf_scene_describe",
+           "svgf_scene_camera", "svgf_scene_num_textures", "svgf_scene_texture_file", "svgf_scene_set_texture", "svgf_scene_mesh_boxes"]
 
 _lib = None
 
@@ -106,6 +107,15 @@ def lib():
         L.svgf_destroy.argtypes = [vp]
         L.svgf_reset.argtypes = [vp]
         L.svgf_render.argtypes = [vp, ctypes.POINTER(Camera), ctypes.POINTER(Params), ci, vp, vp]
+        L.svgf_scene_load.argtypes = [ctypes.POINTER(vp), cp, cp]
+        L.svgf_scene_free.argtypes = [vp]; L.svgf_scene_free.restype = None
+        L.svgf_scene_error.argtypes = [vp]; L.svgf_scene_error.restype = ctypes.c_char_p
+        L.svgf_scene_describe.argtypes = [vp, ci, ci, ctypes.POINTER(SceneDesc)]
+        L.svgf_scene_camera.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.svgf_scene_num_textures.argtypes = [vp]
+        L.svgf_scene_texture_file.argtypes = [vp, ci]; L.svgf_scene_texture_file.restype = ctypes.c_char_p
+        L.svgf_scene_set_texture.argtypes = [vp, ci, ci, ci, ci, vp]
+        L.svgf_scene_mesh_boxes.argtypes = [vp, vp, ci]
         L.svgf_render_async.argtypes = [vp, ctypes.POINTER(Camera), ctypes.POINTER(Params), ci, vp, vp]
         L.svgf_wait_image.argtypes = [vp, vp]
         L.svgf_denoise.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Camera), ctypes.POINTER(Params)]
@@ -331,6 +341,62 @@ def connect_local(renderers, row_starts=None):
     rc = lib().svgf_peer_connect_local(arr, world, rs.ctypes.data)
     if rc != SVGF_OK:
         raise SvgfError("svgf_peer_connect_local -> %d" % rc)
+
+
+class SceneFile:
+    """svgf_scene_*: the reference's text scene + OBJ meshes parsed, transformed and BVH-built natively (csrc/scene_ingest.cpp).
+    Same duck type as SceneBlob for Renderer/camera_driver: .desc(W, H), .camera_driver(W, H, automate)."""
+
+    def __init__(self, scene_file, models_dir=None):
+        h = ctypes.c_void_p()
+        rc = lib().svgf_scene_load(ctypes.byref(h), scene_file.encode(), models_dir.encode() if models_dir else None)
+        self.h = h
+        if rc != 0:
+            msg = lib().svgf_scene_error(h).decode() if h else "svgf_scene_load failed"
+            self.close()
+            raise SvgfError(msg)
+        eye = np.zeros(3, np.float32); look = np.zeros(3, np.float32); up = np.zeros(3, np.float32)
+        fovy = ctypes.c_float(); res = np.zeros(2, np.int32)
+        lib().svgf_scene_camera(h, eye.ctypes.data, look.ctypes.data, up.ctypes.data, ctypes.addressof(fovy), res.ctypes.data)
+        self.eye, self.lookat, self.up, self.fovy, self.res = eye, look, up, float(fovy.value), (int(res[0]), int(res[1]))
+        self.texture_files = [lib().svgf_scene_texture_file(h, i).decode() for i in range(lib().svgf_scene_num_textures(h))]
+
+    def set_texture(self, index, pixels):
+        """pixels: (H, W, C) uint8, row-major (what stb_image hands the reference, src/sceneStructs.h:193-199)."""
+        a = np.ascontiguousarray(pixels, np.uint8)
+        rc = lib().svgf_scene_set_texture(self.h, index, a.shape[1], a.shape[0], a.shape[2], a.ctypes.data)
+        if rc != 0:
+            raise SvgfError("svgf_scene_set_texture failed")
+
+    def desc(self, W, H):
+        d = SceneDesc()
+        if lib().svgf_scene_describe(self.h, W, H, ctypes.byref(d)) != 0:
+            raise SvgfError(lib().svgf_scene_error(self.h).decode())
+        return d
+
+    def arrays(self, W=1, H=1):
+        """Copies of the ingest result as raw byte arrays in the reference's struct layouts (tests)."""
+        d = self.desc(W, H)
+        def grab(ptr, n, sz):
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), (max(n * sz, 0),)).copy() if n else np.zeros(0, np.uint8)
+        boxes = np.zeros((max(lib().svgf_scene_mesh_boxes(self.h, None, 0), 1), 6), np.float32)
+        nb = lib().svgf_scene_mesh_boxes(self.h, boxes.ctypes.data, boxes.shape[0])
+        return dict(geoms=grab(d.geoms, d.n_geoms, 248), materials=grab(d.materials, d.n_materials, 56),
+                    triangles=grab(d.triangles, d.n_triangles, 136), bvh=grab(d.bvh_nodes, d.n_bvh_nodes, 40), boxes=boxes[:nb])
+
+    def camera_driver(self, W, H, automate=False, speeds=CameraDriver.SPEEDS_C5):
+        return CameraDriver(self.eye, self.lookat, self.up, self.fovy, W, H, automate, speeds)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().svgf_scene_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def scene_path(name):

@@ -27,9 +27,9 @@ inline float minor2(const float *m, int ca, int cb, int ra, int rb) {
 }
 }  // namespace
 
-void svgf_view_matrix(const svgf_camera *cam, float *out16) {
-    const float m[16] = {cam->right[0], cam->right[1], cam->right[2], 0.f, cam->up[0], cam->up[1], cam->up[2], 0.f,
-                         cam->view[0], cam->view[1], cam->view[2], 0.f, cam->position[0], cam->position[1], cam->position[2], 1.f};
+// glm::inverse(mat4) = detail::compute_inverse (external/include/glm/detail/type_mat4x4.inl:37-92), column-major, fp32.
+// Also used by the scene ingest for Geom::inverseTransform (src/scene.cpp:103).
+void svgf_mat4_inverse(const float *m, float *out16) {
     // coef[k][*] = {Coef(k*4), Coef(k*4), Coef(k*4+2), Coef(k*4+3)}: minors over rows (2,3) (1,3) (1,2) [k=0], ...
     float fac[6][4];
     const int rowpair[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};
@@ -51,6 +51,12 @@ void svgf_view_matrix(const svgf_camera *cam, float *out16) {
     const float d0 = m[0] * inv[0][0], d1 = m[1] * inv[1][0], d2 = m[2] * inv[2][0], d3 = m[3] * inv[3][0];
     const float rdet = 1.0f / ((d0 + d1) + (d2 + d3));
     for (int cidx = 0; cidx < 4; cidx++) for (int r = 0; r < 4; r++) out16[cidx * 4 + r] = inv[cidx][r] * rdet;
+}
+
+void svgf_view_matrix(const svgf_camera *cam, float *out16) {
+    const float m[16] = {cam->right[0], cam->right[1], cam->right[2], 0.f, cam->up[0], cam->up[1], cam->up[2], 0.f,
+                         cam->view[0], cam->view[1], cam->view[2], 0.f, cam->position[0], cam->position[1], cam->position[2], 1.f};
+    svgf_mat4_inverse(m, out16);
 }
 
 extern "C" void svgf_camera_init(svgf_camera *cam, svgf_camera_rig *rig, const float eye[3], const float lookat[3],

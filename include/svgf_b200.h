@@ -236,6 +236,28 @@ void svgf_camera_init(svgf_camera *cam, svgf_camera_rig *rig, const float eye[3]
 /* Optional automation step (main.cpp:156-169) followed by the camchanged block (main.cpp:171-190). */
 void svgf_camera_step(svgf_camera *cam, svgf_camera_rig *rig, int automate, const float speeds[5]);
 
+/* ---- scene ingest: the reference's scene files -> the arrays svgf_create takes ---------------- */
+/* Parses the reference's text scene format (MATERIAL / OBJECT / CAMERA blocks, src/scene.cpp:9-238) and its OBJ meshes,
+ * transforms the triangles to world space (scene.cpp:240-311) and builds the SAH BVH (src/bvhtree.cpp), reproducing the
+ * arrays of the reference's own loader bit for bit (csrc/scene_ingest.cpp). `models_dir` NULL = "<dir of scene_file>/Models"
+ * (the reference hard-codes ../scenes/Models/, scene.cpp:236). A scene object is returned even on failure so that
+ * svgf_scene_error() can say why; free it in both cases. Host only: no CUDA call is made. */
+typedef struct svgf_scene svgf_scene;
+int svgf_scene_load(svgf_scene **out, const char *scene_file, const char *models_dir);
+void svgf_scene_free(svgf_scene *scene);
+const char *svgf_scene_error(const svgf_scene *scene);
+/* Fills `desc` with pointers into `scene` (valid until svgf_scene_free); every texture must have pixels by then. */
+int svgf_scene_describe(svgf_scene *scene, int width, int height, svgf_scene_desc *desc);
+/* The CAMERA block: EYE / LOOKAT / UP / FOVY / RES, the inputs of svgf_camera_init. Any pointer may be NULL. */
+int svgf_scene_camera(const svgf_scene *scene, float eye[3], float lookat[3], float up[3], float *fovy, int res[2]);
+/* Textures are referenced by file name (TEXTURE lines, scene.cpp:213-219); decoding is the caller's (the reference uses
+ * stb_image): attach RGB8 pixels, row-major, before svgf_scene_describe. */
+int svgf_scene_num_textures(const svgf_scene *scene);
+const char *svgf_scene_texture_file(const svgf_scene *scene, int index);
+int svgf_scene_set_texture(svgf_scene *scene, int index, int width, int height, int components, const unsigned char *pixels);
+/* Scene::BoudningBoxs (one {min, max} per MESH geom, scene.cpp:309; not read by the hot path). Returns their number. */
+int svgf_scene_mesh_boxes(const svgf_scene *scene, float *out6, int max_boxes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,104 @@
+"""Scene ingest (CPU, no GPU needed): svgf_scene_load -- the reference's text scene format, OBJ meshes,
+world-space transform and SAH BVH build restated in csrc/scene_ingest.cpp -- against the arrays the REFERENCE'S OWN loader
+produced (tests/golden/scenes/*.scene, exported by oracle/ref/harness.cpp:refh_export_scene from src/scene.cpp +
+src/bvhtree.cpp + tinyobjloader, with the fields the reference leaves uninitialised zeroed). Bar: byte for byte -- geoms
+(matrices included), materials, BVH-ordered triangles, BVH nodes, mesh boxes, camera block.
+
+The scene text files and OBJ models are the reference's data (scenes/*.txt, scenes/Models/*.obj); they are read where they
+lie, and these tests skip when /root/reference is absent (the GPU box). A scene written for this repo (tests/golden/
+scenes_txt) covers the parser's branches everywhere."""
+import os
+
+import numpy as np
+import pytest
+
+from util import ROOT, svgf
+
+REF_SCENES = "/root/reference/scenes"
+OWN_SCENES = os.path.join(ROOT, "tests", "golden", "scenes_txt")
+needs_reference = pytest.mark.skipif(not os.path.isdir(REF_SCENES), reason="reference scene files not present")
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["cornell", "room", "bunny", "diamond"])
+def test_ingest_equals_reference_loader_bytes(name):
+    m = svgf()
+    blob = m.SceneBlob(m.scene_path(name))
+    sc = m.SceneFile(os.path.join(REF_SCENES, name + ".txt"))
+    for i, (w, h, c, px) in enumerate(blob.textures):      # decoded pixels come from outside (stb_image in the reference)
+        sc.set_texture(i, px.reshape(h, w, c))
+    a = sc.arrays()
+    assert len(sc.texture_files) == len(blob.textures)
+    for key, ref, sz in (("geoms", blob.geoms, 248), ("materials", blob.materials, 56), ("triangles", blob.triangles, 136), ("bvh", blob.bvh, 40)):
+        got = a[key]
+        assert got.size == ref.size, "%s: %d vs %d records" % (key, got.size // sz, ref.size // sz)
+        if not np.array_equal(got, ref):
+            bad = np.nonzero(got.reshape(-1, sz) != ref.reshape(-1, sz))
+            raise AssertionError("%s differs: first at record %d byte %d (%d bytes in all)" % (key, bad[0][0], bad[1][0], bad[0].size))
+    lc = blob.loader_camera
+    assert np.array_equal(sc.eye, np.array(lc.position[:], np.float32)) and np.array_equal(sc.lookat, np.array(lc.lookAt[:], np.float32))
+    assert np.array_equal(sc.up, np.array(lc.up[:], np.float32)) and sc.fovy == blob.fovy
+    # the camera the two sources drive through resetCamera / camchanged is the same, bit for bit
+    c0, c1 = blob.camera_driver(96, 64).step(), sc.camera_driver(96, 64).step()
+    assert np.array_equal(c0.as_array().view(np.uint32), c1.as_array().view(np.uint32))
+    sc.close()
+
+
+@needs_reference
+def test_mesh_boxes_follow_the_reference_quirk():
+    """Scene::BoudningBoxs starts its maxima at FLT_MIN (a tiny POSITIVE number, scene.cpp:255), kept for fidelity."""
+    m = svgf()
+    raw = np.fromfile(m.scene_path("bunny"), np.uint8)
+    hdr = raw[8:32].view(np.int32)
+    ng, nm, nt, nb, nx, ntex = (int(v) for v in hdr)
+    off = 40 + 84 + ng * 248 + nm * 56 + nt * 136 + nb * 40
+    ref_boxes = raw[off:off + nx * 24].view(np.float32).reshape(nx, 6)
+    sc = m.SceneFile(os.path.join(REF_SCENES, "bunny.txt"))
+    assert np.array_equal(sc.arrays()["boxes"].view(np.uint32), ref_boxes.view(np.uint32))
+    sc.close()
+
+
+def test_own_scene_parses_and_is_consistent():
+    """A scene written for this repo: CRLF line ends, comments, a polygon face with negative indices, a v/vt/vn mesh."""
+    m = svgf()
+    sc = m.SceneFile(os.path.join(OWN_SCENES, "two_meshes.txt"))
+    assert sc.res == (320, 200) and sc.fovy == 40.0 and sc.texture_files == ["checker.jpg"]
+    with pytest.raises(m.SvgfError, match="no pixels"):
+        sc.desc(8, 8)                       # a TEXTURE line was seen but nobody attached decoded pixels yet
+    sc.set_texture(0, np.zeros((2, 2, 3), np.uint8))
+    assert sc.desc(8, 8).n_textures == 1
+    a = sc.arrays()
+    geoms = a["geoms"].reshape(-1, 248); tris = a["triangles"].reshape(-1, 136); bvh = a["bvh"].reshape(-1, 40)
+    assert geoms.shape[0] == 4 and a["materials"].size == 3 * 56
+    types = geoms[:, 0:4].copy().view(np.int32)[:, 0]
+    assert list(types) == [1, 0, 2, 2]
+    # quad (fan of 2) + pyramid (4 triangles + a quad base = 6)
+    assert tris.shape[0] == 8
+    ids = sorted(tris[:, 0:4].copy().view(np.int32)[:, 0].tolist())
+    assert ids == list(range(8)), "triangle ids are the load order, each exactly once"
+    rng = geoms[:, 236:248].copy().view(np.int32)
+    assert rng[2, 0] == 0 and rng[2, 1] == 2 and rng[3, 0] == 2 and rng[3, 1] == 8
+    # every triangle is referenced by exactly one leaf, children follow their parent, bounds contain the triangles
+    n = bvh.shape[0]
+    f = bvh.copy().view(np.float32).reshape(n, 10); q = bvh.copy().view(np.int32).reshape(n, 10)
+    seen = np.zeros(tris.shape[0], np.int32)
+    pos = tris[:, 4:100].copy().view(np.float32).reshape(-1, 3, 8)[:, :, 0:3]
+    for i in range(n):
+        if q[i, 6] > 0:
+            sl = slice(q[i, 8], q[i, 8] + q[i, 6]); seen[sl] += 1
+            assert (pos[sl] >= f[i, 0:3] - 1e-6).all() and (pos[sl] <= f[i, 3:6] + 1e-6).all()
+        else:
+            assert i + 1 < n and i < q[i, 9] < n and 0 <= q[i, 7] <= 2
+    assert (seen == 1).all()
+    # the identity-transformed quad keeps its coordinates (whichever slots the BVH order gave its two triangles)
+    quad = pos[np.isin(tris[:, 0:4].copy().view(np.int32)[:, 0], [0, 1])]
+    assert set(np.unique(quad).tolist()) == {-4.0, 0.0, 4.0}
+    sc.close()
+
+
+def test_errors_are_reported():
+    m = svgf()
+    with pytest.raises(m.SvgfError, match="cannot open scene file"):
+        m.SceneFile("/nonexistent/scene.txt")
+    with pytest.raises(m.SvgfError, match="cannot open OBJ"):
+        m.SceneFile(os.path.join(OWN_SCENES, "missing_mesh.txt"))
