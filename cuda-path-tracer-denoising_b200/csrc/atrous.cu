@@ -35,6 +35,11 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Distance for an edge-stopping weight. The reference clamps the normal and position weights with min(1.0f, expf(-d/s))
+// (denoise.cu:144-145; CUDA's min = fminf, which drops a NaN operand): for d >= 0 that is the identity, but a NaN distance --
+// a mesh without vertex normals interpolates normalize(0) = NaN (sceneStructs.h:168-172) -- yields weight 1, not NaN. fmaxf
+// drops the NaN here (one FMNMX on the ALU pipe, which has slack), so such a pair is filtered as if the two normals agreed.
+__device__ __forceinline__ float dist_of(float d2) { return fmaxf(sqrt_approx(d2), 0.0f); }
 
 struct AtrousK {
     const float4 *cv_in; float4 *cv_out;
@@ -93,8 +98,8 @@ atrous_direct_kernel(AtrousK k) {
                 const float lq = lum_ref(cq.x, cq.y, cq.z);
                 const float dnx = nq.x - np.x, dny = nq.y - np.y, dnz = nq.z - np.z;
                 const float dpx = pq.x - pp.x, dpy = pq.y - pp.y, dpz = pq.z - pp.z;
-                const float dn = sqrtf(dnx * dnx + dny * dny + dnz * dnz);
-                const float dx = sqrtf(dpx * dpx + dpy * dpy + dpz * dpz);
+                const float dn = fmaxf(sqrtf(dnx * dnx + dny * dny + dnz * dnz), 0.0f);     // NaN -> weight 1, see dist_of()
+                const float dx = fmaxf(sqrtf(dpx * dpx + dpy * dpy + dpz * dpz), 0.0f);
                 const float e = fabsf(lq - lp) * kl + dn * k.kn + dx * k.kx;
                 const float hi = (i == 0 ? 0.375f : ((i == 1 || i == -1) ? 0.25f : 0.0625f));
                 const float hj = (j == 0 ? 0.375f : ((j == 1 || j == -1) ? 0.25f : 0.0625f));
@@ -273,7 +278,7 @@ __device__ __forceinline__ float2 at_dist2(const AtTap &T, float2 cx, float2 cy,
 // one tap against both centres of a patch row; h = {h of centre 0, h of centre 1}
 __device__ __forceinline__ void at_twin(const AtTap &T, const AtCentre2 &C, AtAcc2 &A, float2 h) {
     const float2 d0 = at_dist2(T, C.nx_px[0], C.ny_py[0], C.nz_pz[0]), d1 = at_dist2(T, C.nx_px[1], C.ny_py[1], C.nz_pz[1]);
-    const float2 dn = make_float2(sqrt_approx(d0.x), sqrt_approx(d1.x)), dp = make_float2(sqrt_approx(d0.y), sqrt_approx(d1.y));
+    const float2 dn = make_float2(dist_of(d0.x), dist_of(d1.x)), dp = make_float2(dist_of(d0.y), dist_of(d1.y));
     const float2 dl = __fadd2_rn(make_float2(T.lum, T.lum), make_float2(-C.lum.x, -C.lum.y));
     const float2 e = __fadd2_rn(__ffma2_rn(make_float2(fabsf(dl.x), fabsf(dl.y)), C.kl, dn), dp);
     const float2 w = __fmul2_rn(make_float2(ex2_approx(-e.x), ex2_approx(-e.y)), h);
@@ -290,7 +295,7 @@ __device__ __forceinline__ void at_twin(const AtTap &T, const AtCentre2 &C, AtAc
 template <int CA>
 __device__ __forceinline__ void at_single(const AtTap &T, const AtCentre2 &C, AtAcc2 &A, float h) {
     const float2 d2 = at_dist2(T, C.nx_px[CA], C.ny_py[CA], C.nz_pz[CA]);
-    const float dn = sqrt_approx(d2.x), dp = sqrt_approx(d2.y);
+    const float dn = dist_of(d2.x), dp = dist_of(d2.y);
     const float lum = CA ? C.lum.y : C.lum.x, kl = CA ? C.kl.y : C.kl.x;
     const float e = fmaf(fabsf(T.lum - lum), kl, dn) + dp;
     const float w = ex2_approx(-e) * h, w2 = w * w;

@@ -117,6 +117,23 @@ def test_zero_variance_and_extreme_inputs():
     R.close()
 
 
+def test_nan_normals_get_weight_one():
+    """min(1.0f, expf(-NaN)) = 1 in the reference (CUDA's min drops the NaN, denoise.cu:144-145): pixels whose shading normal
+    is NaN (meshes without vertex normals, sceneStructs.h:168-172) are filtered as if all normals agreed; colour and variance
+    stay finite and match the oracle."""
+    W, H = 96, 72
+    m, R = ctx_for(W, H)
+    color, var, g = synthetic_planes(W, H, seed=21)
+    g[20:50, 30:70, 0:3] = np.nan
+    for level in (1, 3):
+        co, vo = R.atrous_level(color, var, g, level, level == 3, m.default_params())
+        oc, ov = orc.atrous_level(color, var, g, level, level == 3, orc.default_params())
+        assert np.isfinite(oc).all() and np.isfinite(co).all() and np.isfinite(vo).all()
+        assert_close(co, oc, COLOR_FLOOR, "colour L%d with NaN normals" % level)
+        assert_close(vo, ov, VAR_FLOOR, "variance L%d with NaN normals" % level)
+    R.close()
+
+
 @pytest.mark.parametrize("size", [(1920, 1080), (3840, 2160)])
 def test_full_size_properties(size):
     """Size-independent properties at BASELINE.json's sizes (the oracle would take minutes here):

@@ -65,3 +65,21 @@ def synthetic_planes(W, H, seed=1234):
     g[..., 9:12] = 1.0
     g[..., 12] = np.broadcast_to(band[None, :].astype(np.int32), (H, W)).view(np.float32)
     return color, variance, g
+
+
+def write_scene_blob(scene_file, path, textures=()):
+    """Serialise a natively ingested scene (SceneFile) in the blob format the oracle reads (same layout as the blobs the
+    reference's loader exported, see cuda-path-tracer-denoising_b200/__init__.py:SceneBlob)."""
+    import struct
+    m = svgf()
+    a = scene_file.arrays()
+    hdr = b"SVGFSCN1" + struct.pack("<6i", a["geoms"].size // 248, a["materials"].size // 56, a["triangles"].size // 136,
+                                    a["bvh"].size // 40, a["boxes"].shape[0], len(textures)) + struct.pack("<f", scene_file.fovy) + b"\0" * 4
+    cam = m.Camera()
+    cam.position[:] = list(scene_file.eye); cam.lookAt[:] = list(scene_file.lookat); cam.up[:] = list(scene_file.up)
+    out = hdr + bytes(cam) + a["geoms"].tobytes() + a["materials"].tobytes() + a["triangles"].tobytes() + a["bvh"].tobytes() + a["boxes"].tobytes()
+    for t in textures:
+        t = np.ascontiguousarray(t, np.uint8)
+        out += struct.pack("<3i", t.shape[1], t.shape[0], t.shape[2]) + t.tobytes()
+    with open(path, "wb") as f:
+        f.write(out)
