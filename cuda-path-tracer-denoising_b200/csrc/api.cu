@@ -434,6 +434,14 @@ int svgf_stage_times(svgf_ctx *c, float *ms11) {
 
 void *svgf_stream(svgf_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
+int svgf_set_option(svgf_ctx *c, const char *name, int value) {
+    if (!c || !name) return SVGF_ERR_INVALID;
+    if (!strcmp(name, "reprojection_fov_aspect")) { c->opt_reprojection_fov_aspect = value != 0; return SVGF_OK; }
+    if (!strcmp(name, "history_cap")) { if (value < 0) return SVGF_ERR_INVALID; c->opt_history_cap = value; return SVGF_OK; }
+    c->err = std::string("svgf_set_option: unknown option '") + name + "'";
+    return SVGF_ERR_UNKNOWN_NAME;
+}
+
 int svgf_sync(svgf_ctx *c) {
     if (!c) return SVGF_ERR_INVALID;
     CK(cudaStreamSynchronize(c->stream));
@@ -466,10 +474,17 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
     }
     const float color_alpha = P->temporal_enable ? P->color_alpha : 1.0f;
     const float moment_alpha = P->temporal_enable ? P->moment_alpha : 1.0f;
+    // generateRayFromCamera spreads the frame over +-pixelLength * res / 2 = +-tan(fovy) * aspect and +-tan(fovy) at unit depth
+    // (scene.cpp:159-166, pathtrace.cu:197-200); the reference's back-projection assumes both are 1 (denoise.cu:201-207)
+    float clip_rx = 1.0f, clip_ry = 1.0f;
+    if (c->opt_reprojection_fov_aspect) {
+        clip_rx = 1.0f / (cam->pixelLength[0] * (float)c->W * 0.5f);
+        clip_ry = 1.0f / (cam->pixelLength[1] * (float)c->H * 0.5f);
+    }
     if (P->temporal_enable) {
         CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->p_nrm[c->cur_nrm ^ 1], c->pos, c->p_cv[c->hist_cv], c->p_mom[c->cur_mom],
                            c->p_hlen[c->cur_hlen], acc, c->lv[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1],
-                           c->view_matrix_prev, color_alpha, moment_alpha));
+                           c->view_matrix_prev, color_alpha, moment_alpha, clip_rx, clip_ry));
     } else {
         CK(launch_no_temporal(c, image, acc, c->lv[acc_slot]));
     }

@@ -45,7 +45,7 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
                 const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,
                 const __grid_constant__ PeerPtr<int> hlen_tab, const __grid_constant__ RowOwner ro, int me,
                 float4 *__restrict__ acc_cv, float2 *__restrict__ acc_lv, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
-                float color_alpha_min, float moment_alpha_min) {
+                float color_alpha_min, float moment_alpha_min, float clip_rx, float clip_ry, int hist_cap) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= row_end) return;
@@ -60,7 +60,10 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
         const float vx = (vm.m[0] * pp.x + vm.m[4] * pp.y) + (vm.m[8] * pp.z + vm.m[12] * 1.0f);
         const float vy = (vm.m[1] * pp.x + vm.m[5] * pp.y) + (vm.m[9] * pp.z + vm.m[13] * 1.0f);
         const float vz = (vm.m[2] * pp.x + vm.m[6] * pp.y) + (vm.m[10] * pp.z + vm.m[14] * 1.0f);
-        const float clipx = vx / vz, clipy = vy / vz;
+        // clip_rx = clip_ry = 1 reproduces the reference, which leaves out the FOV/aspect term (denoise.cu:201-207: exact only
+        // for FOVY 45 and square frames; x * 1.0f is exact, so the default path keeps its bits). SURVEY.md 8(f) N4 switch
+        // "reprojection_fov_aspect": 1 / (tan(fovy) * aspect) and 1 / tan(fovy), the inverse of generateRayFromCamera's scaling.
+        const float clipx = (vx / vz) * clip_rx, clipy = (vy / vz) * clip_ry;
         const float ndcx = -clipx * 0.5f + 0.5f, ndcy = -clipy * 0.5f + 0.5f;
         const float prevx = ndcx * W - 0.5f, prevy = ndcy * H - 0.5f;
         const float floorx = floorf(prevx), floory = floorf(prevy);
@@ -121,7 +124,8 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
         if (valid) {
             const float color_alpha = fmaxf(1.0f / (float)(N + 1), color_alpha_min);
             const float moment_alpha = fmaxf(1.0f / (float)(N + 1), moment_alpha_min);
-            hlen_out[p] = (int)phl + 1;
+            const int hl = (int)phl + 1;            // unbounded in the reference (denoise.cu:290-294); optional cap (N4)
+            hlen_out[p] = hist_cap > 0 ? min(hl, hist_cap) : hl;
             const float first = moment_alpha * pm1 + (1.0f - moment_alpha) * luminance;
             const float second = moment_alpha * pm2 + (1.0f - moment_alpha) * luminance * luminance;
             mom_acc[p] = make_float2(first, second);
@@ -272,14 +276,14 @@ inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (
 cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const PeerPtr<float4> &nrm_prev,
                             const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
                             const PeerPtr<int> &hlen_in, float4 *acc_cv, float2 *acc_lv, float2 *mom_acc, int *hlen_out,
-                            const float *prev_viewmat, float color_alpha, float moment_alpha) {
+                            const float *prev_viewmat, float color_alpha, float moment_alpha, float clip_rx, float clip_ry) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     Mat4 vm; for (int i = 0; i < 16; i++) vm.m[i] = prev_viewmat[i];
     dim3 b(32, 8);
     temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
                                                                  nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lv, mom_acc,
-                                                                 hlen_out, vm, color_alpha, moment_alpha);
+                                                                 hlen_out, vm, color_alpha, moment_alpha, clip_rx, clip_ry, c->opt_history_cap);
     return cudaGetLastError();
 }
 

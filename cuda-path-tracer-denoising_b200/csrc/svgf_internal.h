@@ -132,6 +132,10 @@ struct svgf_ctx {
     int copy_slot = 0, copy_pending[2] = {0, 0};
     const float *copy_host[2] = {nullptr, nullptr};
 
+    // quality switches the reference leaves as TODOs; all off by default (parity), svgf_set_option
+    int opt_reprojection_fov_aspect = 0;    // 1: the back-projection honours FOV and aspect ratio (denoise.cu:200-207 does not)
+    int opt_history_cap = 0;                // > 0: history length saturates there (unbounded in the reference)
+
     float view_matrix_prev[16];         // denoise.cu:15; identity until the first denoise (glm::mat4())
     int last_variance_valid = 0;        // var_out holds the final variance of the last frame
 
@@ -173,7 +177,7 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out);
 cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const PeerPtr<float4> &nrm_prev,
                             const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
                             const PeerPtr<int> &hlen_in, float4 *acc_cv, float2 *acc_lv, float2 *mom_acc, int *hlen_out,
-                            const float *prev_viewmat, float color_alpha, float moment_alpha);
+                            const float *prev_viewmat, float color_alpha, float moment_alpha, float clip_rx, float clip_ry);
 struct HaloPlane { const void *local; void *peer[SVGF_MAX_RANKS]; int esz; };     // esz = bytes per pixel (multiple of 8)
 cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes);
 cudaError_t launch_signal(svgf_ctx *c, int stage);

@@ -206,6 +206,14 @@ int svgf_stage_times(svgf_ctx *ctx, float *ms11);
  * own events. */
 void *svgf_stream(svgf_ctx *ctx);
 
+/* ---- quality switches beyond the reference; all 0 = the reference's behaviour, bit for bit ------- */
+/*   "reprojection_fov_aspect" 0/1  the temporal back-projection divides by tan(fovy)*aspect and tan(fovy). The reference
+ *                                  leaves that term out (denoise.cu:200-207), so its history only lines up for FOVY 45 on
+ *                                  square frames: at 16:9 a static camera maps x to cx + 1.78 (x - cx) and most of the
+ *                                  frame never accumulates.
+ *   "history_cap"             n    history_length saturates at n > 0 (unbounded in the reference, denoise.cu:290-294). */
+int svgf_set_option(svgf_ctx *ctx, const char *name, int value);
+
 /* ---- multi-GPU: a frame sharded by row strips, one process (context) per GPU -------------------------------- */
 /* Every rank holds full-frame planes and renders rows [row_starts[rank], row_starts[rank+1]); rows owned by other
  * ranks are read in place from the owner's memory over NVLink (CUDA IPC), ordered by per-stage flags -- no halo copy,
