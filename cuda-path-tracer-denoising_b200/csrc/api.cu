@@ -230,9 +230,10 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     c->shard = svgf_shard{0, 1, 0, c->H};
     if (const char *v = getenv("SVGF_RT_VARIANT")) c->rt_variant = (!strcmp(v, "wavefront") || !strcmp(v, "1")) ? 1 : ((!strcmp(v, "persistent") || !strcmp(v, "2")) ? 2 : 0);
     if (const char *v = getenv("SVGF_HALO")) c->halo_push = strcmp(v, "pull") != 0;      // A/B testing
-    if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3) ? atoi(v) : 2;    // A/B testing
+    if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3 || atoi(v) == 4) ? atoi(v) : 2;    // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_SHAPE")) c->atrous_shape = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_PROBE")) c->atrous_probe = atoi(v);
+    if (const char *v = getenv("SVGF_ATROUS_PAIR_ROWS")) c->atrous_pair_rows = atoi(v) == 1 ? 1 : 2;
     if (const char *v = getenv("SVGF_ATROUS_SHAPES")) {      // "a,b,c,...": shape of level 1, 2, 3, ...
         int level = 1;
         for (const char *q = v; *q && level <= SVGF_MAX_LEVELS; level++) {

@@ -13,6 +13,7 @@
 //     while neighbours read it (denoise.cu:111,153,161), which is a data race; the Jacobi form is what its result
 //     converges to when all reads win the race and is the only deterministic, shardable definition.
 #include "svgf_internal.h"
+#include "atrous_pair_core.h"
 
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda/barrier>
@@ -267,7 +268,7 @@ struct AtCentre2 {          // the two centres of one patch row; G-buffer terms 
     float2 nx_px[AT_TX], ny_py[AT_TX], nz_pz[AT_TX];    // {-kn*n, -kx*p} per component, per centre
     float2 lum, kl;                                     // {centre 0, centre 1}
 };
-struct AtAcc2 { float2 w, w2, r, g, b, v; };           // {centre 0, centre 1}: sum w, sum w^2, sum w*rgb, sum w^2*var
+using AtAcc2 = PairAcc;                                 // {centre 0, centre 1}: sum w, sum w^2, sum w*rgb, sum w^2*var
 struct AtTap { float4 cv; float2 nx_px, ny_py, nz_pz; float lum; };
 
 __device__ __forceinline__ float2 at_dist2(const AtTap &T, float2 cx, float2 cy, float2 cz) {       // {|dn|^2, |dp|^2}
@@ -330,25 +331,16 @@ __device__ __forceinline__ void at_column(const float4 *s_cv, const float4 *s_np
 
 namespace cde = cuda::device::experimental;
 
-template <int LX, int LY, int AT_TY, int MINB>
-__global__ void __launch_bounds__((AtShape<LX, LY, AT_TY>::THREADS), MINB)
-atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
-    using SH = AtShape<LX, LY, AT_TY>;
-    static_assert(SH::OK, "tile shape");
-    constexpr int AT_LX = LX, AT_SW = SH::SW, AT_SH = SH::SH, AT_THREADS = SH::THREADS, TILE = SH::TILE, HALF = SH::HALF;
-    extern __shared__ __align__(128) unsigned char at_smem_raw[];
-    float4 *s_cv = reinterpret_cast<float4 *>(at_smem_raw), *s_np = s_cv + TILE;
-    float2 *s_zl = reinterpret_cast<float2 *>(s_np + TILE), *s_lv = s_zl + TILE;
-    using barrier_t = cuda::barrier<cuda::thread_scope_block>;
-    barrier_t &bar = *reinterpret_cast<barrier_t *>(at_smem_raw + TILE * 48);
+using barrier_t = cuda::barrier<cuda::thread_scope_block>;
+
+// Stage tile + apron of one residue class into shared memory (shape SH: AtShape or PairShape). Returns true when the TMA path
+// was taken (the data has landed), false when cp.async copies are still in flight (caller: cp.async.wait_group + barrier).
+template <class SH>
+__device__ __forceinline__ bool at_stage_tile(const AtrousT &t, float4 *s_cv, float4 *s_np, float2 *s_zl, float2 *s_lv, barrier_t &bar,
+                                              int X0, int a0, int b0, int yc, int tid) {
+    constexpr int AT_SW = SH::SW, AT_SH = SH::SH, AT_THREADS = SH::THREADS, TILE = SH::TILE, HALF = SH::HALF;
     const AtrousK &k = t.k;
     const int W = k.W, H = k.H, step = k.step;
-    const int cg = blockIdx.x % t.ncg, tile_x = blockIdx.x / t.ncg;
-    const int yc = blockIdx.y % step, tile_y = blockIdx.y / step;
-    const int X0 = cg * AT_C;
-    const int a0 = tile_x * AT_LX - 2, b0 = t.b_first + tile_y * LY - 2;
-    const int tid = threadIdx.x;
-
     // rows a live centre of this strip can reach (strip +- 2 steps); a coarse tile spans far more rows than the strip
     const int y_lo = max(0, k.row_begin - 2 * step), y_hi = min(H, k.row_end + 2 * step);
     // does the tile need rows owned by another rank? (first/last needed row of this tile)
@@ -420,6 +412,79 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
+    return tma;
+}
+
+// Normalise the sums of a 2 x TY patch and write them: {colour, variance} + {luminance, variance} for the next level, and on the
+// last level the final colour (x albedo) in the reference's vec3 layout + the variance plane.
+template <int AT_TY>
+__device__ __forceinline__ void at_write_outputs(const AtrousK &k, const AtAcc2 (&A)[AT_TY], int X0, int a0, int b0, int yc, int ap, int bq, int c) {
+    const int W = k.W, step = k.step;
+    // ---- outputs: all 8 results (incl. the fp64 luminance of the new colour, a long dependent chain) are computed as
+    // straight-line code first, then stored under predicates, so the 8 chains overlap ----
+    float4 o[AT_TX][AT_TY]; float ol[AT_TX][AT_TY]; int op[AT_TX][AT_TY];
+#pragma unroll
+    for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+        for (int cb = 0; cb < AT_TY; cb++) {
+            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + AT_TY * bq + cb + 2) * step;
+            op[ca][cb] = (x < W && y >= k.row_begin && y < k.row_end) ? x + y * W : -1;
+            // weights_sum >= 9/64 always (the centre tap), so the reference's `else` branch (denoise.cu:162-164) is dead
+            const AtAcc2 &a = A[cb];
+            const float rw = __frcp_rn(ca ? a.w.y : a.w.x);
+            o[ca][cb] = make_float4((ca ? a.r.y : a.r.x) * rw, (ca ? a.g.y : a.g.x) * rw, (ca ? a.b.y : a.b.x) * rw,
+                                    __fdividef(ca ? a.v.y : a.v.x, ca ? a.w2.y : a.w2.x));
+        }
+    if (k.is_last && k.addcolor) {
+#pragma unroll
+        for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+            for (int cb = 0; cb < AT_TY; cb++) {
+                const float4 al = __ldg(&k.alb[max(op[ca][cb], 0)]);
+                o[ca][cb].x *= al.x; o[ca][cb].y *= al.y; o[ca][cb].z *= al.z;
+            }
+    }
+    if (k.cv_out) {
+#pragma unroll
+        for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+            for (int cb = 0; cb < AT_TY; cb++) ol[ca][cb] = lum_ref(o[ca][cb].x, o[ca][cb].y, o[ca][cb].z);
+    }
+#pragma unroll
+    for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+        for (int cb = 0; cb < AT_TY; cb++) {
+            const int p = op[ca][cb];
+            if (p < 0) continue;
+            if (k.is_last) {
+                float *d = k.denoised_out + 3 * (size_t)p;
+                d[0] = o[ca][cb].x; d[1] = o[ca][cb].y; d[2] = o[ca][cb].z;
+                k.var_out[p] = o[ca][cb].w;
+            }
+            if (k.cv_out) { k.cv_out[p] = o[ca][cb]; k.lv_out[p] = make_float2(ol[ca][cb], o[ca][cb].w); }
+        }
+}
+
+template <int LX, int LY, int AT_TY, int MINB>
+__global__ void __launch_bounds__((AtShape<LX, LY, AT_TY>::THREADS), MINB)
+atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
+    using SH = AtShape<LX, LY, AT_TY>;
+    static_assert(SH::OK, "tile shape");
+    constexpr int AT_LX = LX, AT_SW = SH::SW, AT_SH = SH::SH, AT_THREADS = SH::THREADS, TILE = SH::TILE, HALF = SH::HALF;
+    extern __shared__ __align__(128) unsigned char at_smem_raw[];
+    float4 *s_cv = reinterpret_cast<float4 *>(at_smem_raw), *s_np = s_cv + TILE;
+    float2 *s_zl = reinterpret_cast<float2 *>(s_np + TILE), *s_lv = s_zl + TILE;
+    barrier_t &bar = *reinterpret_cast<barrier_t *>(at_smem_raw + TILE * 48);
+    const AtrousK &k = t.k;
+    const int W = k.W, H = k.H, step = k.step;
+    const int cg = blockIdx.x % t.ncg, tile_x = blockIdx.x / t.ncg;
+    const int yc = blockIdx.y % step, tile_y = blockIdx.y / step;
+    const int X0 = cg * AT_C;
+    const int a0 = tile_x * AT_LX - 2, b0 = t.b_first + tile_y * LY - 2;
+    const int tid = threadIdx.x;
+
+    const bool tma = at_stage_tile<SH>(t, s_cv, s_np, s_zl, s_lv, bar, X0, a0, b0, yc, tid);
+
     const int c = tid & 1, ap = (tid >> 1) % (AT_LX / 2), bq = tid / AT_LX;
     // centres' kl from the pre-pass plane, issued before the barrier
     float c_kl[AT_TX][AT_TY];
@@ -473,49 +538,63 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     }
     at_column<SH, false, true>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + 5, C, A, 0.f, 0.0625f);        // i = +2 for centre column 1
 
-    // ---- outputs: all 8 results (incl. the fp64 luminance of the new colour, a long dependent chain) are computed as
-    // straight-line code first, then stored under predicates, so the 8 chains overlap ----
-    float4 o[AT_TX][AT_TY]; float ol[AT_TX][AT_TY]; int op[AT_TX][AT_TY];
+    at_write_outputs<AT_TY>(k, A, X0, a0, b0, yc, ap, bq, c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Symmetric ("pair") variant of the tile kernel (SVGF_ATROUS_VARIANT=4): same tiles, same staging, same outputs; the pair
+// arithmetic is split in two phases over shared memory so that the two square roots are taken once per UNORDERED pair
+// (csrc/atrous_pair_core.h, which the CPU suite also runs through a host emulation, tests/test_atrous_pair_emu.py).
+template <int LX, int LY, int PR, int MINB>
+__global__ void __launch_bounds__((PairShape<LX, LY, PR>::THREADS), MINB)
+atrous_pair_kernel(const __grid_constant__ AtrousT t) {
+    using SH = PairShape<LX, LY, PR>;
+    static_assert(SH::OK, "tile shape");
+    constexpr int TILE = SH::TILE;
+    extern __shared__ __align__(128) unsigned char at_smem_raw[];
+    float4 *s_cv = reinterpret_cast<float4 *>(at_smem_raw), *s_np = s_cv + TILE;
+    float2 *s_zl = reinterpret_cast<float2 *>(s_np + TILE), *s_lv = s_zl + TILE;
+    float *s_g = reinterpret_cast<float *>(at_smem_raw + TILE * 48);
+    barrier_t &bar = *reinterpret_cast<barrier_t *>(at_smem_raw + TILE * 48 + SH::NOFF * SH::GN * 4);
+    const AtrousK &k = t.k;
+    const int W = k.W, step = k.step;
+    const int cg = blockIdx.x % t.ncg, tile_x = blockIdx.x / t.ncg;
+    const int yc = blockIdx.y % step, tile_y = blockIdx.y / step;
+    const int X0 = cg * AT_C;
+    const int a0 = tile_x * LX - 2, b0 = t.b_first + tile_y * LY - 2;
+    const int tid = threadIdx.x;
+
+    const bool tma = at_stage_tile<SH>(t, s_cv, s_np, s_zl, s_lv, bar, X0, a0, b0, yc, tid);
+
+    // Phase-2 patch of this thread (2 x PR centres). The two half-warps of a warp take patches 4 lattice rows apart (80 floats of
+    // g = 16 banks), so that their 4-byte reads of g do not meet in a bank; plain order when the tile height does not allow it.
+    const int c = tid & 1, ap = (tid >> 1) % (LX / 2);
+    int bq = tid / LX;
+    constexpr int D = 4 / PR;
+    if (LX == 16 && (LY / PR) % (2 * D) == 0) { const int hw = (tid >> 4) & 1, wp = tid >> 5; bq = (wp % D) + D * hw + 2 * D * (wp / D); }
+    float c_kl[2][PR];
+    bool live = false;
 #pragma unroll
-    for (int ca = 0; ca < AT_TX; ca++)
+    for (int ca = 0; ca < 2; ca++)
 #pragma unroll
-        for (int cb = 0; cb < AT_TY; cb++) {
-            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + AT_TY * bq + cb + 2) * step;
-            op[ca][cb] = (x < W && y >= k.row_begin && y < k.row_end) ? x + y * W : -1;
-            // weights_sum >= 9/64 always (the centre tap), so the reference's `else` branch (denoise.cu:162-164) is dead
-            const AtAcc2 &a = A[cb];
-            const float rw = __frcp_rn(ca ? a.w.y : a.w.x);
-            o[ca][cb] = make_float4((ca ? a.r.y : a.r.x) * rw, (ca ? a.g.y : a.g.x) * rw, (ca ? a.b.y : a.b.x) * rw,
-                                    __fdividef(ca ? a.v.y : a.v.x, ca ? a.w2.y : a.w2.x));
+        for (int cb = 0; cb < PR; cb++) {
+            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + PR * bq + cb + 2) * step;
+            const bool ok = x < W && y >= k.row_begin && y < k.row_end;
+            live |= ok;
+            c_kl[ca][cb] = ok ? __ldg(&t.kl[x + y * W]) : 0.f;
         }
-    if (k.is_last && k.addcolor) {
-#pragma unroll
-        for (int ca = 0; ca < AT_TX; ca++)
-#pragma unroll
-            for (int cb = 0; cb < AT_TY; cb++) {
-                const float4 al = __ldg(&k.alb[max(op[ca][cb], 0)]);
-                o[ca][cb].x *= al.x; o[ca][cb].y *= al.y; o[ca][cb].z *= al.z;
-            }
-    }
-    if (k.cv_out) {
-#pragma unroll
-        for (int ca = 0; ca < AT_TX; ca++)
-#pragma unroll
-            for (int cb = 0; cb < AT_TY; cb++) ol[ca][cb] = lum_ref(o[ca][cb].x, o[ca][cb].y, o[ca][cb].z);
-    }
-#pragma unroll
-    for (int ca = 0; ca < AT_TX; ca++)
-#pragma unroll
-        for (int cb = 0; cb < AT_TY; cb++) {
-            const int p = op[ca][cb];
-            if (p < 0) continue;
-            if (k.is_last) {
-                float *d = k.denoised_out + 3 * (size_t)p;
-                d[0] = o[ca][cb].x; d[1] = o[ca][cb].y; d[2] = o[ca][cb].z;
-                k.var_out[p] = o[ca][cb].w;
-            }
-            if (k.cv_out) { k.cv_out[p] = o[ca][cb]; k.lv_out[p] = make_float2(ol[ca][cb], o[ca][cb].w); }
-        }
+    if (!tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- phase 1: g = |dn'| + |dp'| - log2 h for the 12 forward offsets of every staged point that can pair with a centre ----
+    for (int n = tid; n < SH::ITEMS; n += SH::THREADS) pair_phase1_item<SH>(n, s_np, s_zl, s_g);
+    __syncthreads();
+    if (!live) return;
+
+    // ---- phase 2: one ex2 per (centre, tap) ----
+    PairAcc A[PR];
+    pair_phase2_thread<SH>(c, ap, bq, s_cv, s_lv, s_g, c_kl, A);
+    at_write_outputs<PR>(k, A, X0, a0, b0, yc, ap, bq, c);
 }
 
 }  // namespace
@@ -626,6 +705,45 @@ static int at_pick_shape(const svgf_ctx *c, int level, int lat_w, int lat_rows) 
     return lat_rows >= 100 ? 2 : 9;
 }
 
+// SVGF_ATROUS_VARIANT=4: the symmetric pair kernel, 16 x 16 tiles (16 x 12 for short lattices); its tile boxes are those of
+// shapes 2 and 9, so it shares their tensor maps.
+static cudaError_t launch_atrous_pair(svgf_ctx *c, AtrousT &t, const AtrousArgs &a, int lat_w, int lat_rows) {
+    const bool tall = lat_rows >= 100 || c->atrous_shape == 2;
+    const int shape = (tall && c->atrous_shape != 9) ? 2 : 9;
+    t.use_tma = c->tma_ok && a.src_slot >= 0;
+    t.probe = 0;
+    if (t.use_tma) {
+        t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, 3 + a.src_slot, a.level, shape);
+        t.tm_np = *tmap_at(c, 6, a.level, shape); t.tm_zl = *tmap_at(c, 7, a.level, shape);
+    } else {
+        memset(&t.tm_cv, 0, sizeof(CUtensorMap)); memset(&t.tm_lv, 0, sizeof(CUtensorMap));
+        memset(&t.tm_np, 0, sizeof(CUtensorMap)); memset(&t.tm_zl, 0, sizeof(CUtensorMap));
+    }
+    struct PairInst { const void *fn; int threads, smem; void (*launch)(dim3, cudaStream_t, const AtrousT &); };
+    static const PairInst inst[4] = {       // [tall ? 0 : 1][patch rows 2 ? 0 : 1]
+        {(const void *)atrous_pair_kernel<16, 16, 2, 3>, PairShape<16, 16, 2>::THREADS, PairShape<16, 16, 2>::SMEM,
+         [](dim3 g, cudaStream_t st, const AtrousT &tt) { atrous_pair_kernel<16, 16, 2, 3><<<g, PairShape<16, 16, 2>::THREADS, PairShape<16, 16, 2>::SMEM, st>>>(tt); }},
+        {(const void *)atrous_pair_kernel<16, 16, 1, 3>, PairShape<16, 16, 1>::THREADS, PairShape<16, 16, 1>::SMEM,
+         [](dim3 g, cudaStream_t st, const AtrousT &tt) { atrous_pair_kernel<16, 16, 1, 3><<<g, PairShape<16, 16, 1>::THREADS, PairShape<16, 16, 1>::SMEM, st>>>(tt); }},
+        {(const void *)atrous_pair_kernel<16, 12, 2, 3>, PairShape<16, 12, 2>::THREADS, PairShape<16, 12, 2>::SMEM,
+         [](dim3 g, cudaStream_t st, const AtrousT &tt) { atrous_pair_kernel<16, 12, 2, 3><<<g, PairShape<16, 12, 2>::THREADS, PairShape<16, 12, 2>::SMEM, st>>>(tt); }},
+        {(const void *)atrous_pair_kernel<16, 12, 1, 3>, PairShape<16, 12, 1>::THREADS, PairShape<16, 12, 1>::SMEM,
+         [](dim3 g, cudaStream_t st, const AtrousT &tt) { atrous_pair_kernel<16, 12, 1, 3><<<g, PairShape<16, 12, 1>::THREADS, PairShape<16, 12, 1>::SMEM, st>>>(tt); }},
+    };
+    if (!c->atrous_pair_attr_set) {
+        for (const PairInst &pi : inst) {
+            cudaError_t e = cudaFuncSetAttribute(pi.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pi.smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(pi.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
+        c->atrous_pair_attr_set = true;
+    }
+    const int step = t.k.step, ly = shape == 2 ? 16 : 12;
+    const dim3 g(((lat_w + 15) / 16) * t.ncg, ((lat_rows + ly - 1) / ly) * step);
+    inst[(shape == 2 ? 0 : 2) + (c->atrous_pair_rows == 1 ? 1 : 0)].launch(g, c->stream, t);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
@@ -664,6 +782,7 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     t.ncg = step / AT_C;
     const int lat_w = (c->W + step - 1) / step;                                 // lattice columns per class
     const int lat_rows = (k.row_end - 1) / step - t.b_first + 1;                // lattice rows touching the strip
+    if (c->atrous_variant == 4) return launch_atrous_pair(c, t, a, lat_w, lat_rows);
     const int shape = at_pick_shape(c, a.level, lat_w, lat_rows);
     const AtShapeInfo &si = g_at_shapes[shape];
     t.use_tma = c->tma_ok && a.src_slot >= 0 && c->atrous_variant != 3;

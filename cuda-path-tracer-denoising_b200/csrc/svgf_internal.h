@@ -95,10 +95,12 @@ struct svgf_ctx {
     // sharded frames: 1 = every stage pushes the rows its neighbours will tap into their copy of the plane, levels read local
     // memory only (TMA tiles everywhere); 0 = levels read neighbours' rows in place over NVLink (SVGF_HALO=pull, A/B)
     int halo_push = 1;
-    int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled (TMA tile loads), 3 = lattice-tiled (cp.async)
-    bool atrous_attr_set = false;
+    int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled (TMA tile loads), 3 = lattice-tiled (cp.async),
+                                        // 4 = lattice-tiled, symmetric two-phase pair arithmetic (atrous_pair_core.h)
+    bool atrous_attr_set = false, atrous_pair_attr_set = false;
     // tile shape of the lattice-tiled kernel (index into atrous.cu's table): -1 = chosen per level by the cost model;
     // SVGF_ATROUS_SHAPE=<id> forces one for every level, SVGF_ATROUS_SHAPES=<id>,<id>,... one per level (A/B runs)
+    int atrous_pair_rows = 2;           // SVGF_ATROUS_PAIR_ROWS: centre rows per thread in phase 2 of the pair kernel (1 = 256-thread blocks)
     int atrous_probe = 0;               // SVGF_ATROUS_PROBE: timing probes of the tiled kernel (results are garbage)
     int atrous_shape = -1, atrous_shape_level[SVGF_MAX_LEVELS + 1] = {-1, -1, -1, -1, -1, -1, -1, -1};
     int rt_variant = 0;                 // 0 = state machine, one pixel per thread (default), 1 = wavefront (stage kernels +

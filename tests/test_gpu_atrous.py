@@ -47,6 +47,29 @@ def test_every_tile_shape_matches_oracle(shape, monkeypatch):
     R.close()
 
 
+@pytest.mark.parametrize("rows", [1, 2])
+@pytest.mark.parametrize("forced_shape", [None, 2, 9])
+@pytest.mark.parametrize("size", [(256, 256), (333, 77), (31, 5), (1, 1)])
+def test_pair_variant_matches_oracle(size, forced_shape, rows, monkeypatch):
+    """SVGF_ATROUS_VARIANT=4: the symmetric two-phase kernel (csrc/atrous_pair_core.h; indexing also checked on the CPU by
+    tests/test_atrous_pair_emu.py) meets the same bar as the default kernel, both tile shapes, NaN normals included."""
+    monkeypatch.setenv("SVGF_ATROUS_VARIANT", "4")
+    monkeypatch.setenv("SVGF_ATROUS_PAIR_ROWS", str(rows))
+    if forced_shape is not None:
+        monkeypatch.setenv("SVGF_ATROUS_SHAPE", str(forced_shape))
+    W, H = size
+    m, R = ctx_for(W, H)
+    color, var, g = synthetic_planes(W, H, seed=77 + W)
+    if W > 100:
+        g[H // 3:H // 2, W // 4:W // 2, 0:3] = np.nan
+    for level, last in ((1, False), (2, False), (4, True), (6, False)):
+        co, vo = R.atrous_level(color, var, g, level, last, m.default_params())
+        oc, ov = orc.atrous_level(color, var, g, level, last, orc.default_params())
+        assert_close(co, oc, COLOR_FLOOR, "pair variant colour %dx%d L%d" % (W, H, level))
+        assert_close(vo, ov, VAR_FLOOR, "pair variant variance %dx%d L%d" % (W, H, level))
+    R.close()
+
+
 @pytest.mark.parametrize("shape", [2, 6])
 def test_tile_shapes_in_the_frame_path(shape, monkeypatch):
     """Whole frames with a forced tile shape equal the default shape choice bit for bit (same arithmetic per pixel; only
