@@ -1,14 +1,14 @@
 #!/bin/bash
-# End-of-round GPU session: full GPU test suite, bench lines for every BASELINE.json config (ours + reference arm),
+# End-of-round GPU session (EXTRA_WORKLOADS="c1 c3 c5 c4" EXTRA_REF_WORKLOADS="c1 c3" for every BASELINE.json config): full GPU test suite, bench lines for every BASELINE.json config (ours + reference arm),
 # the ncu launch list of the bench command and one full capture of the a-trous / temporal kernels. Output: gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 timeout -s INT 400 python -m pytest tests -m gpu -q --durations=8 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 timeout 200 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
-for w in c1 c3 c5 c4; do
+for w in $EXTRA_WORKLOADS; do
   timeout 200 python bench.py --workload $w --steps 50 --warmup 10 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
 done
-for w in c2 c1 c3; do
+for w in c2 $EXTRA_REF_WORKLOADS; do
   timeout 200 python bench.py --impl reference --workload $w --steps 30 --warmup 5 > gpurun_out/bench_ref_$w.json 2> gpurun_out/bench_ref_$w.err
 done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches.log 2>&1
