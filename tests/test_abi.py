@@ -75,3 +75,29 @@ def test_scene_blob_reader_matches_oracle_reader():
     for scene in ("cornell", "room", "bunny", "diamond"):
         blob = m.SceneBlob(m.scene_path(scene))
         assert blob.counts == orc.Scene(scene).counts()
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/svgf_b200.h must compile as C99 (no C++/CUDA/torch types), and a C program must link
+    against the library through it (host-only calls; nothing here touches a GPU)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "svgf_b200.h"\n#include <stdio.h>\n'
+                   "int main(void) {\n"
+                   "  svgf_params p; svgf_camera cam; svgf_camera_rig rig; svgf_scene *sc = 0; svgf_scene_desc d;\n"
+                   "  const float eye[3] = {0, 5, 10}, at[3] = {0, 5, 0}, up[3] = {0, 1, 0};\n"
+                   "  svgf_params_default(&p);\n"
+                   "  svgf_camera_init(&cam, &rig, eye, at, up, 45.0f, 64, 48);\n"
+                   "  if (svgf_scene_load(&sc, \"/nonexistent.txt\", 0) == SVGF_OK) return 2;\n"
+                   "  printf(\"%d %d %d %s\\n\", svgf_abi_version(), p.atrous_nlevel, cam.resolution[0], svgf_scene_error(sc));\n"
+                   "  svgf_scene_free(sc); (void)d;\n"
+                   "  return (sizeof(svgf_geom) == 248 && sizeof(svgf_gbuffer_texel) == 52) ? 0 : 1;\n}\n")
+    libdir = os.path.join(ROOT, "cuda-path-tracer-denoising_b200")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lsvgf_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(" ", 3)
+    assert out[0] == "1" and out[1] == "5" and out[2] == "64" and "cannot open scene file" in out[3]
