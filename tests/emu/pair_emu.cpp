@@ -1,7 +1,7 @@
 // pair_emu.cpp -- host emulation of atrous_pair_kernel (csrc/atrous.cu): the kernel's two phases (csrc/atrous_pair_core.h) are
 // executed item by item on a staged tile that is filled the way the TMA load + border fix-up fill shared memory, for every
 // tile of the grid. TEST INFRASTRUCTURE: it lets the CPU suite check the kernel's indexing (forward/backward pair lookup,
-// aprons, ragged borders, strips) against the oracle without a GPU. Built by tests/test_atrous_pair_emu.py with g++.
+// aprons, ragged borders, strips) against the oracle without a GPU. Built by tests/test_atrous_emu.py with g++.
 #include <cstring>
 #include <vector>
 

@@ -1,7 +1,8 @@
-"""CPU: the symmetric ("pair") a-trous tile kernel's two phases (csrc/atrous_pair_core.h -- the very functions the CUDA
-kernel calls) emulated item by item on the host (tests/emu/pair_emu.cpp) against the oracle's restatement of ATrousFilter
-(src/denoise.cu:77-170). Checks what a GPU is not needed for: which unordered pair every (centre, tap) looks up, the aprons,
-ragged image borders, strips of a sharded frame, both tile shapes. Bar as for the CUDA kernel: 1e-4 relative."""
+"""CPU: the a-trous tile kernels' per-thread code -- csrc/atrous_tile_core.h (the production kernel) and
+csrc/atrous_pair_core.h (the symmetric two-phase variant): the very functions the CUDA kernels call -- emulated thread by thread
+on the host (tests/emu/*.cpp) against the oracle's restatement of ATrousFilter (src/denoise.cu:77-170). Checks what a GPU is
+not needed for: the packed pair arithmetic, which taps (and which unordered pair) every centre uses, the aprons, ragged image
+borders, strips of a sharded frame, every tile shape of the kernel's table. Bar as for the CUDA kernels: 1e-4 relative."""
 import ctypes
 import os
 import subprocess
@@ -12,18 +13,28 @@ import pytest
 from util import ROOT, synthetic_planes, assert_close, COLOR_FLOOR, VAR_FLOOR
 import orc
 
-SRC = os.path.join(ROOT, "tests", "emu", "pair_emu.cpp")
-LIB = os.path.join(ROOT, "tests", "emu", "libpair_emu.so")
+CSRC = os.path.join(ROOT, "cuda-path-tracer-denoising_b200", "csrc")
+
+
+def build_emu(name):
+    src, lib = os.path.join(ROOT, "tests", "emu", name + ".cpp"), os.path.join(ROOT, "tests", "emu", "lib" + name + ".so")
+    hdrs = [os.path.join(CSRC, "atrous_pair_core.h"), os.path.join(CSRC, "atrous_tile_core.h")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(f) for f in [src] + hdrs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", src, "-o", lib], check=True)
+    L = ctypes.CDLL(lib)
+    fn = getattr(L, name + "_level")
+    fn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    return fn
 
 
 @pytest.fixture(scope="module")
 def emu():
-    hdr = os.path.join(ROOT, "cuda-path-tracer-denoising_b200", "csrc", "atrous_pair_core.h")
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", SRC, "-o", LIB], check=True)
-    L = ctypes.CDLL(LIB)
-    L.pair_emu_level.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
-    return L
+    return build_emu("pair_emu")
+
+
+@pytest.fixture(scope="module")
+def tile_emu():
+    return build_emu("tile_emu")
 
 
 def device_planes(color, var, g, P):
@@ -58,7 +69,7 @@ def emu_level(L, color, var, g, level, P, shape=0, rows=None):
     cv, gnp, gzl, lv, kl = (np.ascontiguousarray(a) for a in device_planes(color, var, g, P))
     out = np.full((H, W, 4), np.nan, np.float32)
     r0, r1 = rows if rows else (0, H)
-    rc = L.pair_emu_level(cv.ctypes.data, gnp.ctypes.data, gzl.ctypes.data, lv.ctypes.data, kl.ctypes.data, W, H, 1 << level, r0, r1, shape, out.ctypes.data)
+    rc = L(cv.ctypes.data, gnp.ctypes.data, gzl.ctypes.data, lv.ctypes.data, kl.ctypes.data, W, H, 1 << level, r0, r1, shape, out.ctypes.data)
     assert rc == 0
     return out
 
@@ -87,3 +98,29 @@ def test_emulated_strip_and_nan_normals(emu):
     assert np.isnan(out[:19]).all() and np.isnan(out[41:]).all() and np.isfinite(out[19:41]).all()
     assert_close(out[19:41, :, 0:3], oc[19:41], COLOR_FLOOR, "strip colour")
     assert_close(out[19:41, :, 3], ov[19:41], VAR_FLOOR, "strip variance")
+
+
+@pytest.mark.parametrize("shape", range(11))
+@pytest.mark.parametrize("case", [(96, 80, 1), (61, 45, 2), (50, 70, 4), (33, 17, 5), (5, 3, 1), (130, 40, 7)])
+def test_emulated_production_kernel_matches_oracle(tile_emu, case, shape):
+    W, H, level = case
+    color, var, g = synthetic_planes(W, H, seed=300 + W + level)
+    if W > 60:
+        g[H // 4:H // 2, W // 3:W // 2, 0:3] = np.nan          # NaN normals get weight 1 (denoise.cu:144)
+    P = orc.default_params()
+    out = emu_level(tile_emu, color, var, g, level, P, shape)
+    assert np.isfinite(out).all(), "a pixel was not written"
+    oc, ov = orc.atrous_level(color, var, g, level, False, P)
+    assert_close(out[..., 0:3], oc, COLOR_FLOOR, "colour %dx%d L%d shape %d" % (case + (shape,)))
+    assert_close(out[..., 3], ov, VAR_FLOOR, "variance %dx%d L%d shape %d" % (case + (shape,)))
+
+
+def test_emulated_production_kernel_strip(tile_emu):
+    W, H, level = 72, 64, 3
+    color, var, g = synthetic_planes(W, H, seed=9)
+    P = orc.default_params(blurvariance=0)
+    oc, ov = orc.atrous_level(color, var, g, level, False, P)
+    out = emu_level(tile_emu, color, var, g, level, P, 9, rows=(23, 52))
+    assert np.isnan(out[:23]).all() and np.isnan(out[52:]).all()
+    assert_close(out[23:52, :, 0:3], oc[23:52], COLOR_FLOOR, "strip colour")
+    assert_close(out[23:52, :, 3], ov[23:52], VAR_FLOOR, "strip variance")

@@ -52,7 +52,7 @@ def test_every_tile_shape_matches_oracle(shape, monkeypatch):
 @pytest.mark.parametrize("size", [(256, 256), (333, 77), (31, 5), (1, 1)])
 def test_pair_variant_matches_oracle(size, forced_shape, rows, monkeypatch):
     """SVGF_ATROUS_VARIANT=4: the symmetric two-phase kernel (csrc/atrous_pair_core.h; indexing also checked on the CPU by
-    tests/test_atrous_pair_emu.py) meets the same bar as the default kernel, both tile shapes, NaN normals included."""
+    tests/test_atrous_emu.py) meets the same bar as the default kernel, both tile shapes, NaN normals included."""
     monkeypatch.setenv("SVGF_ATROUS_VARIANT", "4")
     monkeypatch.setenv("SVGF_ATROUS_PAIR_ROWS", str(rows))
     if forced_shape is not None:
