@@ -122,14 +122,13 @@ M4 inverse_transpose(const M4 &mm) {
 inline void store(float *dst, const M4 &m) { memcpy(dst, &m, 64); }
 
 // ---- text helpers (utilityCore::safeGetline / tokenizeString, src/utilities.cpp:73-110) ----
-bool get_line(std::istream &is, std::string &t) {      // handles \n, \r\n, \r and a last line without terminator
+void get_line(std::istream &is, std::string &t) {      // handles \n, \r\n, \r and a last line without terminator
     t.clear();
-    if (!is.good()) return false;
+    if (!is.good()) return;
     for (;;) {
-        const int ch = is.get();
-        if (ch == '\n') return true;
-        if (ch == '\r') { if (is.peek() == '\n') is.get(); return true; }
-        if (ch == EOF) { if (t.empty()) is.setstate(std::ios::eofbit); return !t.empty() || false; }
+        const int ch = is.get();        // at end of file this also sets eofbit, which ends the callers' `while (in.good())`
+        if (ch == '\n' || ch == EOF) return;
+        if (ch == '\r') { if (is.peek() == '\n') is.get(); return; }
         t += (char)ch;
     }
 }
