@@ -793,6 +793,14 @@ extern "C" int svgf_fetch(svgf_ctx *c, const char *name, void *host, size_t byte
         CK(cudaStreamSynchronize(c->stream));
         return d2h(c->aos_g, px * sizeof(svgf_gbuffer_texel));
     }
+    if (!strcmp(name, "bvh_packed")) return d2h(c->scene.bvh, (size_t)c->scene.n_nodes * 32);        // 2 x float4 per node
+    if (!strcmp(name, "triangle_ids")) {        // load-order id of the triangle in every slot, in the current (BVH) order
+        std::vector<float4> hot(3 * (size_t)c->scene.n_tris);
+        if (bytes != (size_t)c->scene.n_tris * 4) { c->err = "svgf_fetch(triangle_ids): size mismatch"; return SVGF_ERR_INVALID; }
+        if (!hot.empty()) CK(cudaMemcpy(hot.data(), c->scene.tri_hot, hot.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < c->scene.n_tris; i++) memcpy(static_cast<char *>(host) + 4 * (size_t)i, &hot[3 * (size_t)i].w, 4);
+        return SVGF_OK;
+    }
     if (!strcmp(name, "view_matrix_prev")) {
         if (bytes != 64) return SVGF_ERR_INVALID;
         memcpy(host, c->view_matrix_prev, 64);

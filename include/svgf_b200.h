@@ -214,6 +214,14 @@ void *svgf_stream(svgf_ctx *ctx);
  *   "history_cap"             n    history_length saturates at n > 0 (unbounded in the reference, denoise.cu:290-294). */
 int svgf_set_option(svgf_ctx *ctx, const char *name, int value);
 
+/* ---- BVH build on the device -------------------------------------------------------------------- */
+/* Replaces the tree uploaded by svgf_create (the reference's host-built SAH tree, src/bvhtree.cpp) with a linear BVH built on
+ * the GPU over the context's triangles (Morton codes, radix sort, Karras' radix tree; csrc/lbvh_core.h), re-ordering the
+ * triangle records to match. Same node semantics (pre-order, left child = index + 1, BVH_ArrNode, src/bvhtree.h:48-54), so the
+ * traversal is unchanged and frames match the host-built tree up to ties between equal hit distances. For geometry that
+ * changes on the device; synchronises the context's stream. svgf_fetch names: "bvh_packed", "triangle_ids". */
+int svgf_rebuild_bvh(svgf_ctx *ctx);
+
 /* ---- multi-GPU: a frame sharded by row strips, one process (context) per GPU -------------------------------- */
 /* Every rank holds full-frame planes and renders rows [row_starts[rank], row_starts[rank+1]); rows owned by other
  * ranks are read in place from the owner's memory over NVLink (CUDA IPC), ordered by per-stage flags -- no halo copy,
