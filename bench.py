@@ -127,7 +127,12 @@ def run_reference(args, wl, rank, world):
     line = {"impl": "reference", "metric": "Mpixels/sec", "unit": "Mpixels/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "scene": wl["scene"], "width": wl["W"], "height": wl["H"], "atrous_levels": wl["nlevel"]}}
-    if refh.available("gpu"):
+    try:        # the reference's own error handling is print + exit(EXIT_FAILURE) (pathtrace.cu:25-43): never enter it without a device
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if refh.available("gpu") and have_gpu:
         try:
             h = refh.RefHarness("gpu")
             h.load_blob(wl["scene"], wl["W"], wl["H"])
@@ -152,7 +157,7 @@ def run_reference(args, wl, rank, world):
     cb = cpu_baseline(wl, frames)
     line.update({"value": cb["value"], "fps": cb["fps"], "ms_per_step": 1000.0 / cb["fps"], "cpu_baseline": cb,
                  "e2e": {"value": cb["value"], "unit": "Mpixels/sec", "fps": cb["fps"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                 "config": dict(line["config"], parallelism="host cores", device="cpu (oracle port; reference binary absent)")})
+                 "config": dict(line["config"], parallelism="host cores", device="cpu (oracle port: no CUDA device, or the reference binary did not travel)")})
     print(json.dumps(line), flush=True)
 
 
