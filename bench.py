@@ -46,6 +46,10 @@ WORKLOADS = {   # BASELINE.json configs
     "c3": dict(scene="room", W=1920, H=1080, nlevel=5, moving=False, name="C3 room.txt 1920x1080, 1spp, 5 a-trous iters"),
     "c4": dict(scene="cornell", W=3840, H=2160, nlevel=5, moving=False, name="C4 cornell.txt 3840x2160, 1spp, 5 a-trous iters"),
     "c5": dict(scene="bunny", W=1920, H=1080, nlevel=5, moving=True, name="C5 bunny.txt moving camera 1920x1080, 1spp, 5 a-trous iters"),
+    # north_star: "cornell.txt and room.txt at 720p/1080p/4K"
+    "cornell720": dict(scene="cornell", W=1280, H=720, nlevel=5, moving=False, name="cornell.txt 1280x720, 1spp, 5 a-trous iters"),
+    "room720": dict(scene="room", W=1280, H=720, nlevel=5, moving=False, name="room.txt 1280x720, 1spp, 5 a-trous iters"),
+    "room4k": dict(scene="room", W=3840, H=2160, nlevel=5, moving=False, name="room.txt 3840x2160, 1spp, 5 a-trous iters"),
 }
 C5_SPEEDS = dict(camera_speed_x=0.05, camera_speed_y=0.02, camera_speed_z=0.02, camera_speed_theta=0.02, camera_speed_phi=0.05)
 
@@ -104,7 +108,8 @@ def measured_peak():
 
 
 def cpu_baseline(wl, frames=2):
-    """Oracle port of the whole frame on the host cores, bounded: `frames` frames from a reset."""
+    """Oracle port on the host cores, bounded: `frames` whole frames from a reset, then the a-trous levels on their own
+    (north_star: "a CPU a-trous baseline timed on the box's host cores (core count stated)") on the planes those frames left."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
     sc = orc.Scene(wl["scene"]); o = orc.Oracle(sc, wl["W"], wl["H"]); P = orc.default_params(atrous_nlevel=wl["nlevel"])
@@ -114,8 +119,29 @@ def cpu_baseline(wl, frames=2):
     for f in range(frames):
         o.frame(drv.step(), P, f, orc.VAR_JACOBI, threads)
     dt = time.perf_counter() - t0
-    return {"value": frames / dt * wl["W"] * wl["H"] / 1e6, "unit": "Mpixels/sec", "fps": frames / dt, "cores": threads, "kind": "port",
-            "sample": "%d frames of %s from reset, oracle/svgf_oracle.cpp (OpenMP, %d threads), %.1f s" % (frames, wl["name"], threads, dt)}
+    color, var, g = o.fetch("color_acc"), o.fetch("variance"), o.fetch("gbuffer")
+    lv_ms = []
+    for level in range(1, wl["nlevel"] + 1):
+        t1 = time.perf_counter()
+        color, var = orc.atrous_level(color, var, g, level, level == wl["nlevel"], P, orc.VAR_JACOBI, threads)
+        lv_ms.append((time.perf_counter() - t1) * 1e3)
+    px = wl["W"] * wl["H"]
+    return {"value": frames / dt * px / 1e6, "unit": "Mpixels/sec", "fps": frames / dt, "cores": threads, "kind": "port",
+            "atrous_ms_per_level": lv_ms,
+            "atrous_gbs_per_level": [px * (68 if l == wl["nlevel"] - 1 else 56) / (t * 1e-3) / 1e9 for l, t in enumerate(lv_ms)],
+            "sample": "%d frames of %s from reset, oracle/svgf_oracle.cpp (OpenMP, %d threads), %.1f s; then each a-trous level once on "
+                      "the accumulated planes of the last frame (ATrousFilter port, same threads, %.0f ms)" % (frames, wl["name"], threads, dt, sum(lv_ms))}
+
+
+def kernel_source_hash():
+    """Hash of the a-trous kernel sources: profiles/atrous_traffic.json records the hash it was captured with."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, PKG, "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.startswith("atrous") and (f.endswith(".cu") or f.endswith(".h") or f.endswith(".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def run_reference(args, wl, rank, world):
@@ -209,6 +235,7 @@ def run_ours(args, wl, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank); clocks.start()       # from before the warm-up, so that short runs get samples too
     for _ in range(max(args.warmup, 3)):
         R.pathtrace(drv.step(), P, frame, host_image=host_np); frame += 1
     for i in range(3):      # sets up the copy stream and the second output buffer of the pipelined path
@@ -216,7 +243,6 @@ def run_ours(args, wl, rank, world, local_rank):
     R.wait_image(None)
 
     # ---- device-resident throughput (value): K frames back to back, CUDA events on the library's stream ----
-    clocks = ClockSampler(local_rank); clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -257,6 +283,29 @@ def run_ours(args, wl, rank, world, local_rank):
     clk = clocks.stop()
     if world > 1 and R.peer_error():
         raise SystemExit("bench.py: a cross-rank wait timed out (a peer stopped making progress)")
+    # ---- N > 1: the same workload UNSHARDED on one GPU in the same run (rank 0), so that the strong-scaling factor is a
+    # same-run, same-resolution number ----
+    anchor = None
+    if world > 1:
+        if rank == 0:
+            _, R1 = m.open_scene(wl["scene"], W, H, device=local_rank)
+            d1 = blob.camera_driver(W, H, automate=wl["moving"])
+            s1 = torch.cuda.ExternalStream(R1.stream(), device=torch.device("cuda", local_rank))
+            f1 = 0
+            for _ in range(max(args.warmup, 3)):
+                R1.pathtrace(d1.step(), P, f1); f1 += 1
+            R1.sync()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(s1)
+            for _ in range(args.steps):
+                R1.pathtrace(d1.step(), P, f1); f1 += 1
+            a1.record(s1)
+            R1.sync()
+            ms1 = a0.elapsed_time(a1)
+            anchor = {"value": args.steps * 1000.0 / ms1 * W * H / 1e6, "fps": args.steps * 1000.0 / ms1, "ms_per_step": ms1 / args.steps,
+                      "what": "the same workload unsharded on ONE GPU (rank 0's), same run, device-resident"}
+            R1.close()
+        barrier()
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e, ms_blk], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -278,9 +327,11 @@ def run_ours(args, wl, rank, world, local_rank):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "atrous_traffic.json")
     if os.path.exists(tp) and world == 1 and (W, H) == (1920, 1080):     # the capture is of C2; other workloads report null
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        if tj.get("kernel_source_hash") == kernel_source_hash():            # a capture of other kernel code is stale: null
+            traffic = tj.get("dram_bytes_per_launch")
     cb = cpu_baseline(wl, 2) if world == 1 and not args.no_cpu_baseline else None
-    launches_per_frame = 1 + 1 + 2 * nl + 1 + (0 if world == 1 else 3 + 2 * nl)     # rt, temporal, (kl + tiled) x levels, pack [+ signal/wait]
+    launches_per_frame = 1 + 1 + 2 * nl + 1 + (0 if world == 1 else 2)     # rt, temporal, (kl + tiled) x levels, pack [+ frame wait/signal]
     line = {
         "metric": "Mpixels/sec", "value": fps_dev * px / 1e6, "unit": "Mpixels/sec", "fps": fps_dev, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -294,6 +345,8 @@ def run_ours(args, wl, rank, world, local_rank):
                 "blocking": {"value": fps_blk * px / 1e6, "fps": fps_blk, "ms_per_step": ms_blk / args.steps,
                              "api": "svgf_render(..., host_image): returns with the image in place, like the reference's pathtrace()"},
                 "note": "every rank copies its own strip of the image to its host buffer each frame" if world > 1 else "whole image to host each frame"},
+        "e2e_blocking": {"value": fps_blk * px / 1e6, "unit": "Mpixels/sec", "fps": fps_blk,
+                         "note": "like for like with the reference arm, whose pathtrace() blocks on its D2H every frame (e2e.value is the pipelined API)"},
         "gpu_launches": launches_per_frame * args.steps * 4 * world,
         "roofline": {"bound": "hbm", "kernel": "atrous level (all %d levels)" % nl, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -304,7 +357,61 @@ def run_ours(args, wl, rank, world, local_rank):
     }
     if cb:
         line["cpu_baseline"] = cb
+    if anchor:
+        line["anchor_1gpu"] = anchor
+        line["speedup_vs_1gpu_same_run"] = line["value"] / anchor["value"]
     print(json.dumps(line), flush=True)
+
+
+def run_verify(args, wl, rank, world, local_rank):
+    """--verify: parity of the REAL multi-GPU path (one process per GPU, CUDA-IPC mappings, cross-device flags, dual stores
+    over NVLink, an uneven cost-style partition): every rank renders the frames sharded AND, on its own GPU, the same frames
+    unsharded, and compares its strip of every buffer bit for bit. Prints one JSON line; exit code 1 on any mismatch."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    m = importlib.import_module(PKG)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, H, nl = wl["W"], wl["H"], wl["nlevel"]
+    blob, R = m.open_scene(wl["scene"], W, H, device=local_rank)
+    _, F = m.open_scene(wl["scene"], W, H, device=local_rank)
+    P = m.default_params(atrous_nlevel=nl)
+    rows = [0, H]
+    if world > 1:       # deliberately uneven strips, like the cost-balanced partitions of the bench
+        cost = [1.0 + 0.35 * ((r * 5) % 3) for r in range(world)]
+        rows = m.balanced_partition(m.row_partition(H, world), cost)
+        m.connect_ranks(R, dist, rank, world, rows)
+    drv = blob.camera_driver(W, H, automate=wl["moving"])
+    frames = max(2, min(args.steps, 8))
+    keys = ["image", "gbuffer", "history_length", "moment_acc", "color_history", "variance", "denoised", "pbo"]
+    bad = []
+    for f in range(frames):
+        cam = m.Camera.from_array(drv.step().as_array())
+        R.pathtrace(cam, P, f); F.pathtrace(cam, P, f)
+        if f in (0, frames // 2, frames - 1):
+            R.sync(); F.sync()
+            for k in keys:
+                a, b = R.fetch(k)[rows[rank]:rows[rank + 1]], F.fetch(k)[rows[rank]:rows[rank + 1]]
+                if not np.array_equal(a.view(np.uint8), b.view(np.uint8)):
+                    bad.append("frame %d %s: %d differing bytes in rank %d's rows [%d, %d)" % (f, k, int((a.view(np.uint8) != b.view(np.uint8)).sum()), rank, rows[rank], rows[rank + 1]))
+            if world > 1:
+                dist.barrier()      # nobody races ahead into frames whose inputs a fetching rank still reads
+    R.sync()
+    perr = R.peer_error() if world > 1 else 0
+    nbad = torch.tensor([len(bad) + (1 if perr else 0)], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(nbad)
+    for b in bad[:8]:
+        print("rank %d: %s" % (rank, b), file=sys.stderr, flush=True)
+    if rank == 0:
+        print(json.dumps({"verify": "ok" if int(nbad.item()) == 0 else "MISMATCH", "n_gpus": world, "workload": wl["name"], "frames": frames,
+                          "rows": rows, "buffers": keys, "mismatching_comparisons": int(nbad.item()),
+                          "what": "every rank's strip of every buffer, sharded vs unsharded on the same GPU, bit for bit"}), flush=True)
+    if world > 1:
+        dist.barrier()
+    sys.exit(0 if int(nbad.item()) == 0 else 1)
 
 
 def main():
@@ -315,10 +422,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="multi-GPU parity: sharded == unsharded, bit for bit, on the real transport")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload or ("c2" if args.gpus == 1 else "c4")]
-    if args.impl == "reference":
+    if args.verify:
+        run_verify(args, wl, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, wl, rank, world)
     else:
         run_ours(args, wl, rank, world, local_rank)

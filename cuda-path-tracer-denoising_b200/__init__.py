@@ -83,7 +83,7 @@ EXPORTS = ["svgf_params_default", "svgf_create", "svgf_destroy", "svgf_reset", "
            "svgf_denoise_host", "svgf_atrous_host", "svgf_fetch", "svgf_last_error", "svgf_abi_version", "svgf_stage_times",
            "svgf_set_profiling", "svgf_stream", "svgf_set_shard", "svgf_ipc_handles_size", "svgf_ipc_export",
            "svgf_ipc_connect", "svgf_peer_connect_local", "svgf_peer_error", "svgf_camera_init", "svgf_camera_step",
-           "svgf_render_async", "svgf_wait_image", "svgf_scene_load", "svgf_scene_free", "svgf_scene_error", "svgf_scene_describe",
+           "svgf_render_async", "svgf_wait_image", "svgf_register_host", "svgf_unregister_host", "svgf_scene_load", "svgf_scene_free", "svgf_scene_error", "svgf_scene_describe",
            "svgf_set_option", "svgf_rebuild_bvh", "svgf_scene_camera", "svgf_scene_num_textures", "svgf_scene_texture_file", "svgf_scene_set_texture", "svgf_scene_mesh_boxes"]
 
 _lib = None
@@ -120,6 +120,8 @@ def lib():
         L.svgf_scene_mesh_boxes.argtypes = [vp, vp, ci]
         L.svgf_render_async.argtypes = [vp, ctypes.POINTER(Camera), ctypes.POINTER(Params), ci, vp, vp]
         L.svgf_wait_image.argtypes = [vp, vp]
+        L.svgf_register_host.argtypes = [vp, vp, ctypes.c_size_t]
+        L.svgf_unregister_host.argtypes = [vp, vp]
         L.svgf_denoise.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Camera), ctypes.POINTER(Params)]
         L.svgf_denoise_host.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Camera), ctypes.POINTER(Params)]
         L.svgf_atrous_host.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ctypes.POINTER(Params)]
@@ -248,6 +250,13 @@ class Renderer:
         complete after wait_image(host_image). Alternate between two host arrays to keep one frame in flight."""
         self._ck(lib().svgf_render_async(self.h, ctypes.byref(cam), ctypes.byref(params), frame, pbo_dev, host_image.ctypes.data),
                  "svgf_render_async")
+
+    def register_host(self, array):
+        """Page-lock a numpy array for direct DMA (svgf_register_host); keep it alive until unregister_host/close."""
+        self._ck(lib().svgf_register_host(self.h, array.ctypes.data, array.nbytes), "svgf_register_host")
+
+    def unregister_host(self, array):
+        self._ck(lib().svgf_unregister_host(self.h, array.ctypes.data), "svgf_unregister_host")
 
     def wait_image(self, host_image=None):
         self._ck(lib().svgf_wait_image(self.h, host_image.ctypes.data if host_image is not None else None), "svgf_wait_image")
@@ -387,6 +396,7 @@ class SceneFile:
         d = SceneDesc()
         if lib().svgf_scene_describe(self.h, W, H, ctypes.byref(d)) != 0:
             raise SvgfError(lib().svgf_scene_error(self.h).decode())
+        d._keepalive = self     # the arrays live inside the svgf_scene: keep it alive as long as the description
         return d
 
     def arrays(self, W=1, H=1):

@@ -156,8 +156,8 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
 // The planes another rank may read, in the fixed order used for IPC export (SVGF_IPC_NBUF entries).
 static void shared_bufs(svgf_ctx *c, void **o) {
     int n = 0;
-    for (int i = 0; i < 3; i++) o[n++] = c->cv[i];
-    for (int i = 0; i < 3; i++) o[n++] = c->lv[i];
+    for (int i = 0; i < SVGF_NCV; i++) o[n++] = c->cv[i];
+    for (int i = 0; i < SVGF_NCV; i++) o[n++] = c->lv[i];
     for (int i = 0; i < 2; i++) o[n++] = c->nrm[i];
     for (int i = 0; i < 2; i++) o[n++] = c->mom[i];
     for (int i = 0; i < 2; i++) o[n++] = c->hlen[i];
@@ -165,8 +165,8 @@ static void shared_bufs(svgf_ctx *c, void **o) {
 }
 static void set_peer(svgf_ctx *c, int r, void *const *b) {
     int n = 0;
-    for (int i = 0; i < 3; i++) c->p_cv[i].p[r] = (float4 *)b[n++];
-    for (int i = 0; i < 3; i++) c->p_lv[i].p[r] = (float2 *)b[n++];
+    for (int i = 0; i < SVGF_NCV; i++) c->p_cv[i].p[r] = (float4 *)b[n++];
+    for (int i = 0; i < SVGF_NCV; i++) c->p_lv[i].p[r] = (float2 *)b[n++];
     for (int i = 0; i < 2; i++) c->p_nrm[i].p[r] = (float4 *)b[n++];
     for (int i = 0; i < 2; i++) c->p_mom[i].p[r] = (float2 *)b[n++];
     for (int i = 0; i < 2; i++) c->p_hlen[i].p[r] = (int *)b[n++];
@@ -176,8 +176,8 @@ static void set_peer(svgf_ctx *c, int r, void *const *b) {
 static int alloc_frame_buffers(svgf_ctx *c) {
     const size_t px = c->px;
     // planes the TMA tile loader addresses get SVGF_PAD_ROWS rows of (zeroed, never written) padding: lattice extents round up
-    const size_t ppx = px + (size_t)SVGF_PAD_ROWS * c->W;
-    for (int i = 0; i < 3; i++) {
+    const size_t ppx = px + (size_t)SVGF_PAD_ROWS * c->W + SVGF_PAD_PX;
+    for (int i = 0; i < SVGF_NCV; i++) {
         CK(dalloc(&c->cv[i], ppx)); CK(dalloc(&c->lv[i], ppx));
         CK(cudaMemset(c->cv[i], 0, ppx * sizeof(float4))); CK(cudaMemset(c->lv[i], 0, ppx * sizeof(float2)));
     }
@@ -187,8 +187,14 @@ static int alloc_frame_buffers(svgf_ctx *c) {
     CK(dalloc(&c->image, 3 * px)); CK(dalloc(&c->denoised, 3 * px)); CK(dalloc(&c->var_out, px));
     CK(dalloc(&c->stale_nm, px)); CK(dalloc(&c->stale_uv, px)); CK(dalloc(&c->kl, px));
     CK(cudaMalloc((void **)&c->pbo_own, px * 8));
-    CK(cudaMalloc((void **)&c->flags, (SVGF_MAX_RANKS * SVGF_NUM_STAGES + 1) * sizeof(unsigned)));
-    CK(cudaMemset(c->flags, 0, (SVGF_MAX_RANKS * SVGF_NUM_STAGES + 1) * sizeof(unsigned)));
+    CK(cudaMalloc((void **)&c->flags, SVGF_MAX_RANKS * SVGF_NUM_STAGES * sizeof(unsigned)));
+    CK(cudaMemset(c->flags, 0, SVGF_MAX_RANKS * SVGF_NUM_STAGES * sizeof(unsigned)));
+    CK(cudaMalloc((void **)&c->done_count, SVGF_NUM_STAGES * sizeof(unsigned)));
+    CK(cudaMemset(c->done_count, 0, SVGF_NUM_STAGES * sizeof(unsigned)));
+    // the "a cross-rank wait gave up" word lives in mapped host memory: kernels set it, the host reads it without a copy
+    CK(cudaHostAlloc((void **)&c->comm_err, sizeof(unsigned), cudaHostAllocMapped));
+    *c->comm_err = 0u;
+    CK(cudaHostGetDevicePointer((void **)&c->comm_err_dev, c->comm_err, 0));
     {   // until peers are connected every table entry is this context's own plane
         void *own[SVGF_IPC_NBUF]; shared_bufs(c, own);
         for (int r = 0; r < SVGF_MAX_RANKS; r++) set_peer(c, r, own);
@@ -263,8 +269,10 @@ int svgf_destroy(svgf_ctx *c) {
     DeviceScene &s = c->scene;
     cudaFree(s.geoms); cudaFree(s.materials); cudaFree(s.bvh); cudaFree(s.tri_hot); cudaFree(s.tri_cold); cudaFree(s.textures);
     for (unsigned char *p : s.tex_pixels) cudaFree(p);      // the reference leaks these (pathtrace.cu:136 vs 160-183)
-    for (int i = 0; i < 3; i++) { cudaFree(c->cv[i]); cudaFree(c->lv[i]); }
+    for (int i = 0; i < SVGF_NCV; i++) { cudaFree(c->cv[i]); cudaFree(c->lv[i]); }
     free(c->tmaps);
+    cudaFree(c->done_count);
+    if (c->comm_err) cudaFreeHost(c->comm_err);
     for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }
     cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->gnp); cudaFree(c->gzl); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
     cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl); cudaFree(c->flags); cudaFree(c->wf_mem); cudaFree(c->rt_counter);
@@ -290,9 +298,10 @@ int svgf_reset(svgf_ctx *c) {
     CK(cudaSetDevice(c->device));
     const size_t px = c->px;
     cudaStream_t st = c->stream;
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < SVGF_NCV; i++) {
         CK(cudaMemsetAsync(c->cv[i], 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->lv[i], 0, px * sizeof(float2), st));
     }
+    CK(cudaMemsetAsync(c->done_count, 0, SVGF_NUM_STAGES * sizeof(unsigned), st));
     for (int i = 0; i < 2; i++) {
         CK(cudaMemsetAsync(c->nrm[i], 0, px * sizeof(float4), st));
         CK(cudaMemsetAsync(c->mom[i], 0, px * sizeof(float2), st));
@@ -311,6 +320,7 @@ int svgf_reset(svgf_ctx *c) {
     CK(cudaMemsetAsync(c->pbo_own, 0, px * 8, st));
     c->hist_cv = 0; c->cur_nrm = 0; c->cur_mom = 0; c->cur_hlen = 0;
     CK(cudaStreamSynchronize(st));
+    if (c->comm_err) *c->comm_err = 0u;      // a reset is the way out of a communication error
     return SVGF_OK;
 }
 
@@ -388,13 +398,10 @@ int svgf_peer_connect_local(svgf_ctx **ctxs, int world, const int *row_starts) {
     return SVGF_OK;
 }
 
-// 1 if a cross-rank wait timed out since the context was created (a peer stopped making progress).
+// 1 if a cross-rank wait timed out since the last svgf_reset (a peer stopped making progress).
 int svgf_peer_error(svgf_ctx *c) {
     if (!c) return SVGF_ERR_INVALID;
-    unsigned v = 0;
-    CK(cudaSetDevice(c->device));
-    CK(cudaMemcpy(&v, c->flags + SVGF_MAX_RANKS * SVGF_NUM_STAGES, sizeof(v), cudaMemcpyDeviceToHost));
-    return (int)v;
+    return c->comm_err ? (int)*static_cast<volatile unsigned *>(c->comm_err) : 0;
 }
 
 enum { SVGF_PROF_MAX_FRAMES = 512 };
@@ -443,11 +450,47 @@ int svgf_set_option(svgf_ctx *c, const char *name, int value) {
     return SVGF_ERR_UNKNOWN_NAME;
 }
 
+// A wait that gave up let its frame continue on stale rows of a peer: everything rendered since is suspect.
+static int comm_check(svgf_ctx *c) {
+    if (c->rows.world > 1 && c->comm_err && *static_cast<volatile unsigned *>(c->comm_err)) {
+        c->err = "a cross-rank wait timed out (a peer stopped making progress); frames since then are invalid -- svgf_reset on all ranks to recover";
+        return SVGF_ERR_COMM;
+    }
+    return SVGF_OK;
+}
+
 int svgf_sync(svgf_ctx *c) {
     if (!c) return SVGF_ERR_INVALID;
     CK(cudaStreamSynchronize(c->stream));
     if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
+    return comm_check(c);
+}
+
+// Page-lock a caller buffer for svgf_render_async (and for direct DMA from svgf_render). The buffer must stay allocated
+// until svgf_unregister_host or svgf_destroy.
+int svgf_register_host(svgf_ctx *c, void *host, size_t bytes) {
+    if (!c || !host || !bytes) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    for (auto &r : c->registered_hosts) if (r.first == host) return r.second >= bytes ? SVGF_OK : SVGF_ERR_INVALID;
+    CK(cudaHostRegister(host, bytes, cudaHostRegisterDefault));
+    c->registered_hosts.push_back({host, bytes});
     return SVGF_OK;
+}
+
+int svgf_unregister_host(svgf_ctx *c, void *host) {
+    if (!c || !host) return SVGF_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    for (size_t i = 0; i < c->registered_hosts.size(); i++)
+        if (c->registered_hosts[i].first == host) {
+            CK(cudaStreamSynchronize(c->stream));
+            if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
+            for (int k = 0; k < 2; k++) if (c->copy_host[k] == host) { c->copy_pending[k] = 0; c->copy_host[k] = nullptr; }
+            CK(cudaHostUnregister(host));
+            c->registered_hosts.erase(c->registered_hosts.begin() + i);
+            return SVGF_OK;
+        }
+    c->err = "svgf_unregister_host: not registered by this context";
+    return SVGF_ERR_INVALID;
 }
 
 }  // extern "C"
@@ -460,16 +503,20 @@ template <class T> static HaloPlane halo_plane(const T *local, const PeerPtr<T> 
     return h;
 }
 
-static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, const svgf_params *P, cudaEvent_t *ev) {
-    const int acc_slot = (c->hist_cv + 1) % 3;          // any buffer that is not the current history
+static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, const svgf_params *P, cudaEvent_t *ev, bool gbuf_pushed) {
+    // Four colour buffers rotate: H = the history the previous frame left (read in place by every rank's temporal pass and
+    // therefore never written during this frame), the accumulated colour, and two for the a-trous ping-pong.
+    const int H_old = c->hist_cv;
+    const int acc_slot = (H_old + 1) % SVGF_NCV;
     float4 *acc = c->cv[acc_slot];
     // Sharded frames, push mode: a level taps rows up to 2*step beyond the strip. Instead of reading them from their owners
-    // in place (32-byte gathers over NVLink, every coarse tile), each stage's producer copies the rows its neighbours will
-    // tap into THEIR copy of the plane right after producing them (dense stores, nobody waits on them), and the levels read
-    // local memory only. The G-buffer view travels once per frame, for the coarsest level's reach.
+    // in place (32-byte gathers over NVLink, every coarse tile), each stage's producer stores the rows its neighbours will
+    // tap into THEIR copy of the plane as it produces them (dual stores), and the levels read local memory only. The
+    // G-buffer view travels once per frame, for the coarsest level's reach.
     const bool filter = P->right_view_option == 0 && P->atrous_nlevel > 0 && P->spatial_enable;
-    const bool push = c->halo_push && c->shard.world > 1 && filter;
-    if (push) {
+    const bool sharded = c->rows.world > 1 && filter;
+    const bool push = c->halo_push && sharded;
+    if (push && !gbuf_pushed) {
         const HaloPlane g[2] = {halo_plane(c->gnp, c->p_gnp), halo_plane(c->gzl, c->p_gzl)};
         CK(launch_halo_push(c, 2 << P->atrous_nlevel, g, 2));
     }
@@ -483,17 +530,21 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
         clip_ry = 1.0f / (cam->pixelLength[1] * (float)c->H * 0.5f);
     }
     if (P->temporal_enable) {
-        CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->p_nrm[c->cur_nrm ^ 1], c->pos, c->p_cv[c->hist_cv], c->p_mom[c->cur_mom],
+        // level 1 (step 2) taps +-4 rows: those rows of the accumulated planes go to the neighbours from inside the kernel,
+        // whose last block raises the stage flag
+        HaloOut ho = halo_out(c, SVGF_STAGE_TEMPORAL, sharded ? 4 : 0, true);
+        if (!push) memset(&ho.peers.lo, 0, sizeof(ho.peers.lo)), memset(&ho.peers.hi, 0, sizeof(ho.peers.hi));   // pull mode: flags only
+        CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->p_nrm[c->cur_nrm ^ 1], c->pos, c->p_cv[H_old], c->p_mom[c->cur_mom],
                            c->p_hlen[c->cur_hlen], acc, c->lv[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1],
-                           c->view_matrix_prev, color_alpha, moment_alpha, clip_rx, clip_ry));
+                           c->view_matrix_prev, color_alpha, moment_alpha, clip_rx, clip_ry, ho, c->p_cv[acc_slot], c->p_lv[acc_slot]));
     } else {
         CK(launch_no_temporal(c, image, acc, c->lv[acc_slot]));
+        if (push) {
+            const HaloPlane h[2] = {halo_plane(c->cv[acc_slot], c->p_cv[acc_slot]), halo_plane(c->lv[acc_slot], c->p_lv[acc_slot])};
+            CK(launch_halo_push(c, 4, h, 2));
+        }
+        if (sharded) CK(launch_signal(c, SVGF_STAGE_TEMPORAL, 4));
     }
-    if (push) {     // level 1 (step 2) taps +-4 rows
-        const HaloPlane h[2] = {halo_plane(c->cv[acc_slot], c->p_cv[acc_slot]), halo_plane(c->lv[acc_slot], c->p_lv[acc_slot])};
-        CK(launch_halo_push(c, 4, h, 2));
-    }
-    CK(launch_signal(c, SVGF_STAGE_TEMPORAL));
     if (ev) CK(cudaEventRecord(ev[2], c->stream));
     int new_hist = acc_slot;        // denoise.cu:366/370: colour history := accumulated (or input) colour
     if (P->right_view_option == 1) {
@@ -510,12 +561,9 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
         for (int level = 1; level <= P->atrous_nlevel; level++) {
             const bool last = level == P->atrous_nlevel;
             const bool is_hist = level == P->history_level;
-            // destination: any slot that is neither the source nor the (new) history
+            // destination: a slot that is neither the source, nor the (new) history, nor the history other ranks still read
             int dst = -1;
-            for (int s = 0; s < 3; s++) if (s != src && s != new_hist) { dst = s; break; }
-            // a level reads its input planes (and the G-buffer) of rows owned by other ranks in place: those ranks
-            // must have finished producing them, and must be done reading what this level overwrites (same condition)
-            CK(launch_wait(c, level == 1 ? SVGF_STAGE_TEMPORAL : SVGF_STAGE_LEVEL0 + level - 1, c->seq));
+            for (int s = 0; s < SVGF_NCV; s++) if (s != src && s != new_hist && s != H_old) { dst = s; break; }
             AtrousArgs a;
             a.src_slot = src;
             a.cv_in = c->cv[src];
@@ -525,12 +573,14 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             a.denoised_out = last ? c->denoised : nullptr; a.var_out = last ? c->var_out : nullptr;
             a.level = level; a.is_last = last; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
             a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;
+            // A level reads rows of the neighbours in reach (2 * step): they must have produced them -- and be done reading what
+            // this level's stores overwrite in their planes, which the same flag says. The wait sits in the edge blocks of the
+            // level's pre-pass; the edge rows and the flag for the NEXT level (reach 4 * step) leave from the tile kernel.
+            const int prev_stage = level == 1 ? SVGF_STAGE_TEMPORAL : SVGF_STAGE_LEVEL0 + level - 1;
+            a.wait = halo_in(c, prev_stage, sharded ? (2 << level) : 0, c->seq);
+            a.ho = halo_out(c, SVGF_STAGE_LEVEL0 + level, (sharded && !last) ? (4 << level) : 0, true);
+            if (!push) memset(&a.ho.peers.lo, 0, sizeof(a.ho.peers.lo)), memset(&a.ho.peers.hi, 0, sizeof(a.ho.peers.hi));
             CK(launch_atrous(c, a));
-            if (push && !last) {        // the next level (step 2^(level+1)) taps +-2 steps
-                const HaloPlane h[2] = {halo_plane(c->cv[dst], c->p_cv[dst]), halo_plane(c->lv[dst], c->p_lv[dst])};
-                CK(launch_halo_push(c, 4 << level, h, 2));
-            }
-            CK(launch_signal(c, SVGF_STAGE_LEVEL0 + level));
             if (ev && level <= SVGF_MAX_LEVELS) CK(cudaEventRecord(ev[2 + level], c->stream));
             if (is_hist) new_hist = dst;     // denoise.cu:391: colour history := this level's output
             src = dst;
@@ -561,13 +611,11 @@ static cudaEvent_t *prof_begin(svgf_ctx *c, const svgf_params *P) {
     return pf.ev;
 }
 
-// Page-lock a caller buffer the first time it is seen, so the per-frame D2H (pathtrace.cu:450) is a direct DMA.
-static bool host_is_registered(svgf_ctx *c, void *p, size_t bytes) {
-    for (auto &r : c->registered_hosts) if (r.first == p && r.second >= bytes) return true;
+// Is `p` page-locked right now (by the caller, or through svgf_register_host)? Asked of the driver on every call: a cached
+// answer would outlive the memory it was given for.
+static bool host_is_pinned(const void *p) {
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;   // already pinned by the caller
-    (void)cudaGetLastError();
-    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) { c->registered_hosts.push_back({p, bytes}); return true; }
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;
     (void)cudaGetLastError();
     return false;
 }
@@ -598,7 +646,11 @@ static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P
     if (async && host_image) {
         int rc = async_setup(c);
         if (rc != SVGF_OK) return rc;
-        if (!host_is_registered(c, host_image, c->px * 12)) { c->err = "svgf_render_async: host_image cannot be page-locked"; return SVGF_ERR_INVALID; }
+        // the copy outlives this call, so the buffer must be page-locked; done here on first sight (documented in the header:
+        // the caller keeps it allocated until svgf_unregister_host / svgf_destroy)
+        if (!host_is_pinned(host_image) && svgf_register_host(c, host_image, c->px * 12) != SVGF_OK) {
+            c->err = "svgf_render_async: host_image cannot be page-locked"; return SVGF_ERR_INVALID;
+        }
         // this frame writes the buffer whose copy was queued two frames ago: that copy must have drained
         std::swap(c->denoised, c->denoised_alt);
         c->copy_slot ^= 1;
@@ -607,10 +659,12 @@ static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P
         int rc = order_after_copies(c);
         if (rc != SVGF_OK) return rc;
     }
+    { int rc = comm_check(c); if (rc != SVGF_OK) return rc; }
     cudaEvent_t *ev = prof_begin(c, P);
     c->seq++;
-    // before this frame overwrites planes that peers read in place, they must have finished the previous frame
-    if (c->seq > 1) CK(launch_wait(c, SVGF_STAGE_FRAME, c->seq - 1));
+    // before this frame overwrites planes that peers read in place (any rank: the reprojection may land in any strip), they
+    // must have finished the previous frame
+    if (c->seq > 1) CK(launch_wait(c, SVGF_STAGE_FRAME, c->seq - 1, -1));
     if (ev) CK(cudaEventRecord(ev[0], c->stream));      // after the wait: stage times measure this rank's own work
     RtParams rp;
     rp.W = c->W; rp.H = c->H; rp.row_begin = c->shard.row_begin; rp.row_end = c->shard.row_end;
@@ -619,16 +673,17 @@ static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P
     atrous_scales(P->sigman, P->sigmax, &rp.kn, &rp.kx);
     rp.cam = *cam;
     c->gbuf_nrm = c->cur_nrm;            // where this frame's normals/geomIds live (svgf_fetch("gbuffer"))
-    CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm]));
-    CK(launch_signal(c, SVGF_STAGE_RT));
+    const bool filter = P->denoise_enable && P->right_view_option == 0 && P->atrous_nlevel > 0 && P->spatial_enable;
+    bool gbuf_pushed = false;
+    CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm], (filter && c->halo_push && c->rows.world > 1) ? (2 << P->atrous_nlevel) : 0, &gbuf_pushed));
     if (ev) CK(cudaEventRecord(ev[1], c->stream));
     if (P->denoise_enable) {
-        int rc = denoise_soa(c, c->image, cam, P, ev);
+        int rc = denoise_soa(c, c->image, cam, P, ev, gbuf_pushed);
         if (rc != SVGF_OK) return rc;
     } else {
         CK(launch_copy_f3(c, c->denoised, c->image));        // pathtrace.cu:440
     }
-    CK(launch_signal(c, SVGF_STAGE_FRAME));
+    CK(launch_signal(c, SVGF_STAGE_FRAME, -1));
     unsigned char *pbo = pbo_dev ? static_cast<unsigned char *>(pbo_dev) : c->pbo_own;
     CK(launch_pack_pbo(c, pbo, c->image, c->denoised));
     if (ev) CK(cudaEventRecord(ev[10], c->stream));
@@ -640,8 +695,10 @@ static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P
         CK(cudaMemcpyAsync(host_image + off, c->denoised + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
         CK(cudaEventRecord(c->copy_done[c->copy_slot], c->copy_stream));
         c->copy_pending[c->copy_slot] = 1; c->copy_host[c->copy_slot] = host_image;
-    } else if (host_image) {   // pathtrace.cu:450 (scene->state.image): synchronous like the reference, but a pinned DMA
-        if (host_is_registered(c, host_image, c->px * 12)) {
+    } else if (host_image) {   // pathtrace.cu:450 (scene->state.image): synchronous like the reference
+        // page-locked memory (the caller's own, or svgf_register_host) takes the DMA directly; anything else goes through the
+        // context's staging buffer -- caller memory is never registered behind the caller's back here
+        if (host_is_pinned(host_image)) {
             CK(cudaMemcpyAsync(host_image + off, c->denoised + off, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
             if (ev) CK(cudaEventRecord(ev[11], c->stream));
             CK(cudaStreamSynchronize(c->stream));
@@ -674,7 +731,7 @@ extern "C" int svgf_wait_image(svgf_ctx *c, const float *host_image) {
             CK(cudaEventSynchronize(c->copy_done[i]));
             c->copy_pending[i] = 0;
         }
-    return SVGF_OK;
+    return comm_check(c);
 }
 
 extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_dev, const svgf_gbuffer_texel *gbuffer_dev,
@@ -682,7 +739,7 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     if (!c || !output_dev || !input_dev || !gbuffer_dev || !cam || !P) return SVGF_ERR_INVALID;
     if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_denoise: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
     if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS) { c->err = "svgf_denoise: atrous_nlevel out of range"; return SVGF_ERR_INVALID; }
-    if (c->shard.world > 1) { c->err = "svgf_denoise: the AoS entry point is single-GPU; sharded frames go through svgf_render"; return SVGF_ERR_INVALID; }
+    if (c->rows.world > 1 || c->shard.row_begin != 0 || c->shard.row_end != c->H) { c->err = "svgf_denoise: the AoS entry point is single-GPU; sharded frames go through svgf_render"; return SVGF_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
     { int rc = order_after_copies(c); if (rc != SVGF_OK) return rc; }
     cudaEvent_t *ev = prof_begin(c, P);
@@ -691,7 +748,7 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     atrous_scales(P->sigman, P->sigmax, &kn, &kx);
     c->gbuf_nrm = c->cur_nrm;
     CK(launch_aos_to_soa(c, gbuffer_dev, c->nrm[c->cur_nrm], c->pos, c->alb, kn, kx));
-    int rc = denoise_soa(c, input_dev, cam, P, ev);
+    int rc = denoise_soa(c, input_dev, cam, P, ev, false);
     if (rc != SVGF_OK) return rc;
     CK(cudaMemcpyAsync(output_dev, c->denoised, c->px * 12, cudaMemcpyDeviceToDevice, c->stream));
     if (ev) { CK(cudaEventRecord(ev[10], c->stream)); CK(cudaEventRecord(ev[11], c->stream)); }

@@ -13,6 +13,7 @@
 //     while neighbours read it (denoise.cu:111,153,161), which is a data race; the Jacobi form is what its result
 //     converges to when all reads win the race and is the only deterministic, shardable definition.
 #include "svgf_internal.h"
+#include "halo_sync.cuh"
 #include "atrous_pair_core.h"
 #include "atrous_tile_core.h"
 
@@ -153,8 +154,14 @@ struct AtrousT {
     int b_first;        // first lattice row index covered by the grid (row_begin / step)
     int ncg;            // column groups per class row: step / C
     int use_tma;
-    int probe;          // timing probes (SVGF_ATROUS_PROBE, never set in production): 1 = skip the tile load, 2 = skip the arithmetic
+#ifdef SVGF_ATROUS_PROBES
+    int probe;          // timing probes (make PROBES=1 + SVGF_ATROUS_PROBE; not compiled into the product): 1 = skip the tile load, 2 = skip the arithmetic
+#endif
     const float *kl;    // per-pixel luminance-weight scale from atrous_kl_kernel
+    // sharded frames: rows of this level's output that the neighbours tap at the NEXT level go into their planes as well, and
+    // the last block to finish raises this level's flag in their memory (halo_sync.cuh)
+    HaloOut ho;
+    float4 *cv_peer[SVGF_MAX_RANKS - 1]; float2 *lv_peer[SVGF_MAX_RANKS - 1];
     alignas(64) CUtensorMap tm_cv, tm_np, tm_zl, tm_lv;
 };
 
@@ -163,7 +170,15 @@ struct AtrousT {
 // it is coalesced instead of per lattice point inside the tiled kernel. 8 B read (L1-shared) + 4 B written per pixel.
 __global__ void __launch_bounds__(256)
 atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_constant__ RowOwner ro, float *__restrict__ kl,
-                 int W, int H, int row_begin, int row_end, int blur_variance, float sigma_c) {
+                 int W, int H, int row_begin, int row_end, int blur_variance, float sigma_c, const __grid_constant__ HaloIn wait) {
+    // Sharded frames: the rows beyond the strip were stored into this GPU's planes by the neighbours' producers. Only the
+    // first and the last block row read such rows here (+-1 row); they wait for the neighbours' flags -- for every neighbour in
+    // reach of the level, so that the tile kernel, which starts after this grid has drained, finds its whole apron in place.
+    // Interior blocks start at once; the waiting blocks are a few dozen, so they cannot keep a producer off the SMs.
+    if (wait.n > 0 && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) halo_wait(wait);
+        __syncthreads();
+    }
     // one thread = 4 consecutive pixels of a row: 3 rows x (left neighbour, 4 pixels, right neighbour)
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
@@ -247,9 +262,10 @@ __device__ __forceinline__ bool at_stage_tile(const AtrousT &t, float4 *s_cv, fl
     const bool remote = t.ro.world > 1 && yt0 <= yt1 && (yt0 < t.ro.start[t.me] || yt1 >= t.ro.start[t.me + 1]);
     const bool tma = t.use_tma && !remote;
 
-    if (t.probe == 1) {
-        // timing probe: arithmetic on whatever shared memory holds
-    } else if (tma) {
+#ifdef SVGF_ATROUS_PROBES
+    if (t.probe == 1) return tma;       // timing probe: arithmetic on whatever shared memory holds
+#endif
+    if (tma) {
         if (tid == 0) {
             init(&bar, AT_THREADS);
             cde::fence_proxy_async_shared_cta();
@@ -317,7 +333,8 @@ __device__ __forceinline__ bool at_stage_tile(const AtrousT &t, float4 *s_cv, fl
 // Normalise the sums of a 2 x TY patch and write them: {colour, variance} + {luminance, variance} for the next level, and on the
 // last level the final colour (x albedo) in the reference's vec3 layout + the variance plane.
 template <int AT_TY>
-__device__ __forceinline__ void at_write_outputs(const AtrousK &k, const AtAcc2 (&A)[AT_TY], int X0, int a0, int b0, int yc, int ap, int bq, int c) {
+__device__ __forceinline__ void at_write_outputs(const AtrousT &t, const AtAcc2 (&A)[AT_TY], int X0, int a0, int b0, int yc, int ap, int bq, int c) {
+    const AtrousK &k = t.k;
     const int W = k.W, step = k.step;
     // ---- outputs: all 8 results (incl. the fp64 luminance of the new colour, a long dependent chain) are computed as
     // straight-line code first, then stored under predicates, so the 8 chains overlap ----
@@ -360,7 +377,14 @@ __device__ __forceinline__ void at_write_outputs(const AtrousK &k, const AtAcc2 
                 d[0] = o[ca][cb].x; d[1] = o[ca][cb].y; d[2] = o[ca][cb].z;
                 k.var_out[p] = o[ca][cb].w;
             }
-            if (k.cv_out) { k.cv_out[p] = o[ca][cb]; k.lv_out[p] = make_float2(ol[ca][cb], o[ca][cb].w); }
+            if (k.cv_out) {
+                const float2 lvo = make_float2(ol[ca][cb], o[ca][cb].w);
+                k.cv_out[p] = o[ca][cb]; k.lv_out[p] = lvo;
+                for (unsigned m = halo_targets(t.ho.peers, p / W); m; m &= m - 1) {       // rows a neighbour taps at the next level
+                    const int i = __ffs(m) - 1;
+                    t.cv_peer[i][p] = o[ca][cb]; t.lv_peer[i][p] = lvo;
+                }
+            }
         }
 }
 
@@ -399,16 +423,18 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
         }
     if (!tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (!live) return;
+#ifdef SVGF_ATROUS_PROBES
     if (t.probe == 2) {     // timing probe: tile load + kl only; one store keeps the loads alive
         if (c_kl[0][0] == 123.456f) k.var_out[0] = s_cv[tid].x;
         return;
     }
-
-    AtAcc2 A[AT_TY];
-    at_thread_compute<SH>(c, ap, bq, s_cv, s_np, s_zl, s_lv, c_kl, A);
-
-    at_write_outputs<AT_TY>(k, A, X0, a0, b0, yc, ap, bq, c);
+#endif
+    if (live) {
+        AtAcc2 A[AT_TY];
+        at_thread_compute<SH>(c, ap, bq, s_cv, s_np, s_zl, s_lv, c_kl, A);
+        at_write_outputs<AT_TY>(t, A, X0, a0, b0, yc, ap, bq, c);
+    }
+    halo_block_done(t.ho);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -459,12 +485,13 @@ atrous_pair_kernel(const __grid_constant__ AtrousT t) {
     // ---- phase 1: g = |dn'| + |dp'| - log2 h for the 12 forward offsets of every staged point that can pair with a centre ----
     for (int n = tid; n < SH::ITEMS; n += SH::THREADS) pair_phase1_item<SH>(n, s_np, s_zl, s_g);
     __syncthreads();
-    if (!live) return;
-
-    // ---- phase 2: one ex2 per (centre, tap) ----
-    PairAcc A[PR];
-    pair_phase2_thread<SH>(c, ap, bq, s_cv, s_lv, s_g, c_kl, A);
-    at_write_outputs<PR>(k, A, X0, a0, b0, yc, ap, bq, c);
+    if (live) {
+        // ---- phase 2: one ex2 per (centre, tap) ----
+        PairAcc A[PR];
+        pair_phase2_thread<SH>(c, ap, bq, s_cv, s_lv, s_g, c_kl, A);
+        at_write_outputs<PR>(t, A, X0, a0, b0, yc, ap, bq, c);
+    }
+    halo_block_done(t.ho);
 }
 
 }  // namespace
@@ -517,7 +544,7 @@ static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-enum { TM_PLANES = 8, TM_LEVELS = SVGF_MAX_LEVELS + 1, TM_SHAPES = AT_NSHAPES };
+enum { TM_PLANES = 2 * SVGF_NCV + 2, TM_LEVELS = SVGF_MAX_LEVELS + 1, TM_SHAPES = AT_NSHAPES };
 static inline CUtensorMap *tmap_at(svgf_ctx *c, int plane, int level, int shape) {
     return static_cast<CUtensorMap *>(c->tmaps) + ((plane * TM_LEVELS + level) * TM_SHAPES + shape);
 }
@@ -541,8 +568,9 @@ int atrous_build_tensor_maps(svgf_ctx *c) {
         const int q = atoi(v);
         promo = q == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : q == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : q == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo;
     }
-    void *planes[TM_PLANES] = {c->cv[0], c->cv[1], c->cv[2], c->lv[0], c->lv[1], c->lv[2], c->gnp, c->gzl};
-    const int fpp[TM_PLANES] = {4, 4, 4, 2, 2, 2, 4, 2};
+    void *planes[TM_PLANES]; int fpp[TM_PLANES];
+    for (int i = 0; i < SVGF_NCV; i++) { planes[i] = c->cv[i]; fpp[i] = 4; planes[SVGF_NCV + i] = c->lv[i]; fpp[SVGF_NCV + i] = 2; }
+    planes[2 * SVGF_NCV] = c->gnp; fpp[2 * SVGF_NCV] = 4; planes[2 * SVGF_NCV + 1] = c->gzl; fpp[2 * SVGF_NCV + 1] = 2;
     for (int pl = 0; pl < TM_PLANES; pl++)
         for (int level = 1; level <= SVGF_MAX_LEVELS; level++)
             for (int shp = 0; shp < TM_SHAPES; shp++) {
@@ -581,10 +609,9 @@ static cudaError_t launch_atrous_pair(svgf_ctx *c, AtrousT &t, const AtrousArgs 
     const bool tall = lat_rows >= 100 || c->atrous_shape == 2;
     const int shape = (tall && c->atrous_shape != 9) ? 2 : 9;
     t.use_tma = c->tma_ok && a.src_slot >= 0;
-    t.probe = 0;
     if (t.use_tma) {
-        t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, 3 + a.src_slot, a.level, shape);
-        t.tm_np = *tmap_at(c, 6, a.level, shape); t.tm_zl = *tmap_at(c, 7, a.level, shape);
+        t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, SVGF_NCV + a.src_slot, a.level, shape);
+        t.tm_np = *tmap_at(c, 2 * SVGF_NCV, a.level, shape); t.tm_zl = *tmap_at(c, 2 * SVGF_NCV + 1, a.level, shape);
     } else {
         memset(&t.tm_cv, 0, sizeof(CUtensorMap)); memset(&t.tm_lv, 0, sizeof(CUtensorMap));
         memset(&t.tm_np, 0, sizeof(CUtensorMap)); memset(&t.tm_zl, 0, sizeof(CUtensorMap));
@@ -626,26 +653,32 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     k.is_last = a.is_last; k.blur_variance = a.blur_variance; k.addcolor = a.addcolor;
     k.sigma_c = a.sigma_c;
     atrous_scales(a.sigma_n, a.sigma_x, &k.kn, &k.kx);
-    if (c->atrous_variant == 1 && c->shard.world == 1) {
+    if (c->atrous_variant == 1 && c->rows.world == 1) {
         dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
         atrous_direct_kernel<<<g, b, 0, c->stream>>>(k);
         return cudaGetLastError();
     }
     AtrousT t;
     t.k = k; t.kl = c->kl; t.ro = c->rows; t.me = c->shard.rank;
+    t.ho = a.ho;
+    for (int i = 0; i < SVGF_MAX_RANKS - 1; i++) {
+        const bool on = i < a.ho.peers.n && a.cv_out && a.dst_slot >= 0;
+        t.cv_peer[i] = on ? c->p_cv[a.dst_slot].p[a.ho.peers.rank[i]] : nullptr;
+        t.lv_peer[i] = on ? c->p_lv[a.dst_slot].p[a.ho.peers.rank[i]] : nullptr;
+    }
     // push mode: the neighbours' rows this level taps were copied into this rank's planes by their producers (api.cu)
-    const bool local_only = c->halo_push || c->shard.world <= 1;
+    const bool local_only = c->halo_push || c->rows.world <= 1;
     if (local_only) { t.ro.world = 1; t.me = 0; }
     PeerPtr<const float2> pv;
     for (int r = 0; r < SVGF_MAX_RANKS; r++) {
-        const bool peer = !local_only && r < c->shard.world && a.src_slot >= 0;
+        const bool peer = !local_only && r < c->rows.world && a.src_slot >= 0;
         t.p_cv.p[r] = peer ? c->p_cv[a.src_slot].p[r] : a.cv_in; t.p_lv.p[r] = peer ? c->p_lv[a.src_slot].p[r] : a.lv_in;
         t.p_gnp.p[r] = peer ? c->p_gnp.p[r] : a.gnp; t.p_gzl.p[r] = peer ? c->p_gzl.p[r] : a.gzl;
         pv.p[r] = t.p_lv.p[r];
     }
     {
         dim3 b(32, 8), g(((c->W + 3) / 4 + 31) / 32, (rows + 7) / 8);
-        atrous_kl_kernel<<<g, b, 0, c->stream>>>(pv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c);
+        atrous_kl_kernel<<<g, b, 0, c->stream>>>(pv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c, a.wait);
     }
     const int step = k.step;
     t.b_first = k.row_begin / step;
@@ -656,10 +689,12 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     const int shape = at_pick_shape(c, a.level, lat_w, lat_rows);
     const AtShapeInfo &si = g_at_shapes[shape];
     t.use_tma = c->tma_ok && a.src_slot >= 0 && c->atrous_variant != 3;
+#ifdef SVGF_ATROUS_PROBES
     t.probe = c->atrous_probe;
+#endif
     if (t.use_tma) {
-        t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, 3 + a.src_slot, a.level, shape);
-        t.tm_np = *tmap_at(c, 6, a.level, shape); t.tm_zl = *tmap_at(c, 7, a.level, shape);
+        t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, SVGF_NCV + a.src_slot, a.level, shape);
+        t.tm_np = *tmap_at(c, 2 * SVGF_NCV, a.level, shape); t.tm_zl = *tmap_at(c, 2 * SVGF_NCV + 1, a.level, shape);
     } else {
         memset(&t.tm_cv, 0, sizeof(CUtensorMap)); memset(&t.tm_lv, 0, sizeof(CUtensorMap));
         memset(&t.tm_np, 0, sizeof(CUtensorMap)); memset(&t.tm_zl, 0, sizeof(CUtensorMap));

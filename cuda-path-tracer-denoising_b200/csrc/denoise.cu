@@ -9,8 +9,10 @@
 //   aos<->soa           layout conversion for the reference-layout entry point svgf_denoise() and svgf_fetch
 // The a-trous filter itself lives in atrous.cu.
 #include "svgf_internal.h"
+#include "halo_sync.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace {
 
@@ -36,26 +38,29 @@ __device__ __forceinline__ bool reprj_valid(int W, int H, float px, float py, co
 
 struct Mat4 { float m[16]; };
 
-// 108 algorithmic bytes per pixel: reads image 12 + normal/geomId 16 + position 12 + own history
-// length 4 + (reprojected, cache-shared) prev normal/geomId 16, colour history 12(16), moments 8, history length 4;
-// writes {colour,variance} 16 + moments 8 + history length 4.
-__global__ void __launch_bounds__(256)
-temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
-                const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
-                const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,
-                const __grid_constant__ PeerPtr<int> hlen_tab, const __grid_constant__ RowOwner ro, int me,
-                float4 *__restrict__ acc_cv, float2 *__restrict__ acc_lv, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, Mat4 vm,
-                float color_alpha_min, float moment_alpha_min, float clip_rx, float clip_ry, int hist_cap) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= row_end) return;
-    const int p = x + y * W;
+struct TemporalOut { float4 cv; float2 lv, mom; int hlen; };
+
+// One pixel of BackProjection (denoise.cu:185-317) fused with the variance estimate. 108 algorithmic bytes per pixel
+// (SURVEY.md 8(d)): reads image 12 + normal/geomId 16 + position 12 + own history length 4 + (reprojected, cache-shared)
+// prev normal/geomId 16, colour history 12(16), moments 8, history length 4; writes {colour,variance} 16 + moments 8 +
+// history length 4.
+// Latency: the reference's control flow is three dependent round trips to memory (own history length -> the four previous
+// normals -> the four history taps). Here the first-round loads (history length, sample, normal, position) are issued
+// together, and the four taps' history records are requested TOGETHER with their normals (the addresses are known as soon as
+// the pixel is projected; a tap whose normal later fails the test costs a few wasted sectors), so a pixel waits for memory
+// twice, not three times. The arithmetic, its order and therefore every bit of the result are the reference's.
+__device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const float *__restrict__ image, const float4 *__restrict__ nrm_cur,
+                                                      const PeerPtr<float4> &nrm_prev, const float4 *__restrict__ pos, const PeerPtr<float4> &hist_cv,
+                                                      const PeerPtr<float2> &mom_hist, const PeerPtr<int> &hlen_tab, const RowOwner &ro, int me,
+                                                      const Mat4 &vm, float color_alpha_min, float moment_alpha_min, float clip_rx, float clip_ry,
+                                                      int hist_cap) {
     const int N = hlen_tab.p[me][p];     // own pixel (denoise.cu:194)
     const float sr = image[3 * (size_t)p], sg = image[3 * (size_t)p + 1], sb = image[3 * (size_t)p + 2];
-    const float luminance = 0.2126 * sr + 0.7152 * sg + 0.0722 * sb;    // double, as denoise.cu:196
     const float4 ncur = nrm_cur[p];
+    const float4 pp = pos[p];
+    const float luminance = 0.2126 * sr + 0.7152 * sg + 0.0722 * sb;    // double, as denoise.cu:196
+    TemporalOut o;
     if (N > 0 && __float_as_int(ncur.w) != -1) {
-        const float4 pp = pos[p];
         // prev_viewmat * vec4(position, 1): (m0 v0 + m1 v1) + (m2 v2 + m3 v3), glm type_mat4x4.inl:617-628
         const float vx = (vm.m[0] * pp.x + vm.m[4] * pp.y) + (vm.m[8] * pp.z + vm.m[12] * 1.0f);
         const float vy = (vm.m[1] * pp.x + vm.m[5] * pp.y) + (vm.m[9] * pp.z + vm.m[13] * 1.0f);
@@ -72,12 +77,29 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
         // glm::ivec2(floorx, floory) + offset: saturating cvt, wrapping integer add (as the reference's SASS)
         const int ifx = __float2int_rz(floorx), ify = __float2int_rz(floory);
         bool v[4]; int qi[4];
+        float4 tn[4], th[4]; float2 tm[4]; int tl[4];
+        bool inr[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {       // addresses of the four taps; all their loads are in flight before the first is used
+            const int lx = (int)((unsigned)ifx + (unsigned)(s & 1)), ly = (int)((unsigned)ify + (unsigned)(s >> 1));
+            const float fx = (float)lx, fy = (float)ly;
+            // isReprjValid's bounds test and FLOAT index (denoise.cu:172-177); NaN coordinates pass the reference's test and
+            // index garbage (undefined) -- rejected here
+            inr[s] = (fx >= 0.f) && (fx < (float)W) && (fy >= 0.f) && (fy < (float)H);
+            qi[s] = lx + ly * W;
+            tn[s] = make_float4(0.f, 0.f, 0.f, 0.f); th[s] = tn[s]; tm[s] = make_float2(0.f, 0.f); tl[s] = 0;
+            if (inr[s]) {
+                const int qn = (int)(fx + fy * (float)W);
+                tn[s] = __ldg(&nrm_prev.p[owner_of(ro, qn / W)][qn]);
+                // in range => 0 <= lx < W and 0 <= ly < H, so the integer index of the history taps is in range as well
+                const int o2 = owner_of(ro, ly);
+                th[s] = __ldg(&hist_cv.p[o2][qi[s]]); tm[s] = __ldg(&mom_hist.p[o2][qi[s]]); tl[s] = __ldg(&hlen_tab.p[o2][qi[s]]);
+            }
+        }
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            const int lx = (int)((unsigned)ifx + (unsigned)(s & 1)), ly = (int)((unsigned)ify + (unsigned)(s >> 1));
-            qi[s] = 0;
-            v[s] = reprj_valid(W, H, (float)lx, (float)ly, ncur, nrm_prev, ro, qi[s]);
-            qi[s] = lx + ly * W;
+            const int gprev = __float_as_int(tn[s].w), gcur = __float_as_int(ncur.w);
+            v[s] = inr[s] && !(gprev == -1 || gprev != gcur) && !(dist3(tn[s].x, tn[s].y, tn[s].z, ncur.x, ncur.y, ncur.z) > 1e-1f);
             valid = valid && v[s];
         }
         float pr = 0.f, pg = 0.f, pb = 0.f, pm1 = 0.f, pm2 = 0.f, phl = 0.f;
@@ -87,11 +109,9 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 if (v[s]) {
-                    const int o = owner_of(ro, qi[s] / W);
-                    const float4 hc = __ldg(&hist_cv.p[o][qi[s]]); const float2 hm = __ldg(&mom_hist.p[o][qi[s]]);
-                    pr += w[s] * hc.x; pg += w[s] * hc.y; pb += w[s] * hc.z;
-                    pm1 += w[s] * hm.x; pm2 += w[s] * hm.y;
-                    phl += w[s] * (float)__ldg(&hlen_tab.p[o][qi[s]]);
+                    pr += w[s] * th[s].x; pg += w[s] * th[s].y; pb += w[s] * th[s].z;
+                    pm1 += w[s] * tm[s].x; pm2 += w[s] * tm[s].y;
+                    phl += w[s] * (float)tl[s];
                     sumw += w[s];
                 }
             }
@@ -125,23 +145,52 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
             const float color_alpha = fmaxf(1.0f / (float)(N + 1), color_alpha_min);
             const float moment_alpha = fmaxf(1.0f / (float)(N + 1), moment_alpha_min);
             const int hl = (int)phl + 1;            // unbounded in the reference (denoise.cu:290-294); optional cap (N4)
-            hlen_out[p] = hist_cap > 0 ? min(hl, hist_cap) : hl;
+            o.hlen = hist_cap > 0 ? min(hl, hist_cap) : hl;
             const float first = moment_alpha * pm1 + (1.0f - moment_alpha) * luminance;
             const float second = moment_alpha * pm2 + (1.0f - moment_alpha) * luminance * luminance;
-            mom_acc[p] = make_float2(first, second);
+            o.mom = make_float2(first, second);
             const float variance = second - first * first;
             const float ar = sr * color_alpha + pr * (1.0f - color_alpha), ag = sg * color_alpha + pg * (1.0f - color_alpha),
                         ab = sb * color_alpha + pb * (1.0f - color_alpha);
-            acc_cv[p] = make_float4(ar, ag, ab, variance > 0.0f ? variance : 0.0f);
+            o.cv = make_float4(ar, ag, ab, variance > 0.0f ? variance : 0.0f);
             // luminance as the a-trous taps will read it (denoise.cu:121,138), and the variance once more for the 3x3 blur
-            acc_lv[p] = make_float2((float)(0.2126 * ar + 0.7152 * ag + 0.0722 * ab), variance > 0.0f ? variance : 0.0f);
-            return;
+            o.lv = make_float2((float)(0.2126 * ar + 0.7152 * ag + 0.0722 * ab), variance > 0.0f ? variance : 0.0f);
+            return o;
         }
     }
-    hlen_out[p] = 1;
-    mom_acc[p] = make_float2(luminance, luminance * luminance);
-    acc_cv[p] = make_float4(sr, sg, sb, 100.0f);
-    acc_lv[p] = make_float2(luminance, 100.0f);
+    o.hlen = 1;
+    o.mom = make_float2(luminance, luminance * luminance);
+    o.cv = make_float4(sr, sg, sb, 100.0f);
+    o.lv = make_float2(luminance, 100.0f);
+    return o;
+}
+
+struct TemporalPush {           // sharded frames: the neighbours' copies of the accumulated planes (level 1 taps +-4 rows)
+    HaloOut ho;
+    float4 *cv[SVGF_MAX_RANKS - 1]; float2 *lv[SVGF_MAX_RANKS - 1];
+};
+
+__global__ void __launch_bounds__(256, 4)
+temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
+                const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
+                const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,
+                const __grid_constant__ PeerPtr<int> hlen_tab, const __grid_constant__ RowOwner ro, int me,
+                float4 *__restrict__ acc_cv, float2 *__restrict__ acc_lv, float2 *__restrict__ mom_acc, int *__restrict__ hlen_out, const __grid_constant__ Mat4 vm,
+                float color_alpha_min, float moment_alpha_min, float clip_rx, float clip_ry, int hist_cap,
+                const __grid_constant__ TemporalPush push) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < W && y < row_end) {
+        const int p = x + y * W;
+        const TemporalOut o = temporal_pixel(W, H, p, image, nrm_cur, nrm_prev, pos, hist_cv, mom_hist, hlen_tab, ro, me, vm,
+                                             color_alpha_min, moment_alpha_min, clip_rx, clip_ry, hist_cap);
+        hlen_out[p] = o.hlen; mom_acc[p] = o.mom; acc_cv[p] = o.cv; acc_lv[p] = o.lv;
+        for (unsigned m = halo_targets(push.ho.peers, y); m; m &= m - 1) {
+            const int i = __ffs(m) - 1;
+            push.cv[i][p] = o.cv; push.lv[i][p] = o.lv;
+        }
+    }
+    halo_block_done(push.ho);
 }
 
 __global__ void __launch_bounds__(256)
@@ -229,22 +278,24 @@ copy_f3_kernel(size_t begin, size_t end, float *__restrict__ dst, const float *_
     if (i < end) dst[i] = src[i];
 }
 
-// ---- cross-rank ordering: sequence flags pushed into every peer's memory, polled locally ----
-__global__ void signal_kernel(PeerPtr<unsigned> flags, int world, int me, int stage, unsigned seq) {
+// ---- cross-rank ordering: sequence flags pushed into the peers' memory, polled locally (halo_sync.cuh). These two kernels
+// are the stand-alone forms, used where the producer/consumer kernel of a stage has no fused signal/wait (frame boundary, the
+// rarely used paths); the hot stages raise their flags from the producer's last block and poll in the consumer's edge blocks.
+struct FlagList { int n; unsigned *flag[SVGF_MAX_RANKS]; };
+__global__ void signal_kernel(const __grid_constant__ FlagList l, unsigned seq) {
     const int j = threadIdx.x;
-    if (j >= world) return;
+    if (j >= l.n) return;
     __threadfence_system();
-    volatile unsigned *f = flags.p[j] + me * SVGF_NUM_STAGES + stage;
-    *f = seq;
+    *reinterpret_cast<volatile unsigned *>(l.flag[j]) = seq;
 }
-__global__ void wait_kernel(unsigned *flags, int world, int stage, unsigned seq) {
+__global__ void wait_kernel(const __grid_constant__ FlagList l, unsigned seq, unsigned *err) {
     const int j = threadIdx.x;
-    if (j >= world) return;
-    volatile unsigned *f = flags + j * SVGF_NUM_STAGES + stage;
+    if (j >= l.n) return;
+    const volatile unsigned *f = l.flag[j];
     const long long t0 = clock64();
     while ((int)(*f - seq) < 0) {
         if (clock64() - t0 > 4000000000LL) {        // ~2 s: a peer died; record it instead of hanging the GPU
-            flags[SVGF_MAX_RANKS * SVGF_NUM_STAGES] = 1u;
+            *reinterpret_cast<volatile unsigned *>(err) = 1u;
             break;
         }
         __nanosleep(200);
@@ -273,17 +324,54 @@ inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (
 
 }  // namespace
 
+// Ranks whose strips lie within `reach` rows of this rank's strip, with the rows of MY strip each of them taps.
+HaloPeers halo_peers(const svgf_ctx *c, int reach) {
+    HaloPeers h; h.n = 0;
+    const int b = c->shard.row_begin, e = c->shard.row_end;
+    if (c->rows.world <= 1 || reach <= 0 || b >= e) return h;
+    for (int r = 0; r < c->rows.world; r++) {
+        if (r == c->shard.rank || c->rows.start[r] >= c->rows.start[r + 1]) continue;
+        const int lo = std::max(b, c->rows.start[r] - reach), hi = std::min(e, c->rows.start[r + 1] + reach);
+        if (lo >= hi) continue;
+        h.rank[h.n] = r; h.lo[h.n] = lo; h.hi[h.n] = hi; h.n++;
+    }
+    return h;
+}
+
+// Producer side of `stage` for the peers in `reach`: where their copies of my flag live, the block counter, this frame's seq.
+HaloOut halo_out(svgf_ctx *c, int stage, int reach, bool fused_signal) {
+    HaloOut o; memset(&o, 0, sizeof(o));
+    o.peers = halo_peers(c, reach);
+    for (int i = 0; i < o.peers.n; i++) o.flag[i] = c->p_flags.p[o.peers.rank[i]] + c->shard.rank * SVGF_NUM_STAGES + stage;
+    o.counter = c->done_count + stage; o.seq = c->seq; o.signal = fused_signal ? 1 : 0;
+    return o;
+}
+
+// Consumer side: my local copies of the flags of `stage` of the peers in `reach`.
+HaloIn halo_in(svgf_ctx *c, int stage, int reach, unsigned seq) {
+    HaloIn w; memset(&w, 0, sizeof(w));
+    const HaloPeers p = halo_peers(c, reach);
+    w.n = p.n;
+    for (int i = 0; i < p.n; i++) w.flag[i] = c->flags + p.rank[i] * SVGF_NUM_STAGES + stage;
+    w.seq = seq; w.err = c->comm_err_dev;
+    return w;
+}
+
 cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const PeerPtr<float4> &nrm_prev,
                             const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
                             const PeerPtr<int> &hlen_in, float4 *acc_cv, float2 *acc_lv, float2 *mom_acc, int *hlen_out,
-                            const float *prev_viewmat, float color_alpha, float moment_alpha, float clip_rx, float clip_ry) {
+                            const float *prev_viewmat, float color_alpha, float moment_alpha, float clip_rx, float clip_ry,
+                            const HaloOut &ho, const PeerPtr<float4> &acc_cv_peers, const PeerPtr<float2> &acc_lv_peers) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
     Mat4 vm; for (int i = 0; i < 16; i++) vm.m[i] = prev_viewmat[i];
+    TemporalPush push; memset(&push, 0, sizeof(push));
+    push.ho = ho;
+    for (int i = 0; i < ho.peers.n; i++) { push.cv[i] = acc_cv_peers.p[ho.peers.rank[i]]; push.lv[i] = acc_lv_peers.p[ho.peers.rank[i]]; }
     dim3 b(32, 8);
     temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
                                                                  nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lv, mom_acc,
-                                                                 hlen_out, vm, color_alpha, moment_alpha, clip_rx, clip_ry, c->opt_history_cap);
+                                                                 hlen_out, vm, color_alpha, moment_alpha, clip_rx, clip_ry, c->opt_history_cap, push);
     return cudaGetLastError();
 }
 
@@ -304,19 +392,18 @@ cudaError_t launch_pack_pbo(svgf_ctx *c, unsigned char *pbo, const float *left, 
     return cudaGetLastError();
 }
 
-// Copies this rank's rows that lie within `halo_rows` of another rank's strip into that rank's copy of the plane(s).
+// Copies this rank's rows that lie within `halo_rows` of another rank's strip into that rank's copy of the plane(s): the
+// stand-alone form of the dual stores, for producers that do not push by themselves.
 cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes) {
-    if (c->shard.world <= 1 || halo_rows <= 0) return cudaSuccess;
+    const HaloPeers hp = halo_peers(c, halo_rows);
+    if (hp.n == 0) return cudaSuccess;
     PushArgs a; int nseg = 0; unsigned long long longest = 0; bool v16 = true;
-    const int b = c->shard.row_begin, e = c->shard.row_end;
-    for (int r = 0; r < c->shard.world; r++) {
-        if (r == c->shard.rank) continue;
-        const int lo = std::max(b, c->rows.start[r] - halo_rows), hi = std::min(e, c->rows.start[r + 1] + halo_rows);
-        if (lo >= hi || c->rows.start[r] >= c->rows.start[r + 1]) continue;       // nothing of mine in reach / empty strip
+    for (int i = 0; i < hp.n; i++) {
+        const int r = hp.rank[i];
         for (int p = 0; p < nplanes; p++) {
             if (!planes[p].peer[r] || planes[p].peer[r] == planes[p].local) continue;     // not connected (yet): own plane
             if (nseg == SVGF_PUSH_MAXSEG) return cudaErrorInvalidValue;
-            const size_t off = (size_t)lo * c->W * planes[p].esz, bytes = (size_t)(hi - lo) * c->W * planes[p].esz;
+            const size_t off = (size_t)hp.lo[i] * c->W * planes[p].esz, bytes = (size_t)(hp.hi[i] - hp.lo[i]) * c->W * planes[p].esz;
             a.seg[nseg].src = static_cast<const char *>(planes[p].local) + off;
             a.seg[nseg].dst = static_cast<char *>(planes[p].peer[r]) + off;
             a.seg[nseg].bytes = bytes;
@@ -334,14 +421,23 @@ cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes
     return cudaGetLastError();
 }
 
-cudaError_t launch_signal(svgf_ctx *c, int stage) {
-    if (c->shard.world <= 1) return cudaSuccess;
-    signal_kernel<<<1, 32, 0, c->stream>>>(c->p_flags, c->shard.world, c->shard.rank, stage, c->seq);
+// reach < 0: every connected rank (frame boundary: the temporal pass reads history in place from any strip)
+cudaError_t launch_signal(svgf_ctx *c, int stage, int reach) {
+    if (c->rows.world <= 1) return cudaSuccess;
+    FlagList l; l.n = 0;
+    if (reach < 0) { for (int r = 0; r < c->rows.world; r++) l.flag[l.n++] = c->p_flags.p[r] + c->shard.rank * SVGF_NUM_STAGES + stage; }
+    else { const HaloOut o = halo_out(c, stage, reach, false); for (int i = 0; i < o.peers.n; i++) l.flag[l.n++] = o.flag[i]; }
+    if (l.n == 0) return cudaSuccess;
+    signal_kernel<<<1, 32, 0, c->stream>>>(l, c->seq);
     return cudaGetLastError();
 }
-cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq) {
-    if (c->shard.world <= 1) return cudaSuccess;
-    wait_kernel<<<1, 32, 0, c->stream>>>(c->flags, c->shard.world, stage, seq);
+cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq, int reach) {
+    if (c->rows.world <= 1) return cudaSuccess;
+    FlagList l; l.n = 0;
+    if (reach < 0) { for (int r = 0; r < c->rows.world; r++) l.flag[l.n++] = c->flags + r * SVGF_NUM_STAGES + stage; }
+    else { const HaloIn w = halo_in(c, stage, reach, seq); for (int i = 0; i < w.n; i++) l.flag[l.n++] = const_cast<unsigned *>(w.flag[i]); }
+    if (l.n == 0) return cudaSuccess;
+    wait_kernel<<<1, 32, 0, c->stream>>>(l, seq, c->comm_err_dev);
     return cudaGetLastError();
 }
 

@@ -15,9 +15,11 @@
 //   * the G-buffer is written as float4 SoA planes, the persistent per-pixel intersection record is reduced to
 //     the 24 bytes that can be observed (stale normal/material/uv on a primary miss, pathtrace.cu:316-322).
 #include "svgf_internal.h"
+#include "halo_sync.cuh"
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -452,6 +454,14 @@ __device__ __noinline__ F3 hit_point(F3 origin, F3 direction, float t) { return 
 constexpr int RT_BX = 8, RT_BY = 16;
 enum { Q_PATH = 0, Q_SHADOW = 1 };
 
+// Sharded frames: the a-trous view of the G-buffer is needed up to 2 * 2^levels rows beyond a strip. The rows of MY strip
+// within that reach of a neighbour's go into the neighbour's planes as they are produced (dual stores over NVLink), so no
+// copy kernel runs between the path tracer and the temporal pass.
+struct RtPush {
+    HaloPeers peers;
+    float4 *gnp[SVGF_MAX_RANKS - 1]; float2 *gzl[SVGF_MAX_RANKS - 1];
+};
+
 template <int MINB>
 __global__ void __launch_bounds__(RT_BX *RT_BY, MINB)
 rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf_material *__restrict__ g_materials,
@@ -459,7 +469,7 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
           const float4 *__restrict__ tri_cold, const TexD *__restrict__ textures,
           float4 *__restrict__ nrm_out, float4 *__restrict__ pos_out, float4 *__restrict__ alb_out,
           float *__restrict__ image, float4 *__restrict__ stale_nm, float2 *__restrict__ stale_uv,
-          float4 *__restrict__ gnp_out, float2 *__restrict__ gzl_out) {
+          float4 *__restrict__ gnp_out, float2 *__restrict__ gzl_out, const __grid_constant__ RtPush push) {
     extern __shared__ __align__(16) unsigned char smem[];
     GeomD *s_geoms = reinterpret_cast<GeomD *>(smem);
     svgf_material *s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomD) * n_geoms);
@@ -527,8 +537,16 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
                 nrm_out[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.geomId));
                 pos_out[idx] = make_float4(p.x, p.y, p.z, 0.f);
                 alb_out[idx] = make_float4(a.x, a.y, a.z, 0.f);
-                gnp_out[idx] = make_float4(is.n.x * P.kn, p.x * P.kx, is.n.y * P.kn, p.y * P.kx);
-                gzl_out[idx] = make_float2(is.n.z * P.kn, p.z * P.kx);
+                const float4 gnp = make_float4(is.n.x * P.kn, p.x * P.kx, is.n.y * P.kn, p.y * P.kx);
+                const float2 gzl = make_float2(is.n.z * P.kn, p.z * P.kx);
+                gnp_out[idx] = gnp; gzl_out[idx] = gzl;
+                if (push.peers.n > 0) {
+                    unsigned m = halo_targets(push.peers, y);
+                    if (m) {
+                        for (; m; m &= m - 1) { const int i = __ffs(m) - 1; push.gnp[i][idx] = gnp; push.gzl[i][idx] = gzl; }
+                        __threadfence_system();     // in the neighbours' memory before any later flag of this rank
+                    }
+                }
             }
             depth++;
             // ---- top of the reference's bounce loop for `depth` (pathtrace.cu:325-356) ----
@@ -986,7 +1004,10 @@ static cudaError_t launch_pathtrace_wavefront(svgf_ctx *c, const RtParams &p, fl
     return cudaGetLastError();
 }
 
-cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
+// gbuf_reach > 0 (sharded frames, push mode): rows of the a-trous G-buffer view within that many rows of a neighbour's strip
+// also go into the neighbour's planes. The state-machine kernel stores them itself; *pushed says whether it did.
+cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, int gbuf_reach, bool *pushed) {
+    if (pushed) *pushed = false;
     if (c->rt_variant == 1) return launch_pathtrace_wavefront(c, p, nrm_out);
     const DeviceScene &s = c->scene;
     if (c->rt_variant == 2) {       // persistent state machine with work refill (A/B; slower: see the kernel's comment)
@@ -1015,6 +1036,12 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
     const int rows = p.row_end - p.row_begin;
     if (rows <= 0) return cudaSuccess;
     dim3 block(RT_BX, RT_BY), grid((p.W + RT_BX - 1) / RT_BX, (rows + RT_BY - 1) / RT_BY);
+    RtPush push; memset(&push, 0, sizeof(push));
+    if (gbuf_reach > 0) {
+        push.peers = halo_peers(c, gbuf_reach);
+        for (int i = 0; i < push.peers.n; i++) { push.gnp[i] = c->p_gnp.p[push.peers.rank[i]]; push.gzl[i] = c->p_gzl.p[push.peers.rank[i]]; }
+        if (pushed) *pushed = true;
+    }
 #define RT_LAUNCH(MINB)                                                                                                          \
     do {                                                                                                                         \
         if (smem > 48 * 1024) {                                                                                                  \
@@ -1023,7 +1050,7 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out) {
         }                                                                                                                        \
         rt_kernel<MINB><<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes,   \
                                                           s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, c->alb, c->image,  \
-                                                          c->stale_nm, c->stale_uv, c->gnp, c->gzl);                             \
+                                                          c->stale_nm, c->stale_uv, c->gnp, c->gzl, push);                       \
     } while (0)
     // Occupancy beats registers here: the kernel waits on dependent fp32 chains and BVH loads, so 8 blocks/SM (64 registers,
     // 84 B of spills) run 15-30 % faster than 4 blocks/SM (110 registers, none); 10 and 12 were slower again (measured on

@@ -66,8 +66,34 @@ __host__ __device__ inline int owner_of(const RowOwner &ro, int y) {
     return r;
 }
 enum { SVGF_STAGE_RT = 0, SVGF_STAGE_TEMPORAL = 1, SVGF_STAGE_LEVEL0 = 1 /* + level */, SVGF_STAGE_FRAME = 9, SVGF_NUM_STAGES = 10 };
-enum { SVGF_IPC_NBUF = 15 };    // cv[3] lv[3] nrm[2] mom[2] hlen[2] gnp gzl flags
-enum { SVGF_PAD_ROWS = 130 };   // rows of zeroed padding behind the planes the TMA tile loads address (lattice dims round up)
+enum { SVGF_NCV = 4 };          // colour/variance buffers in rotation: accumulated, a-trous ping/pong, history of the PREVIOUS frame
+                                // (never written while the frame that reads it is in flight, so only neighbours need to be waited for)
+enum { SVGF_IPC_NBUF = 2 * SVGF_NCV + 9 };    // cv[4] lv[4] nrm[2] mom[2] hlen[2] gnp gzl flags
+enum { SVGF_PAD_ROWS = 130, SVGF_PAD_PX = 2 << SVGF_MAX_LEVELS };   // zeroed padding behind the planes the TMA tile loads address: lattice
+                                // extents round up to ceil(H/s)*s rows and ceil(W/2s)*2s columns (s <= 128), i.e. < (H + 128) * W + 256 pixels
+
+// Sharded frames, push mode: the ranks whose strips lie within `reach` rows of mine. rows [lo[i], hi[i]) of MY strip are tapped
+// by rank[i] at the next stage (its producer stores them into that rank's copy of the plane as well), and the same ranks are the
+// ones whose rows I tap (the reach is symmetric), i.e. whose stage flag I have to see before reading my halo rows.
+struct HaloPeers {
+    int n;
+    int rank[SVGF_MAX_RANKS - 1], lo[SVGF_MAX_RANKS - 1], hi[SVGF_MAX_RANKS - 1];
+};
+struct HaloOut {                // producer side of one stage; peers.n == 0: single GPU / nobody in reach
+    HaloPeers peers;
+    unsigned *flag[SVGF_MAX_RANKS - 1];     // where my flag of this stage lives in peers.rank[i]'s memory
+    unsigned *counter;                      // blocks of this launch that have finished
+    unsigned seq;
+    int signal;                             // 1: the last block raises the flags (0: a separate signal kernel follows)
+};
+
+struct HaloIn {                 // consumer side: flags (in MY memory) that must have reached `seq` before halo rows are read
+    int n;
+    const unsigned *flag[SVGF_MAX_RANKS - 1];
+    unsigned seq;
+    unsigned *err;              // pinned, mapped error word (svgf_ctx::comm_err)
+};
+
 
 struct svgf_ctx {
     int device = 0;
@@ -80,16 +106,19 @@ struct svgf_ctx {
     svgf_shard shard{0, 1, 0, 0};
     RowOwner rows{1, {0}};
     // peer views of every plane another rank may read (index [rank]; [shard.rank] is this context's own pointer)
-    PeerPtr<float4> p_cv[3]; PeerPtr<float2> p_lv[3]; PeerPtr<float4> p_nrm[2]; PeerPtr<float2> p_mom[2]; PeerPtr<int> p_hlen[2];
+    PeerPtr<float4> p_cv[SVGF_NCV]; PeerPtr<float2> p_lv[SVGF_NCV]; PeerPtr<float4> p_nrm[2]; PeerPtr<float2> p_mom[2]; PeerPtr<int> p_hlen[2];
     PeerPtr<float4> p_gnp; PeerPtr<float2> p_gzl; PeerPtr<unsigned> p_flags;
-    unsigned *flags = nullptr;          // [SVGF_MAX_RANKS][SVGF_NUM_STAGES] sequence numbers written by the peers, + 1 error word
+    unsigned *flags = nullptr;          // [SVGF_MAX_RANKS][SVGF_NUM_STAGES] sequence numbers written by the peers
+    unsigned *done_count = nullptr;     // [SVGF_NUM_STAGES] blocks of a producer kernel that have finished (the last one raises the flags)
+    unsigned *comm_err = nullptr;       // pinned, mapped: set by a wait that gave up (a peer stopped making progress); device alias below
+    unsigned *comm_err_dev = nullptr;
     unsigned seq = 0;                   // frame sequence number (identical on all ranks)
     std::vector<void *> ipc_opened;
 
-    float4 *cv[3] = {nullptr, nullptr, nullptr};
+    float4 *cv[SVGF_NCV] = {nullptr, nullptr, nullptr, nullptr};
     // {luminance of cv[i].rgb in the reference's fp64 formula (denoise.cu:121), copy of cv[i].w}: what a tap needs besides
     // colour, and what the 3x3 variance blur reads (8 B/px, coalesced)
-    float2 *lv[3] = {nullptr, nullptr, nullptr};
+    float2 *lv[SVGF_NCV] = {nullptr, nullptr, nullptr, nullptr};
     // TMA descriptors (CUtensorMap, 128 B each) for the lattice tiles of cv[3], lv[3], gnp, gzl: [plane 8][level 1..7][shape 2]
     void *tmaps = nullptr; int tma_ok = 0;
     // sharded frames: 1 = every stage pushes the rows its neighbours will tap into their copy of the plane, levels read local
@@ -175,15 +204,19 @@ struct RtParams {
     svgf_camera cam;
 };
 void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx);
-cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out);
+cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, int gbuf_reach, bool *pushed);
 cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_cur, const PeerPtr<float4> &nrm_prev,
                             const float4 *pos, const PeerPtr<float4> &hist_cv, const PeerPtr<float2> &mom_hist,
                             const PeerPtr<int> &hlen_in, float4 *acc_cv, float2 *acc_lv, float2 *mom_acc, int *hlen_out,
-                            const float *prev_viewmat, float color_alpha, float moment_alpha, float clip_rx, float clip_ry);
+                            const float *prev_viewmat, float color_alpha, float moment_alpha, float clip_rx, float clip_ry,
+                            const HaloOut &ho, const PeerPtr<float4> &acc_cv_peers, const PeerPtr<float2> &acc_lv_peers);
+HaloPeers halo_peers(const svgf_ctx *c, int reach);
+HaloOut halo_out(svgf_ctx *c, int stage, int reach, bool fused_signal);
+HaloIn halo_in(svgf_ctx *c, int stage, int reach, unsigned seq);
 struct HaloPlane { const void *local; void *peer[SVGF_MAX_RANKS]; int esz; };     // esz = bytes per pixel (multiple of 8)
 cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes);
-cudaError_t launch_signal(svgf_ctx *c, int stage);
-cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq);
+cudaError_t launch_signal(svgf_ctx *c, int stage, int reach);                 // reach < 0: every connected rank
+cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq, int reach);
 cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float2 *acc_lv);
 struct AtrousArgs {
     int src_slot;                                   // cv/lum input = c->p_cv[src_slot] / c->p_lum[src_slot] (peer-readable)
@@ -195,6 +228,8 @@ struct AtrousArgs {
     float *denoised_out; float *var_out;            // last level only (AoS vec3 + float plane)
     int level, is_last, blur_variance, addcolor;
     float sigma_c, sigma_n, sigma_x;
+    HaloIn wait;                                    // sharded frames: flags to see before halo rows are read (n == 0: none)
+    HaloOut ho;                                     // ... and who gets this level's edge rows and its flag
 };
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a);
 cudaError_t launch_cv_to_outputs(svgf_ctx *c, const float4 *cv, float *denoised, float *var_out);

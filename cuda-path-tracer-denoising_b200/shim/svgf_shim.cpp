@@ -31,6 +31,7 @@ static_assert(offsetof(Geom, inverseTransform) == offsetof(svgf_geom, inverseTra
 
 static Scene *g_scene = NULL;
 static svgf_ctx *g_ctx = NULL;
+static void *g_pinned = NULL;       // scene->state.image.data() as page-locked by pathtrace() (pathtrace.cu:450 copies into it)
 
 static void die(const char *what, int rc) {     // == checkCUDAErrorFn, pathtrace.cu:25-43
     fprintf(stderr, "CUDA error (svgf_b200): %s: %d: %s\n", what, rc, svgf_last_error(g_ctx));
@@ -76,8 +77,8 @@ void pathtraceInit(Scene *scene) {
 }
 
 void pathtraceFree() {          // may precede the first Init (main.cpp:195): no-op on NULL
-    svgf_destroy(g_ctx);
-    g_ctx = NULL;
+    svgf_destroy(g_ctx);        // also drops the page-lock on the image buffer
+    g_ctx = NULL; g_pinned = NULL;
 }
 
 void denoiseInit(Scene *scene) {    // history restarts (denoise.cu:41-60); the buffers live in the same context
@@ -90,7 +91,14 @@ void denoiseFree() {}
 void pathtrace(uchar4 *pbo, int frame) {
     const svgf_params p = snapshot_ui();
     const svgf_camera c = snapshot_camera();
-    int rc = svgf_render(g_ctx, &c, &p, frame, pbo, reinterpret_cast<float *>(g_scene->state.image.data()));
+    // scene->state.image is a std::vector the Scene owns for its lifetime (sized at load, scene.cpp:170-172): page-lock it once so
+    // that the per-frame copy is a direct DMA, and follow it should the vector ever be reallocated
+    void *img = g_scene->state.image.data();
+    if (img != g_pinned) {
+        if (g_pinned) svgf_unregister_host(g_ctx, g_pinned);
+        g_pinned = svgf_register_host(g_ctx, img, g_scene->state.image.size() * sizeof(glm::vec3)) == SVGF_OK ? img : NULL;
+    }
+    int rc = svgf_render(g_ctx, &c, &p, frame, pbo, reinterpret_cast<float *>(img));
     if (rc) die("pathtrace", rc);
 }
 
@@ -102,14 +110,6 @@ void denoise(glm::vec3 *output, glm::vec3 *input, GBufferTexel *gbuffer) {
     if (rc) die("denoise", rc);
 }
 
-// accessors used by the test harness (oracle/ref/harness.cpp) in place of the reference TUs' file statics
-extern "C" int refh_fetch_pathtrace(const char *name, void *host, size_t bytes) {
-    if (!g_ctx) return -1;
-    if (!strcmp(name, "image") || !strcmp(name, "denoised") || !strcmp(name, "gbuffer")) return svgf_fetch(g_ctx, name, host, bytes) ? -2 : 0;
-    return 1;
-}
-extern "C" int refh_fetch_denoise(const char *name, void *host, size_t bytes) {
-    if (!g_ctx) return -1;
-    int rc = svgf_fetch(g_ctx, name, host, bytes);
-    return rc == SVGF_ERR_UNKNOWN_NAME ? 1 : (rc ? -2 : 0);
-}
+// The context behind the six entry points, for callers that want the library's extras (svgf_set_option, svgf_stage_times,
+// svgf_fetch ...) next to the reference's interface. NULL before pathtraceInit / after pathtraceFree.
+extern "C" svgf_ctx *svgf_shim_context(void) { return g_ctx; }

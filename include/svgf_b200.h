@@ -169,6 +169,13 @@ int svgf_render_async(svgf_ctx *ctx, const svgf_camera *cam, const svgf_params *
                       void *pbo_dev, float *host_image);
 /* Blocks until the image most recently queued into `host_image` has arrived (NULL: every queued image). */
 int svgf_wait_image(svgf_ctx *ctx, const float *host_image);
+/* Page-locking of caller memory. svgf_render copies into `host_image` by direct DMA when the buffer is page-locked (by the
+ * caller, or registered here) and through the context's own staging buffer otherwise -- it never registers memory behind
+ * the caller's back. svgf_render_async needs page-locked memory and registers an unregistered buffer on first sight. A
+ * registered buffer MUST stay allocated until svgf_unregister_host or svgf_destroy: freeing or resizing it earlier leaves
+ * the registration on pages the process no longer owns. */
+int svgf_register_host(svgf_ctx *ctx, void *host, size_t bytes);
+int svgf_unregister_host(svgf_ctx *ctx, void *host);
 /* == denoise(output, input, gbuffer), denoise.cu:349-402, on caller-owned DEVICE buffers in the reference's
  * AoS layouts (vec3 colour, 52-byte texels). */
 int svgf_denoise(svgf_ctx *ctx, float *output_dev, const float *input_dev, const svgf_gbuffer_texel *gbuffer_dev,
@@ -235,7 +242,8 @@ int svgf_ipc_export(svgf_ctx *ctx, void *handles_out);
 int svgf_ipc_connect(svgf_ctx *ctx, int rank, int world, const void *all_handles, const int *row_starts);
 /* Ranks that live in one process (several contexts on one or more GPUs): wire them without IPC. */
 int svgf_peer_connect_local(svgf_ctx **ctxs, int world, const int *row_starts);
-/* 1 if a cross-rank wait gave up (a peer stopped making progress), else 0. */
+/* 1 if a cross-rank wait gave up (a peer made no progress for ~2 s), else 0. The frame in flight continued on stale rows, so
+ * from then on svgf_render / svgf_render_async / svgf_sync / svgf_wait_image return SVGF_ERR_COMM until svgf_reset. */
 int svgf_peer_error(svgf_ctx *ctx);
 /* Restrict a lone context to a row strip (no peers: taps outside the strip read this context's own planes). */
 int svgf_set_shard(svgf_ctx *ctx, const svgf_shard *shard);

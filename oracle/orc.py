@@ -102,6 +102,8 @@ def lib():
         L.orc_frame.argtypes = [ctypes.c_void_p, ctypes.POINTER(Camera), ctypes.POINTER(Params), ctypes.c_int,
                                 ctypes.c_int, ctypes.c_int]
         L.orc_fetch.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.orc_denoise.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Camera),
+                                  ctypes.POINTER(Params), ctypes.c_int, ctypes.c_int]
         L.orc_host_intersect.argtypes = [ctypes.c_void_p] * 8
         L.orc_atrous_level.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 + [ctypes.c_float] * 3 + [ctypes.c_int] * 4
         L.orc_camera_init.argtypes = [ctypes.POINTER(Camera), ctypes.POINTER(CameraRig), ctypes.c_void_p, ctypes.c_void_p,
@@ -185,6 +187,16 @@ class Oracle:
         rc = lib().orc_frame(self.h, ctypes.byref(cam), ctypes.byref(params), frame, variance_mode, threads)
         if rc:
             raise RuntimeError("orc_frame -> %d" % rc)
+
+    def denoise(self, color_in, gbuffer, cam, params, variance_mode=VAR_JACOBI, threads=0):
+        """denoise(output, input, gbuffer) (src/denoise.h:8) on numpy arrays in the reference's AoS layouts."""
+        ci = np.ascontiguousarray(color_in, np.float32); g = np.ascontiguousarray(gbuffer, np.float32)
+        out = np.empty_like(ci)
+        rc = lib().orc_denoise(self.h, out.ctypes.data, ci.ctypes.data, g.ctypes.data, ctypes.byref(cam), ctypes.byref(params),
+                               variance_mode, threads)
+        if rc:
+            raise RuntimeError("orc_denoise -> %d" % rc)
+        return out
 
     def fetch(self, name):
         if name == "pbo":

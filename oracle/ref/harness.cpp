@@ -347,6 +347,40 @@ extern "C" int refh_frame() {
     return rendered;
 }
 
+// ---- the public denoise() entry point on its own (src/denoise.h:8, denoise.cu:349-402) -------------
+// refh_init: the reference's (re)initialisation order without rendering a frame. refh_denoise_host: uploads a 1-spp colour
+// buffer and a G-buffer in the reference's AoS layouts, calls denoise(output, input, gbuffer) -- the reference's own, or the
+// drop-in shim's, whichever this library was linked with -- and returns `output`. The camera is whatever
+// refh_set_camera / refh_frame left in scene->state.camera (denoise.cu:350 re-reads it on every call).
+extern "C" int refh_init() {
+    if (!scene) return -1;
+    pathtraceFree(); pathtraceInit(scene); denoiseFree(); denoiseInit(scene);
+    frame = 0; ui_reset_denoiser = false;
+    return 0;
+}
+extern "C" int refh_set_camera(const void *cam84) {
+    if (!scene) return -1;
+    memcpy(&scene->state.camera, cam84, sizeof(Camera));
+    return 0;
+}
+extern "C" int refh_denoise_host(void *out, const void *in, const void *gbuffer) {
+    if (!scene) return -1;
+    const size_t px = (size_t)scene->state.camera.resolution.x * scene->state.camera.resolution.y;
+    static glm::vec3 *d_in = NULL, *d_out = NULL; static GBufferTexel *d_g = NULL; static size_t cap = 0;
+    if (cap != px) {
+        cudaFree(d_in); cudaFree(d_out); cudaFree(d_g);
+        cudaMalloc((void **)&d_in, px * sizeof(glm::vec3)); cudaMalloc((void **)&d_out, px * sizeof(glm::vec3));
+        cudaMalloc((void **)&d_g, px * sizeof(GBufferTexel));
+        cap = px;
+    }
+    cudaMemcpy(d_in, in, px * sizeof(glm::vec3), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_g, gbuffer, px * sizeof(GBufferTexel), cudaMemcpyHostToDevice);
+    denoise(d_out, d_in, d_g);
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, d_out, px * sizeof(glm::vec3), cudaMemcpyDeviceToHost);
+    return 0;
+}
+
 extern "C" int refh_fetch(const char *name, void *host, size_t bytes) {
     if (!scene) return -1;
     if (!strcmp(name, "pbo")) {

@@ -58,6 +58,9 @@ class RefHarness:
         if hasattr(L, "refh_load_scene_txt"):
             L.refh_load_scene_txt.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
             L.refh_export_scene.argtypes = [ctypes.c_char_p]
+        if hasattr(L, "refh_denoise_host"):
+            L.refh_denoise_host.argtypes = [ctypes.c_void_p] * 3
+            L.refh_set_camera.argtypes = [ctypes.c_void_p]
         if hasattr(L, "refh_host_intersect"):
             L.refh_host_intersect.argtypes = [ctypes.c_void_p] * 7
         self.W = self.H = 0
@@ -90,6 +93,25 @@ class RefHarness:
         if r < 0:
             raise RuntimeError("refh_frame -> %d" % r)
         return r
+
+    def init(self):
+        """pathtraceFree/Init + denoiseFree/Init without rendering (the reference's reset order, main.cpp:192-201)."""
+        if self.lib.refh_init():
+            raise RuntimeError("refh_init failed")
+
+    def set_camera(self, cam21):
+        a = np.ascontiguousarray(cam21, np.float32)
+        assert a.nbytes == 84
+        if self.lib.refh_set_camera(a.ctypes.data):
+            raise RuntimeError("refh_set_camera failed")
+
+    def denoise(self, color_in, gbuffer):
+        """denoise(output, input, gbuffer) (src/denoise.h:8) of whatever this library links: the reference's or the shim's."""
+        ci = np.ascontiguousarray(color_in, np.float32); g = np.ascontiguousarray(gbuffer, np.float32)
+        out = np.empty_like(ci)
+        if self.lib.refh_denoise_host(out.ctypes.data, ci.ctypes.data, g.ctypes.data):
+            raise RuntimeError("refh_denoise_host failed")
+        return out
 
     def time_frames(self, n):
         return self.lib.refh_time_frames(n)

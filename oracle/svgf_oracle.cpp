@@ -879,6 +879,16 @@ int orc_frame(orc_state *S, const svgf_camera *cam, const svgf_params *P, int fr
     return 0;
 }
 
+// denoise(output, input, gbuffer) (src/denoise.h:8, denoise.cu:349-402) on caller buffers, against the state's histories: the
+// public entry point on its own, without the path tracer in front of it.
+int orc_denoise(orc_state *S, float *output, const float *input, const svgf_gbuffer_texel *gbuffer, const svgf_camera *cam,
+                const svgf_params *P, int variance_mode, int threads) {
+    if (cam->resolution[0] != S->W || cam->resolution[1] != S->H) return -1;
+    if (threads <= 0) threads = orc_max_threads();
+    denoiseFrame(*S, output, input, gbuffer, *cam, *P, variance_mode, threads);
+    return 0;
+}
+
 int orc_fetch(orc_state *S, const char *name, void *host, size_t bytes) {
     const void *src = NULL; size_t need = 0;
 #define F(n, vec) if (!strcmp(name, n)) { src = S->vec.data(); need = S->vec.size() * sizeof(S->vec[0]); }

@@ -35,6 +35,9 @@ void orc_reset(orc_state *);    /* pathtraceInit + denoiseInit semantics */
 
 /* pathtrace(pbo, frame) == orc_pathtrace + (denoise_enable ? orc_denoise : copy) + orc_pack_pbo */
 int orc_frame(orc_state *, const svgf_camera *, const svgf_params *, int frame, int variance_mode, int threads);
+/* denoise(output, input, gbuffer) on caller buffers (vec3 colour, 52-byte texels), src/denoise.h:8 */
+int orc_denoise(orc_state *, float *output, const float *input, const svgf_gbuffer_texel *gbuffer, const svgf_camera *,
+                const svgf_params *, int variance_mode, int threads);
 int orc_fetch(orc_state *, const char *name, void *host, size_t bytes);
 int orc_host_intersect(const orc_scene *, const float *origin, const float *dir, float *t, float *normal,
                        float *uv, int *geomId, int *materialId);

@@ -16,3 +16,19 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured parity statistics of every comparison of the session (tests/util.py: REPORT)."""
+    try:
+        import json
+        import util
+        if not util.REPORT:
+            return
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        name = os.environ.get("SVGF_PARITY_REPORT", "parity_report.json")
+        with open(os.path.join(out, name), "w") as f:
+            json.dump({"exitstatus": int(exitstatus), "comparisons": util.REPORT}, f, indent=1)
+    except Exception as e:      # a report must never fail a run
+        print("parity report not written: %s" % e)

@@ -35,7 +35,7 @@ def _worker(rank, world, port, nbytes, q):
 def test_handle_gather_is_rank_ordered(world):
     m = svgf()
     nbytes = m.lib().svgf_ipc_handles_size()
-    assert nbytes == 15 * 64
+    assert nbytes == 17 * 64
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

@@ -75,3 +75,52 @@ def test_oracle_bit_exact_vs_reference_cpu(case):
     assert r.returncode == 0, r.stderr[-2000:]
     bad = json.loads(r.stdout.strip().splitlines()[-1])
     assert bad == [], "buffers differing from the reference (frame, name): %r" % bad
+
+
+DENOISE_WORKER = r'''
+import sys, json
+sys.path.insert(0, %(oracle)r)
+import numpy as np, refh, orc
+variant, mode, scene, W, H, nframes, over = json.loads(sys.argv[1])
+# inputs: frames of the oracle's own path tracer with a moving camera, then DISTORTED (shuffled rows, scaled colour), so that
+# the entry point is exercised on buffers no pathtrace() call would have produced in this order
+sc = orc.Scene(scene); src = orc.Oracle(sc, W, H); P = orc.default_params(**over)
+drv = orc.CameraDriver(sc, W, H, automate=True)
+rng = np.random.default_rng(5)
+h = refh.RefHarness(variant); h.load_blob(scene, W, H); h.set_params(**refh.ALL_ON); h.set_params(**over); h.init()
+o = orc.Oracle(sc, W, H)
+bad = []
+for f in range(nframes):
+    cam = drv.step()
+    src.frame(cam, P, f, mode, 2)
+    img = src.fetch("image") * np.float32(1.0 + 0.25 * f); g = src.fetch("gbuffer")
+    if f == 2:
+        img = img[::-1].copy(); g = g[::-1].copy()
+    h.set_camera(cam.as_array())
+    a = h.denoise(img, g); b = o.denoise(img, g, cam, P, mode, 2)
+    if not np.array_equal(a.view(np.uint8), b.view(np.uint8)):
+        bad.append([f, "output"])
+    for k in ["variance", "color_history", "moment_history", "history_length", "gbuffer_prev"]:
+        if not over.get("temporal_enable", 1) and k in ("moment_history", "history_length"):
+            continue
+        if not np.array_equal(h.fetch(k).view(np.uint8), o.fetch(k).view(np.uint8)):
+            bad.append([f, k])
+print(json.dumps(bad))
+'''
+
+
+@pytest.mark.parametrize("case", [("cpu_jacobi", 0, "cornell", 48, 40, 4, {}), ("cpu", 1, "bunny", 40, 40, 3, {"atrous_nlevel": 3}),
+                                  ("cpu_jacobi", 0, "cornell", 40, 40, 3, {"temporal_enable": 0}),
+                                  ("cpu_jacobi", 0, "room", 40, 40, 3, {"history_level": 2, "sepcolor": 0})],
+                         ids=lambda c: "%s-%s-%s" % (c[0], c[2], "-".join("%s%s" % kv for kv in c[6].items()) or "allon"))
+def test_oracle_denoise_entry_point_bit_exact(case):
+    """The public denoise(output, input, gbuffer) entry (src/denoise.h:8, denoise.cu:349-402) on its own: the oracle's
+    orc_denoise against the reference's own denoise() executed on the CPU, on caller-supplied buffers, every history it
+    leaves behind included."""
+    if not refh.available(case[0]):
+        pytest.skip("oracle/_ref/libref_%s.so not built (needs /root/reference)" % case[0])
+    code = DENOISE_WORKER % {"oracle": os.path.dirname(os.path.abspath(refh.__file__))}
+    r = subprocess.run([sys.executable, "-c", code, json.dumps(case)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    bad = json.loads(r.stdout.strip().splitlines()[-1])
+    assert bad == [], "buffers differing from the reference's denoise() (frame, name): %r" % bad

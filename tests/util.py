@@ -44,9 +44,21 @@ def frac_bad(a, b, floor, tol=REL_TOL):
     return float((rel_err(a, b, floor) > tol).mean())
 
 
+# Every comparison made through assert_close / report() is recorded; tests/conftest.py writes the list to
+# gpurun_out/parity_report.json at the end of a session (copied to profiles/ by hand): the MEASURED fractions and maxima,
+# not just "below budget".
+REPORT = []
+
+
+def report(what, **kv):
+    REPORT.append(dict(what=what, **kv))
+
+
 def assert_close(a, b, floor, what, tol=REL_TOL, max_bad_frac=0.0):
     r = rel_err(a, b, floor)
-    bad = float((r > tol).mean())
+    bad = float((r > tol).mean()) if r.size else 0.0
+    report(what, n=int(r.size), tol=tol, floor=floor, frac_beyond_tol=bad, budget=max_bad_frac, max_rel_err=float(r.max()) if r.size else 0.0,
+           p999_rel_err=float(np.quantile(r, 0.999)) if r.size else 0.0)
     assert bad <= max_bad_frac, "%s: %.4f%% of values exceed %g relative (max %.3g)" % (what, 100 * bad, tol, r.max())
 
 
