@@ -236,7 +236,8 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     c->shard = svgf_shard{0, 1, 0, c->H};
     if (const char *v = getenv("SVGF_RT_VARIANT")) c->rt_variant = (!strcmp(v, "wavefront") || !strcmp(v, "1")) ? 1 : ((!strcmp(v, "persistent") || !strcmp(v, "2")) ? 2 : 0);
     if (const char *v = getenv("SVGF_HALO")) c->halo_push = strcmp(v, "pull") != 0;      // A/B testing
-    if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3 || atoi(v) == 4) ? atoi(v) : 2;    // A/B testing
+    if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3 || atoi(v) == 4 || atoi(v) == 5) ? atoi(v) : 2;    // A/B testing
+    if (const char *v = getenv("SVGF_ATROUS_BANDS")) c->atrous_slide_bands = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_SHAPE")) c->atrous_shape = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_PROBE")) c->atrous_probe = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_PAIR_ROWS")) c->atrous_pair_rows = atoi(v) == 1 ? 1 : 2;
@@ -270,7 +271,7 @@ int svgf_destroy(svgf_ctx *c) {
     cudaFree(s.geoms); cudaFree(s.materials); cudaFree(s.bvh); cudaFree(s.tri_hot); cudaFree(s.tri_cold); cudaFree(s.textures);
     for (unsigned char *p : s.tex_pixels) cudaFree(p);      // the reference leaks these (pathtrace.cu:136 vs 160-183)
     for (int i = 0; i < SVGF_NCV; i++) { cudaFree(c->cv[i]); cudaFree(c->lv[i]); }
-    free(c->tmaps);
+    free(c->tmaps); free(c->tmaps_slide);
     cudaFree(c->done_count);
     if (c->comm_err) cudaFreeHost(c->comm_err);
     for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }

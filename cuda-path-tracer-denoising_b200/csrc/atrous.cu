@@ -16,9 +16,11 @@
 #include "halo_sync.cuh"
 #include "atrous_pair_core.h"
 #include "atrous_tile_core.h"
+#include "atrous_slide_core.h"
 
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda/barrier>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -494,6 +496,220 @@ atrous_pair_kernel(const __grid_constant__ AtrousT t) {
     halo_block_done(t.ho);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sliding kernel (atrous_variant 5): the symmetric formulation with the pair distances in registers, csrc/atrous_slide_core.h.
+// Every WARP is its own pipeline: it owns a strip of 16 lattice columns x 2 sub-columns of one residue class and walks down a
+// band of lattice rows. Rows are staged one at a time into a private ring of SL_DEPTH slots by TMA -- a row of a residue class
+// is the box {2 pixels, 16 cells, 1, 1} of the 4-D view {s-pixel cell | cell | row in band | band} of the row-major plane
+// (4 copies of 512/512/256/256 bytes per row, issued by lane 0, completion on the slot's mbarrier) -- five rows ahead of their
+// use, so no lane ever waits for a tile and nobody synchronises across warps. Items (class, strip, band) are dealt to the
+// warps round-robin; launch_atrous_slide sizes the bands so that the items fill the resident warps once.
+constexpr int SL_DEPTH = 8, SL_WARPS = 4, SL_SLOT = SL_ROW * 48;         // bytes of one staged row: cv 512 | np 512 | zl 256 | lv 256
+constexpr int SL_SMEM = SL_WARPS * (SL_DEPTH * SL_SLOT + SL_DEPTH * 8);
+
+struct AtrousS {
+    AtrousK k;
+    SlGrid g;
+    const float *kl;
+    int use_tma;
+    HaloOut ho;
+    float4 *cv_peer[SVGF_MAX_RANKS - 1]; float2 *lv_peer[SVGF_MAX_RANKS - 1];
+    alignas(64) CUtensorMap tm_cv, tm_np, tm_zl, tm_lv;
+};
+
+__device__ __forceinline__ unsigned sl_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sl_mbar_init(unsigned long long *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sl_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void sl_mbar_expect(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sl_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sl_mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(sl_smem(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 22)) __trap();       // a row that never lands is a bug: fail the launch, do not hang the GPU
+    } while (!done);
+}
+__device__ __forceinline__ void sl_tma_row(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(sl_smem(dst)), "l"(tm), "r"(sl_smem(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+struct SlWarp {                     // what a warp knows about its current item
+    unsigned char *ring; unsigned long long *bars;
+    int lane, x, xv, need_fix;      // this lane's pixel column, is it inside the image, does the strip touch the image's edge
+    int X0, yc, a0, b0;             // b0 = lattice row of staged row 0 of the item
+    unsigned g0;                    // rows staged by this warp before the item (slot and parity bookkeeping)
+};
+
+__device__ __forceinline__ SlRow sl_slot(const SlWarp &w, unsigned g) {
+    unsigned char *p = w.ring + (g % SL_DEPTH) * SL_SLOT;
+    SlRow r;
+    r.cv = reinterpret_cast<const float4 *>(p); r.np = reinterpret_cast<const float4 *>(p + 512);
+    r.zl = reinterpret_cast<const float2 *>(p + 1024); r.lv = reinterpret_cast<const float2 *>(p + 1280);
+    return r;
+}
+
+// Start the load of staged row r of the item (lattice row b0 + r) into its slot.
+__device__ __forceinline__ void sl_issue(const AtrousS &t, const SlWarp &w, int r) {
+    const unsigned g = w.g0 + (unsigned)r;
+    unsigned char *p = w.ring + (g % SL_DEPTH) * SL_SLOT;
+    const int b = w.b0 + r, step = t.k.step;
+    if (t.use_tma) {
+        if (w.lane == 0) {
+            unsigned long long *bar = w.bars + (g % SL_DEPTH);
+            sl_mbar_expect(bar, SL_SLOT);
+            sl_tma_row(p, &t.tm_cv, 4 * w.X0, w.a0, w.yc, b, bar);
+            sl_tma_row(p + 512, &t.tm_np, 4 * w.X0, w.a0, w.yc, b, bar);
+            sl_tma_row(p + 1024, &t.tm_zl, 2 * w.X0, w.a0, w.yc, b, bar);
+            sl_tma_row(p + 1280, &t.tm_lv, 2 * w.X0, w.a0, w.yc, b, bar);
+        }
+    } else {        // odd widths (8-byte planes need a 16-byte pitch for TMA): every lane fetches its own entry
+        const int y = w.yc + b * step;
+        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), np = cv; float2 zl = make_float2(0.f, 0.f), lv = make_float2(3e38f, 0.f);
+        if (w.xv && b >= 0 && y < t.k.H) {
+            const size_t q = (size_t)w.x + (size_t)y * t.k.W;
+            cv = __ldg(&t.k.cv_in[q]); np = __ldg(&t.k.gnp[q]); zl = __ldg(&t.k.gzl[q]); lv = __ldg(&t.k.lv_in[q]);
+        }
+        reinterpret_cast<float4 *>(p)[w.lane] = cv; reinterpret_cast<float4 *>(p + 512)[w.lane] = np;
+        reinterpret_cast<float2 *>(p + 1024)[w.lane] = zl; reinterpret_cast<float2 *>(p + 1280)[w.lane] = lv;
+    }
+}
+
+// Staged row r has landed (and columns outside the image carry lum = 3e38, which zeroes every weight of such a tap).
+__device__ __forceinline__ void sl_wait(const AtrousS &t, const SlWarp &w, int r) {
+    const unsigned g = w.g0 + (unsigned)r;
+    if (t.use_tma) {
+        sl_mbar_wait(w.bars + (g % SL_DEPTH), (g / SL_DEPTH) & 1u);
+        if (w.need_fix) {           // cells left of the image are zero-filled, cells right of it alias the next row
+            if (!w.xv) reinterpret_cast<float2 *>(w.ring + (g % SL_DEPTH) * SL_SLOT + 1280)[w.lane].x = 3e38f;
+            __syncwarp();
+        }
+    } else {
+        __syncwarp();
+    }
+}
+
+template <int PHI>
+__device__ __forceinline__ void sl_step(const AtrousS &t, const SlWarp &w, SlLane &L, int rt, int rows, const int (&e)[5], float kl_enter) {
+    constexpr int KE = sl_set(PHI, 2), KX = sl_set(PHI, -2);
+    const AtrousK &k = t.k;
+    // the centre two rows below the tap row enters flight
+    sl_wait(t, w, rt + 2);
+    sl_enter<KE>(L, sl_slot(w, w.g0 + rt + 2), w.lane, kl_enter);
+    const int b = w.b0 + rt, y = w.yc + b * k.step;
+    if (b >= 0 && y < k.H) {        // tap rows outside the image have no pairs (warp-uniform)
+        const SlRow row = sl_slot(w, w.g0 + rt);
+        // what the lanes owning the neighbouring columns hold for this lane's centres above the tap row (registers written one
+        // and two steps ago: the shuffles depend on nothing in this step)
+        float r1[5], r2[5], s[2], bk[2];
+#pragma unroll
+        for (int ti = 0; ti < 5; ti++) {
+            const int i = ti - 2;
+            if (i == 0) { r1[2] = sl_offer_r1<PHI>(L, 0); r2[2] = sl_offer_r2<PHI>(L, 0); continue; }
+            r1[ti] = __shfl_sync(0xffffffffu, sl_offer_r1<PHI>(L, i), w.lane + 2 * i);
+            r2[ti] = __shfl_sync(0xffffffffu, sl_offer_r2<PHI>(L, i), w.lane + 2 * i);
+        }
+        {   // same-row pairs: to the right computed, to the left received
+            const SlTap t3 = sl_load_tap(row, e[3]), t4 = sl_load_tap(row, e[4]);
+            sl_same_row<PHI>(L, t3, t4, s);
+            bk[0] = __shfl_sync(0xffffffffu, s[0], w.lane - 2);
+            bk[1] = __shfl_sync(0xffffffffu, s[1], w.lane - 4);
+            sl_tap<PHI, 3>(L, t3, r1[3], r2[3], s[0]);
+            sl_tap<PHI, 4>(L, t4, r1[4], r2[4], s[1]);
+        }
+        sl_tap<PHI, 2>(L, sl_load_tap(row, e[2]), r1[2], r2[2], pair_nlog2h(0, 0));
+        sl_tap<PHI, 1>(L, sl_load_tap(row, e[1]), r1[1], r2[1], bk[0]);
+        sl_tap<PHI, 0>(L, sl_load_tap(row, e[0]), r1[0], r2[0], bk[1]);
+    }
+    // the centre two rows above the tap row is complete
+    const int bo = b - 2, yo = w.yc + bo * k.step;
+    const int a = w.lane >> 1;
+    if (rt >= 4 && rt < rows + 4 && a >= SL_EDGE && a < SL_COLS - SL_EDGE && w.x < k.W && yo >= k.row_begin && yo < k.row_end) {
+        const SlAccS o = sl_exit<KX>(L);
+        // sum w >= h(0,0) always (the centre tap), so the reference's `else` branch (denoise.cu:162-164) is dead
+        const float rw = __frcp_rn(o.w);
+        float4 c = make_float4(o.r * rw, o.g * rw, o.b * rw, __fdividef(o.v, o.w2));
+        const int p = w.x + yo * k.W;
+        if (k.is_last) {
+            if (k.addcolor) { const float4 al = __ldg(&k.alb[p]); c.x *= al.x; c.y *= al.y; c.z *= al.z; }
+            float *d = k.denoised_out + 3 * (size_t)p;
+            d[0] = c.x; d[1] = c.y; d[2] = c.z;
+            k.var_out[p] = c.w;
+        }
+        if (k.cv_out) {
+            const float2 lvo = make_float2(lum_ref(c.x, c.y, c.z), c.w);
+            k.cv_out[p] = c; k.lv_out[p] = lvo;
+            for (unsigned m = halo_targets(t.ho.peers, yo); m; m &= m - 1) {       // rows a neighbour taps at the next level
+                const int i = __ffs(m) - 1;
+                t.cv_peer[i][p] = c; t.lv_peer[i][p] = lvo;
+            }
+        }
+    }
+    // tap row rt is not read again: its slot takes the row SL_DEPTH further down
+    __syncwarp();
+    if (rt + SL_DEPTH < rows + 6) sl_issue(t, w, rt + SL_DEPTH);
+}
+
+__global__ void __launch_bounds__(SL_WARPS * 32, 3)
+atrous_slide_kernel(const __grid_constant__ AtrousS t) {
+    extern __shared__ __align__(1024) unsigned char sl_smem_raw[];
+    const AtrousK &k = t.k;
+    SlWarp w;
+    const int wid = threadIdx.x >> 5;
+    w.lane = threadIdx.x & 31;
+    w.ring = sl_smem_raw + wid * (SL_DEPTH * SL_SLOT);
+    w.bars = reinterpret_cast<unsigned long long *>(sl_smem_raw + SL_WARPS * SL_DEPTH * SL_SLOT) + wid * SL_DEPTH;
+    if (w.lane == 0) {
+        for (int i = 0; i < SL_DEPTH; i++) sl_mbar_init(w.bars + i);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    w.g0 = 0;
+    int e[5];
+#pragma unroll
+    for (int ti = 0; ti < 5; ti++) e[ti] = min(max(w.lane + 2 * (ti - 2), 0), SL_ROW - 1);       // edge lanes: any entry, their sums are dropped
+    const int items = t.g.items(), a = w.lane >> 1, c = w.lane & 1;
+    for (int n = blockIdx.x * SL_WARPS + wid; n < items; n += gridDim.x * SL_WARPS) {
+        const SlItem it = t.g.item(n);
+        const int rows = it.b_hi - it.b_lo;             // centre rows of the band; staged rows: rows + 6, steps: rows + 4
+        if (rows <= 0) continue;
+        w.X0 = it.X0; w.yc = it.yc; w.a0 = it.a0; w.b0 = it.b_lo - 2;
+        w.x = it.X0 + (it.a0 + a) * k.step + c;
+        w.xv = (it.a0 + a >= 0) && (w.x < k.W);
+        w.need_fix = (it.a0 < 0) || (it.X0 + (it.a0 + SL_COLS - 1) * k.step + 1 >= k.W);
+        const int staged = rows + 6;
+        for (int r = 0; r < SL_DEPTH - 1 && r < staged; r++) sl_issue(t, w, r);
+        SlLane L;
+        memset(&L, 0, sizeof(L));
+        // luminance-weight scale of the centres, fetched two steps before they enter flight
+        auto kl_of = [&](int r) -> float {              // staged row r
+            const int y = w.yc + (w.b0 + r) * k.step;
+            return (w.xv && w.b0 + r >= 0 && y < k.H) ? __ldg(&t.kl[w.x + (size_t)y * k.W]) : 0.f;
+        };
+        float q0 = kl_of(2), q1 = kl_of(3);
+        sl_wait(t, w, 0); sl_enter<0>(L, sl_slot(w, w.g0 + 0), w.lane, kl_of(0));
+        sl_wait(t, w, 1); sl_enter<1>(L, sl_slot(w, w.g0 + 1), w.lane, kl_of(1));
+        const int steps = rows + 4;
+        for (int rt = 0; rt < steps; rt += 5) {
+            // five steps = one turn of the register rotation. The centre entering at step r lies in staged row r + 2; its kl is
+            // requested two steps earlier and waits in q0/q1.
+            float kq;
+            kq = q0; q0 = kl_of(rt + 4); sl_step<0>(t, w, L, rt, rows, e, kq);
+            if (rt + 1 < steps) { kq = q1; q1 = kl_of(rt + 5); sl_step<1>(t, w, L, rt + 1, rows, e, kq); }
+            if (rt + 2 < steps) { kq = q0; q0 = kl_of(rt + 6); sl_step<2>(t, w, L, rt + 2, rows, e, kq); }
+            if (rt + 3 < steps) { kq = q1; q1 = kl_of(rt + 7); sl_step<3>(t, w, L, rt + 3, rows, e, kq); }
+            if (rt + 4 < steps) { kq = q0; q0 = kl_of(rt + 8); sl_step<4>(t, w, L, rt + 4, rows, e, kq); }
+            kq = q0; q0 = q1; q1 = kq;
+        }
+        w.g0 += (unsigned)staged;
+    }
+    halo_block_done(t.ho);
+}
+
 }  // namespace
 
 // log2(e) / (sigma + 1e-6) in fp64 (the reference adds and divides in double, denoise.cu:144-145)
@@ -549,6 +765,8 @@ static inline CUtensorMap *tmap_at(svgf_ctx *c, int plane, int level, int shape)
     return static_cast<CUtensorMap *>(c->tmaps) + ((plane * TM_LEVELS + level) * TM_SHAPES + shape);
 }
 
+static int atrous_build_slide_maps(svgf_ctx *c, encode_fn_t encode);
+
 int atrous_build_tensor_maps(svgf_ctx *c) {
     c->tma_ok = 0;
     if (c->W & 1) return 0;         // 8 B/pixel planes need a 16-byte row pitch; odd widths use the cp.async loader
@@ -585,7 +803,33 @@ int atrous_build_tensor_maps(svgf_ctx *c) {
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) return 0;
             }
-    c->tma_ok = 1;
+    c->tma_ok = atrous_build_slide_maps(c, encode) ? 1 : 0;
+    return c->tma_ok;
+}
+
+// Tensor maps of the sliding kernel: one per (plane, level), 4-D {floats of an s-pixel cell | cell | row in band | band}; a staged
+// row is the box {2 pixels, SL_COLS cells, 1, 1}. Same rounding-up of the extents (and the same padding behind the planes) as above.
+static inline CUtensorMap *tmap_slide(svgf_ctx *c, int plane, int level) {
+    return static_cast<CUtensorMap *>(c->tmaps_slide) + (plane * TM_LEVELS + level);
+}
+static int atrous_build_slide_maps(svgf_ctx *c, encode_fn_t encode) {
+    if (!c->tmaps_slide) c->tmaps_slide = aligned_alloc(64, sizeof(CUtensorMap) * TM_PLANES * TM_LEVELS);
+    if (!c->tmaps_slide) return 0;
+    void *planes[TM_PLANES]; int fpp[TM_PLANES];
+    for (int i = 0; i < SVGF_NCV; i++) { planes[i] = c->cv[i]; fpp[i] = 4; planes[SVGF_NCV + i] = c->lv[i]; fpp[SVGF_NCV + i] = 2; }
+    planes[2 * SVGF_NCV] = c->gnp; fpp[2 * SVGF_NCV] = 4; planes[2 * SVGF_NCV + 1] = c->gzl; fpp[2 * SVGF_NCV + 1] = 2;
+    for (int pl = 0; pl < TM_PLANES; pl++)
+        for (int level = 1; level <= SVGF_MAX_LEVELS; level++) {
+            const cuuint64_t s = 1ull << level, W = c->W, H = c->H, f = fpp[pl];
+            const cuuint64_t dims[4] = {f * s, (W + s - 1) / s, s, (H + s - 1) / s};
+            const cuuint64_t strides[3] = {f * 4 * s, f * 4 * W, f * 4 * s * W};
+            const cuuint32_t box[4] = {(cuuint32_t)(f * 2), (cuuint32_t)SL_COLS, 1, 1};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = encode(tmap_slide(c, pl, level), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, planes[pl], dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return 0;
+        }
     return 1;
 }
 
@@ -641,6 +885,53 @@ static cudaError_t launch_atrous_pair(svgf_ctx *c, AtrousT &t, const AtrousArgs 
     return cudaGetLastError();
 }
 
+// SVGF_ATROUS_VARIANT=5: the sliding kernel. Bands are sized so that the items (class x strip x band) fill the resident warps
+// about once: a warp's item is a long serial walk, so what counts is that no warp slot idles while others still hold two items.
+static cudaError_t launch_atrous_slide(svgf_ctx *c, const AtrousK &k, const AtrousArgs &a) {
+    AtrousS t;
+    memset(&t, 0, sizeof(t));
+    t.k = k; t.kl = c->kl;
+    t.ho = a.ho;
+    for (int i = 0; i < SVGF_MAX_RANKS - 1; i++) {
+        const bool on = i < a.ho.peers.n && a.cv_out && a.dst_slot >= 0;
+        t.cv_peer[i] = on ? c->p_cv[a.dst_slot].p[a.ho.peers.rank[i]] : nullptr;
+        t.lv_peer[i] = on ? c->p_lv[a.dst_slot].p[a.ho.peers.rank[i]] : nullptr;
+    }
+    t.use_tma = c->tma_ok && a.src_slot >= 0;
+    if (t.use_tma) {
+        t.tm_cv = *tmap_slide(c, a.src_slot, a.level); t.tm_lv = *tmap_slide(c, SVGF_NCV + a.src_slot, a.level);
+        t.tm_np = *tmap_slide(c, 2 * SVGF_NCV, a.level); t.tm_zl = *tmap_slide(c, 2 * SVGF_NCV + 1, a.level);
+    }
+    if (!c->atrous_slide_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(atrous_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(atrous_slide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->atrous_slide_blocks_per_sm, atrous_slide_kernel, SL_WARPS * 32, SL_SMEM);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        c->atrous_slide_sms = sms;
+        if (e != cudaSuccess) return e;
+        c->atrous_slide_attr_set = true;
+    }
+    const int step = k.step;
+    SlGrid &g = t.g;
+    g.step = step; g.ncg = step / 2;
+    const int lat_w = (c->W + step - 1) / step;
+    g.strips = (lat_w + SL_USE - 1) / SL_USE;
+    g.b_first = k.row_begin / step; g.b_end = (k.row_end - 1) / step + 1;
+    const int lat_rows = g.b_end - g.b_first;
+    const int slots = c->atrous_slide_sms * std::max(1, c->atrous_slide_blocks_per_sm) * SL_WARPS;
+    const int columns = g.ncg * step * g.strips;            // items per band
+    int bands = c->atrous_slide_bands > 0 ? c->atrous_slide_bands : std::max(1, slots / std::max(1, columns));
+    if (columns > slots && c->atrous_slide_bands <= 0) bands = 2;      // several waves anyway: shorter items even the tail out
+    bands = std::min(bands, std::max(1, lat_rows / 4));     // a band pays for 4 rows of run-in
+    g.band_rows = (lat_rows + bands - 1) / bands;
+    g.bands = (lat_rows + g.band_rows - 1) / g.band_rows;
+    const int items = g.items();
+    const int blocks = std::min((items + SL_WARPS - 1) / SL_WARPS, slots / SL_WARPS);
+    atrous_slide_kernel<<<std::max(blocks, 1), SL_WARPS * 32, SL_SMEM, c->stream>>>(t);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     const int rows = c->shard.row_end - c->shard.row_begin;
     if (rows <= 0) return cudaSuccess;
@@ -686,6 +977,7 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     const int lat_w = (c->W + step - 1) / step;                                 // lattice columns per class
     const int lat_rows = (k.row_end - 1) / step - t.b_first + 1;                // lattice rows touching the strip
     if (c->atrous_variant == 4) return launch_atrous_pair(c, t, a, lat_w, lat_rows);
+    if (c->atrous_variant == 5) return launch_atrous_slide(c, k, a);
     const int shape = at_pick_shape(c, a.level, lat_w, lat_rows);
     const AtShapeInfo &si = g_at_shapes[shape];
     t.use_tma = c->tma_ok && a.src_slot >= 0 && c->atrous_variant != 3;

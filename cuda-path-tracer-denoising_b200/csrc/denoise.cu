@@ -44,11 +44,8 @@ struct TemporalOut { float4 cv; float2 lv, mom; int hlen; };
 // (SURVEY.md 8(d)): reads image 12 + normal/geomId 16 + position 12 + own history length 4 + (reprojected, cache-shared)
 // prev normal/geomId 16, colour history 12(16), moments 8, history length 4; writes {colour,variance} 16 + moments 8 +
 // history length 4.
-// Latency: the reference's control flow is three dependent round trips to memory (own history length -> the four previous
-// normals -> the four history taps). Here the first-round loads (history length, sample, normal, position) are issued
-// together, and the four taps' history records are requested TOGETHER with their normals (the addresses are known as soon as
-// the pixel is projected; a tap whose normal later fails the test costs a few wasted sectors), so a pixel waits for memory
-// twice, not three times. The arithmetic, its order and therefore every bit of the result are the reference's.
+// (Requesting the four taps' history records together with their normals -- two dependent round trips to memory instead of
+// three -- was measured on B200 and is SLOWER, 69.6 vs 62 us at C2: 64 registers instead of 47 cost a resident block per SM.)
 __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const float *__restrict__ image, const float4 *__restrict__ nrm_cur,
                                                       const PeerPtr<float4> &nrm_prev, const float4 *__restrict__ pos, const PeerPtr<float4> &hist_cv,
                                                       const PeerPtr<float2> &mom_hist, const PeerPtr<int> &hlen_tab, const RowOwner &ro, int me,
@@ -57,10 +54,10 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
     const int N = hlen_tab.p[me][p];     // own pixel (denoise.cu:194)
     const float sr = image[3 * (size_t)p], sg = image[3 * (size_t)p + 1], sb = image[3 * (size_t)p + 2];
     const float4 ncur = nrm_cur[p];
-    const float4 pp = pos[p];
     const float luminance = 0.2126 * sr + 0.7152 * sg + 0.0722 * sb;    // double, as denoise.cu:196
     TemporalOut o;
     if (N > 0 && __float_as_int(ncur.w) != -1) {
+        const float4 pp = pos[p];
         // prev_viewmat * vec4(position, 1): (m0 v0 + m1 v1) + (m2 v2 + m3 v3), glm type_mat4x4.inl:617-628
         const float vx = (vm.m[0] * pp.x + vm.m[4] * pp.y) + (vm.m[8] * pp.z + vm.m[12] * 1.0f);
         const float vy = (vm.m[1] * pp.x + vm.m[5] * pp.y) + (vm.m[9] * pp.z + vm.m[13] * 1.0f);
@@ -77,29 +74,12 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
         // glm::ivec2(floorx, floory) + offset: saturating cvt, wrapping integer add (as the reference's SASS)
         const int ifx = __float2int_rz(floorx), ify = __float2int_rz(floory);
         bool v[4]; int qi[4];
-        float4 tn[4], th[4]; float2 tm[4]; int tl[4];
-        bool inr[4];
-#pragma unroll
-        for (int s = 0; s < 4; s++) {       // addresses of the four taps; all their loads are in flight before the first is used
-            const int lx = (int)((unsigned)ifx + (unsigned)(s & 1)), ly = (int)((unsigned)ify + (unsigned)(s >> 1));
-            const float fx = (float)lx, fy = (float)ly;
-            // isReprjValid's bounds test and FLOAT index (denoise.cu:172-177); NaN coordinates pass the reference's test and
-            // index garbage (undefined) -- rejected here
-            inr[s] = (fx >= 0.f) && (fx < (float)W) && (fy >= 0.f) && (fy < (float)H);
-            qi[s] = lx + ly * W;
-            tn[s] = make_float4(0.f, 0.f, 0.f, 0.f); th[s] = tn[s]; tm[s] = make_float2(0.f, 0.f); tl[s] = 0;
-            if (inr[s]) {
-                const int qn = (int)(fx + fy * (float)W);
-                tn[s] = __ldg(&nrm_prev.p[owner_of(ro, qn / W)][qn]);
-                // in range => 0 <= lx < W and 0 <= ly < H, so the integer index of the history taps is in range as well
-                const int o2 = owner_of(ro, ly);
-                th[s] = __ldg(&hist_cv.p[o2][qi[s]]); tm[s] = __ldg(&mom_hist.p[o2][qi[s]]); tl[s] = __ldg(&hlen_tab.p[o2][qi[s]]);
-            }
-        }
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            const int gprev = __float_as_int(tn[s].w), gcur = __float_as_int(ncur.w);
-            v[s] = inr[s] && !(gprev == -1 || gprev != gcur) && !(dist3(tn[s].x, tn[s].y, tn[s].z, ncur.x, ncur.y, ncur.z) > 1e-1f);
+            const int lx = (int)((unsigned)ifx + (unsigned)(s & 1)), ly = (int)((unsigned)ify + (unsigned)(s >> 1));
+            qi[s] = 0;
+            v[s] = reprj_valid(W, H, (float)lx, (float)ly, ncur, nrm_prev, ro, qi[s]);
+            qi[s] = lx + ly * W;
             valid = valid && v[s];
         }
         float pr = 0.f, pg = 0.f, pb = 0.f, pm1 = 0.f, pm2 = 0.f, phl = 0.f;
@@ -109,9 +89,11 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 if (v[s]) {
-                    pr += w[s] * th[s].x; pg += w[s] * th[s].y; pb += w[s] * th[s].z;
-                    pm1 += w[s] * tm[s].x; pm2 += w[s] * tm[s].y;
-                    phl += w[s] * (float)tl[s];
+                    const int o = owner_of(ro, qi[s] / W);
+                    const float4 hc = __ldg(&hist_cv.p[o][qi[s]]); const float2 hm = __ldg(&mom_hist.p[o][qi[s]]);
+                    pr += w[s] * hc.x; pg += w[s] * hc.y; pb += w[s] * hc.z;
+                    pm1 += w[s] * hm.x; pm2 += w[s] * hm.y;
+                    phl += w[s] * (float)__ldg(&hlen_tab.p[o][qi[s]]);
                     sumw += w[s];
                 }
             }
@@ -170,7 +152,7 @@ struct TemporalPush {           // sharded frames: the neighbours' copies of the
     float4 *cv[SVGF_MAX_RANKS - 1]; float2 *lv[SVGF_MAX_RANKS - 1];
 };
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256)
 temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
                 const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
                 const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,

@@ -462,7 +462,7 @@ struct RtPush {
     float4 *gnp[SVGF_MAX_RANKS - 1]; float2 *gzl[SVGF_MAX_RANKS - 1];
 };
 
-template <int MINB>
+template <int MINB, bool PUSH>
 __global__ void __launch_bounds__(RT_BX *RT_BY, MINB)
 rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf_material *__restrict__ g_materials,
           int n_materials, const float4 *__restrict__ bvh, int n_nodes, const float4 *__restrict__ tri_hot,
@@ -540,7 +540,7 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
                 const float4 gnp = make_float4(is.n.x * P.kn, p.x * P.kx, is.n.y * P.kn, p.y * P.kx);
                 const float2 gzl = make_float2(is.n.z * P.kn, p.z * P.kx);
                 gnp_out[idx] = gnp; gzl_out[idx] = gzl;
-                if (push.peers.n > 0) {
+                if (PUSH) {     // compile-time: the single-GPU kernel carries none of this
                     unsigned m = halo_targets(push.peers, y);
                     if (m) {
                         for (; m; m &= m - 1) { const int i = __ffs(m) - 1; push.gnp[i][idx] = gnp; push.gzl[i][idx] = gzl; }
@@ -1042,21 +1042,23 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
         for (int i = 0; i < push.peers.n; i++) { push.gnp[i] = c->p_gnp.p[push.peers.rank[i]]; push.gzl[i] = c->p_gzl.p[push.peers.rank[i]]; }
         if (pushed) *pushed = true;
     }
-#define RT_LAUNCH(MINB)                                                                                                          \
+#define RT_LAUNCH(MINB, PUSH)                                                                                                    \
     do {                                                                                                                         \
         if (smem > 48 * 1024) {                                                                                                  \
-            cudaError_t e = cudaFuncSetAttribute(rt_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+            cudaError_t e = cudaFuncSetAttribute(rt_kernel<MINB, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                                      \
         }                                                                                                                        \
-        rt_kernel<MINB><<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes,   \
-                                                          s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, c->alb, c->image,  \
-                                                          c->stale_nm, c->stale_uv, c->gnp, c->gzl, push);                       \
+        rt_kernel<MINB, PUSH><<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh,        \
+                                                                s.n_nodes, s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos,   \
+                                                                c->alb, c->image, c->stale_nm, c->stale_uv, c->gnp, c->gzl, push); \
     } while (0)
     // Occupancy beats registers here: the kernel waits on dependent fp32 chains and BVH loads, so 8 blocks/SM (64 registers,
     // 84 B of spills) run 15-30 % faster than 4 blocks/SM (110 registers, none); 10 and 12 were slower again (measured on
     // B200: C2 0.93/0.80/0.86/0.89 ms, C3 3.73/2.82/2.85/2.92 ms for 4/8/10/12). SVGF_RT_MINBLOCKS=4 keeps the A/B.
     static const int minb = getenv("SVGF_RT_MINBLOCKS") ? atoi(getenv("SVGF_RT_MINBLOCKS")) : 8;
-    if (minb == 4) RT_LAUNCH(4); else RT_LAUNCH(8);
+    const bool do_push = push.peers.n > 0;
+    if (minb == 4) { if (do_push) RT_LAUNCH(4, true); else RT_LAUNCH(4, false); }
+    else { if (do_push) RT_LAUNCH(8, true); else RT_LAUNCH(8, false); }
 #undef RT_LAUNCH
     return cudaGetLastError();
 }

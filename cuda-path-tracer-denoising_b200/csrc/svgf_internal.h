@@ -121,12 +121,16 @@ struct svgf_ctx {
     float2 *lv[SVGF_NCV] = {nullptr, nullptr, nullptr, nullptr};
     // TMA descriptors (CUtensorMap, 128 B each) for the lattice tiles of cv[3], lv[3], gnp, gzl: [plane 8][level 1..7][shape 2]
     void *tmaps = nullptr; int tma_ok = 0;
+    void *tmaps_slide = nullptr;        // ... and of the sliding kernel: [plane][level]
     // sharded frames: 1 = every stage pushes the rows its neighbours will tap into their copy of the plane, levels read local
     // memory only (TMA tiles everywhere); 0 = levels read neighbours' rows in place over NVLink (SVGF_HALO=pull, A/B)
     int halo_push = 1;
     int atrous_variant = 2;             // 1 = direct (one thread per pixel), 2 = lattice-tiled (TMA tile loads), 3 = lattice-tiled (cp.async),
-                                        // 4 = lattice-tiled, symmetric two-phase pair arithmetic (atrous_pair_core.h)
-    bool atrous_attr_set = false, atrous_pair_attr_set = false;
+                                        // 4 = lattice-tiled, symmetric two-phase pair arithmetic (atrous_pair_core.h),
+                                        // 5 = sliding warps, symmetric pair arithmetic in registers (atrous_slide_core.h)
+    bool atrous_attr_set = false, atrous_pair_attr_set = false, atrous_slide_attr_set = false;
+    int atrous_slide_blocks_per_sm = 0, atrous_slide_sms = 148;
+    int atrous_slide_bands = 0;         // SVGF_ATROUS_BANDS: row bands per (class, strip) of the sliding kernel (0 = fill the warp slots once)
     // tile shape of the lattice-tiled kernel (index into atrous.cu's table): -1 = chosen per level by the cost model;
     // SVGF_ATROUS_SHAPE=<id> forces one for every level, SVGF_ATROUS_SHAPES=<id>,<id>,... one per level (A/B runs)
     int atrous_pair_rows = 2;           // SVGF_ATROUS_PAIR_ROWS: centre rows per thread in phase 2 of the pair kernel (1 = 256-thread blocks)
@@ -228,8 +232,8 @@ struct AtrousArgs {
     float *denoised_out; float *var_out;            // last level only (AoS vec3 + float plane)
     int level, is_last, blur_variance, addcolor;
     float sigma_c, sigma_n, sigma_x;
-    HaloIn wait;                                    // sharded frames: flags to see before halo rows are read (n == 0: none)
-    HaloOut ho;                                     // ... and who gets this level's edge rows and its flag
+    HaloIn wait{};                                  // sharded frames: flags to see before halo rows are read (n == 0: none)
+    HaloOut ho{};                                   // ... and who gets this level's edge rows and its flag
 };
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a);
 cudaError_t launch_cv_to_outputs(svgf_ctx *c, const float4 *cv, float *denoised, float *var_out);

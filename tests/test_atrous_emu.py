@@ -18,7 +18,7 @@ CSRC = os.path.join(ROOT, "cuda-path-tracer-denoising_b200", "csrc")
 
 def build_emu(name):
     src, lib = os.path.join(ROOT, "tests", "emu", name + ".cpp"), os.path.join(ROOT, "tests", "emu", "lib" + name + ".so")
-    hdrs = [os.path.join(CSRC, "atrous_pair_core.h"), os.path.join(CSRC, "atrous_tile_core.h")]
+    hdrs = [os.path.join(CSRC, "atrous_pair_core.h"), os.path.join(CSRC, "atrous_tile_core.h"), os.path.join(CSRC, "atrous_slide_core.h")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", src, "-o", lib], check=True)
     L = ctypes.CDLL(lib)
@@ -35,6 +35,11 @@ def emu():
 @pytest.fixture(scope="module")
 def tile_emu():
     return build_emu("tile_emu")
+
+
+@pytest.fixture(scope="module")
+def slide_emu():
+    return build_emu("slide_emu")
 
 
 def device_planes(color, var, g, P):
@@ -121,6 +126,35 @@ def test_emulated_production_kernel_strip(tile_emu):
     P = orc.default_params(blurvariance=0)
     oc, ov = orc.atrous_level(color, var, g, level, False, P)
     out = emu_level(tile_emu, color, var, g, level, P, 9, rows=(23, 52))
+    assert np.isnan(out[:23]).all() and np.isnan(out[52:]).all()
+    assert_close(out[23:52, :, 0:3], oc[23:52], COLOR_FLOOR, "strip colour")
+    assert_close(out[23:52, :, 3], ov[23:52], VAR_FLOOR, "strip variance")
+
+
+@pytest.mark.parametrize("bands", [1, 3])
+@pytest.mark.parametrize("case", [(96, 80, 1), (61, 45, 2), (50, 70, 4), (33, 17, 5), (5, 3, 1), (1, 1, 2), (130, 40, 7), (200, 36, 3), (26, 90, 1)])
+def test_emulated_sliding_kernel_matches_oracle(slide_emu, case, bands):
+    """csrc/atrous_slide_core.h: every unordered pair's distance computed by one lane and mirrored to the other (the shuffles are
+    emulated by reads of the other lane's registers), five centres in flight per lane through the five-phase register rotation,
+    rows staged like the TMA row loads stage them. `bands` is the `shape` argument of the other emulations."""
+    W, H, level = case
+    color, var, g = synthetic_planes(W, H, seed=500 + W + level)
+    if W > 60:
+        g[H // 4:H // 2, W // 3:W // 2, 0:3] = np.nan          # NaN normals get weight 1 (denoise.cu:144)
+    P = orc.default_params()
+    out = emu_level(slide_emu, color, var, g, level, P, bands)
+    assert np.isfinite(out).all(), "a pixel was not written"
+    oc, ov = orc.atrous_level(color, var, g, level, False, P)
+    assert_close(out[..., 0:3], oc, COLOR_FLOOR, "colour %dx%d L%d bands %d" % (case + (bands,)))
+    assert_close(out[..., 3], ov, VAR_FLOOR, "variance %dx%d L%d bands %d" % (case + (bands,)))
+
+
+def test_emulated_sliding_kernel_strip(slide_emu):
+    W, H, level = 72, 64, 2
+    color, var, g = synthetic_planes(W, H, seed=11)
+    P = orc.default_params(blurvariance=0)
+    oc, ov = orc.atrous_level(color, var, g, level, False, P)
+    out = emu_level(slide_emu, color, var, g, level, P, 2, rows=(23, 52))
     assert np.isnan(out[:23]).all() and np.isnan(out[52:]).all()
     assert_close(out[23:52, :, 0:3], oc[23:52], COLOR_FLOOR, "strip colour")
     assert_close(out[23:52, :, 3], ov[23:52], VAR_FLOOR, "strip variance")
