@@ -271,7 +271,7 @@ class Renderer:
         return a
 
     def set_option(self, name, value):
-        """Quality switches beyond the reference (all off by default): 'reprojection_fov_aspect', 'history_cap'."""
+        """Quality switches beyond the reference (all off by default): 'reprojection_fov_aspect', 'history_cap', 'spatial_variance_estimate', 'light_sampling_all'."""
         self._ck(lib().svgf_set_option(self.h, name.encode(), int(value)), "svgf_set_option(%s)" % name)
 
     def sync(self):

@@ -87,6 +87,21 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
             if (!(diag == diag) || g.type == 2) for (int i = 0; i < 3; i++) { o.aabb_min[i] = -3e38f; o.aabb_max[i] = 3e38f; }
         }
     }
+    {   // May a shadow query stop at the first occluder (pathtrace.cu: computeIntersection, light_query)? The answer "is geoms[0] the
+        // closest hit" is unchanged by that iff geoms[0] is a cube or a sphere and every triangle a traversal can return belongs to
+        // some MESH geom's id range (the closest-hit search ignores a closest triangle nobody owns). SVGF_RT_ANYHIT=0: A/B switch.
+        bool ok = d->geoms[0].type != 2 && !(getenv("SVGF_RT_ANYHIT") && atoi(getenv("SVGF_RT_ANYHIT")) == 0);
+        for (int i = 0; ok && i < d->n_triangles; i++) {
+            bool owned = false;
+            for (int g = 0; g < d->n_geoms && !owned; g++)
+                owned = d->geoms[g].type == 2 && d->triangles[i].id >= d->geoms[g].T_startidx && d->triangles[i].id < d->geoms[g].T_endidx;
+            ok = owned;
+        }
+        gd[0].pad_ = ok ? 1.0f : 0.0f;
+        c->n_lights = 0;
+        for (int g = 0; g < d->n_geoms && g < 32 && c->n_lights < 8; g++)
+            if (d->geoms[g].type != 2 && d->materials[d->geoms[g].materialid].emittance > 0.0f) c->lights[c->n_lights++] = g;
+    }
     s.n_geoms = d->n_geoms; s.n_materials = d->n_materials; s.n_nodes = d->n_bvh_nodes; s.n_tris = d->n_triangles; s.n_textures = d->n_textures;
     CK(dalloc(&s.geoms, gd.size()));
     CK(cudaMemcpy(s.geoms, gd.data(), gd.size() * sizeof(GeomD), cudaMemcpyHostToDevice));
@@ -255,6 +270,13 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_err = std::string("svgf_create: ") + cudaGetErrorString(e); delete c; return SVGF_ERR_CUDA; }
+    // CUDA loads a kernel's code at its first launch, which may need the device to go idle. A sharded frame launches kernels
+    // WHILE kernels of other ranks spin on flags that only later launches raise (the frame's first signal kernel, say), so a
+    // first launch in that situation deadlocks until the spin gives up. Load everything now, once per process and device.
+    {
+        static bool loaded[64] = {false};
+        if (device < 64 && !loaded[device]) { preload_pathtrace_kernels(); preload_denoise_kernels(); preload_atrous_kernels(); loaded[device] = true; }
+    }
     rc = upload_scene(c, scene);
     if (rc == SVGF_OK) rc = alloc_frame_buffers(c);
     if (rc == SVGF_OK) rc = svgf_reset(c);
@@ -447,6 +469,8 @@ int svgf_set_option(svgf_ctx *c, const char *name, int value) {
     if (!c || !name) return SVGF_ERR_INVALID;
     if (!strcmp(name, "reprojection_fov_aspect")) { c->opt_reprojection_fov_aspect = value != 0; return SVGF_OK; }
     if (!strcmp(name, "history_cap")) { if (value < 0) return SVGF_ERR_INVALID; c->opt_history_cap = value; return SVGF_OK; }
+    if (!strcmp(name, "light_sampling_all")) { c->opt_light_sampling_all = value != 0; return SVGF_OK; }
+    if (!strcmp(name, "spatial_variance_estimate")) { c->opt_spatial_variance = value != 0; return SVGF_OK; }
     c->err = std::string("svgf_set_option: unknown option '") + name + "'";
     return SVGF_ERR_UNKNOWN_NAME;
 }
@@ -538,6 +562,11 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
         CK(launch_temporal(c, image, c->nrm[c->cur_nrm], c->p_nrm[c->cur_nrm ^ 1], c->pos, c->p_cv[H_old], c->p_mom[c->cur_mom],
                            c->p_hlen[c->cur_hlen], acc, c->lv[acc_slot], c->mom[c->cur_mom ^ 1], c->hlen[c->cur_hlen ^ 1],
                            c->view_matrix_prev, color_alpha, moment_alpha, clip_rx, clip_ry, ho, c->p_cv[acc_slot], c->p_lv[acc_slot]));
+        if (c->opt_spatial_variance) {
+            // whole-frame contexts only: the estimate reads a 7x7 neighbourhood of moments that other ranks would still be writing
+            if (c->rows.world > 1 || c->shard.row_begin != 0 || c->shard.row_end != c->H) { c->err = "spatial_variance_estimate: single-GPU, whole-frame contexts only"; return SVGF_ERR_INVALID; }
+            CK(launch_spatial_variance(c, c->hlen[c->cur_hlen ^ 1], c->mom[c->cur_mom ^ 1], c->nrm[c->cur_nrm], acc, c->lv[acc_slot]));
+        }
     } else {
         CK(launch_no_temporal(c, image, acc, c->lv[acc_slot]));
         if (push) {
@@ -672,6 +701,8 @@ static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P
     rp.frame = frame; rp.max_depth = P->tracedepth; rp.trace_shadowray = P->shadowray; rp.reduce_var = P->reducevar;
     rp.denoise = P->denoise_enable; rp.sepcolor = P->sepcolor; rp.sintensity = P->sintensity; rp.lightradius = P->lightradius;
     atrous_scales(P->sigman, P->sigmax, &rp.kn, &rp.kx);
+    rp.n_lights = (c->opt_light_sampling_all && c->scene.geoms && c->n_lights > 1) ? c->n_lights : 0;
+    for (int i = 0; i < 8; i++) rp.lights[i] = c->lights[i];
     rp.cam = *cam;
     c->gbuf_nrm = c->cur_nrm;            // where this frame's normals/geomIds live (svgf_fetch("gbuffer"))
     const bool filter = P->denoise_enable && P->right_view_option == 0 && P->atrous_nlevel > 0 && P->spatial_enable;

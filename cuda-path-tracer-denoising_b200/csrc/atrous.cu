@@ -499,19 +499,20 @@ atrous_pair_kernel(const __grid_constant__ AtrousT t) {
 // ---------------------------------------------------------------------------------------------------------------
 // Sliding kernel (atrous_variant 5): the symmetric formulation with the pair distances in registers, csrc/atrous_slide_core.h.
 // Every WARP is its own pipeline: it owns a strip of 16 lattice columns x 2 sub-columns of one residue class and walks down a
-// band of lattice rows. Rows are staged one at a time into a private ring of SL_DEPTH slots by TMA -- a row of a residue class
-// is the box {2 pixels, 16 cells, 1, 1} of the 4-D view {s-pixel cell | cell | row in band | band} of the row-major plane
-// (4 copies of 512/512/256/256 bytes per row, issued by lane 0, completion on the slot's mbarrier) -- five rows ahead of their
-// use, so no lane ever waits for a tile and nobody synchronises across warps. Items (class, strip, band) are dealt to the
-// warps round-robin; launch_atrous_slide sizes the bands so that the items fill the resident warps once.
-constexpr int SL_DEPTH = 8, SL_WARPS = 4, SL_SLOT = SL_ROW * 48;         // bytes of one staged row: cv 512 | np 512 | zl 256 | lv 256
-constexpr int SL_SMEM = SL_WARPS * (SL_DEPTH * SL_SLOT + SL_DEPTH * 8);
+// band of lattice rows. Rows are staged two at a time into a private ring of SL_GROUPS groups by TMA -- two rows of a residue
+// class are the box {2 pixels, 16 cells, 1, 2} of the 4-D view {s-pixel cell | cell | row in band | band} of the row-major plane
+// (4 copies per group, issued by one lane, completion on the group's mbarrier) -- five to six rows ahead of their use, so no
+// lane waits for a tile and nobody synchronises across warps. Items (class, strip, band) are dealt to the warps round-robin;
+// launch_atrous_slide sizes the bands so that the items fill the resident warps once.
+constexpr int SL_GROUPS = 4, SL_WARPS = 4;
+constexpr int SL_GROUP_BYTES = 2 * SL_ROW * 48;         // cv r0 r1 (2 x 512) | np r0 r1 (2 x 512) | zl r0 r1 (2 x 256) | lv r0 r1 (2 x 256)
+constexpr int SL_RING_BYTES = SL_GROUPS * SL_GROUP_BYTES;
+constexpr int SL_SMEM = SL_WARPS * (SL_RING_BYTES + SL_GROUPS * 8);
 
 struct AtrousS {
     AtrousK k;
     SlGrid g;
     const float *kl;
-    int use_tma;
     HaloOut ho;
     float4 *cv_peer[SVGF_MAX_RANKS - 1]; float2 *lv_peer[SVGF_MAX_RANKS - 1];
     alignas(64) CUtensorMap tm_cv, tm_np, tm_zl, tm_lv;
@@ -529,10 +530,10 @@ __device__ __forceinline__ void sl_mbar_wait(unsigned long long *bar, unsigned p
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(sl_smem(bar)), "r"(parity) : "memory");
-        if (!done && ++spins > (1u << 22)) __trap();       // a row that never lands is a bug: fail the launch, do not hang the GPU
+        if (!done && ++spins > (1u << 22)) __trap();       // rows that never land are a bug: fail the launch, do not hang the GPU
     } while (!done);
 }
-__device__ __forceinline__ void sl_tma_row(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, unsigned long long *bar) {
+__device__ __forceinline__ void sl_tma_rows(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, unsigned long long *bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(sl_smem(dst)), "l"(tm), "r"(sl_smem(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
@@ -541,50 +542,61 @@ struct SlWarp {                     // what a warp knows about its current item
     unsigned char *ring; unsigned long long *bars;
     int lane, x, xv, need_fix;      // this lane's pixel column, is it inside the image, does the strip touch the image's edge
     int X0, yc, a0, b0;             // b0 = lattice row of staged row 0 of the item
-    unsigned g0;                    // rows staged by this warp before the item (slot and parity bookkeeping)
+    int ngroups;                    // groups of two staged rows of the item
+    unsigned g0;                    // groups staged by this warp before the item (slot and parity bookkeeping)
 };
 
-__device__ __forceinline__ SlRow sl_slot(const SlWarp &w, unsigned g) {
-    unsigned char *p = w.ring + (g % SL_DEPTH) * SL_SLOT;
-    SlRow r;
-    r.cv = reinterpret_cast<const float4 *>(p); r.np = reinterpret_cast<const float4 *>(p + 512);
-    r.zl = reinterpret_cast<const float2 *>(p + 1024); r.lv = reinterpret_cast<const float2 *>(p + 1280);
-    return r;
+// staged row r of the item: second half of a group for odd r
+__device__ __forceinline__ SlRow sl_row(const SlWarp &w, int r) {
+    unsigned char *p = w.ring + ((w.g0 + (unsigned)(r >> 1)) % SL_GROUPS) * SL_GROUP_BYTES;
+    const int q = r & 1;
+    SlRow o;
+    o.cv = reinterpret_cast<const float4 *>(p + q * 512); o.np = reinterpret_cast<const float4 *>(p + 1024 + q * 512);
+    o.zl = reinterpret_cast<const float2 *>(p + 2048 + q * 256); o.lv = reinterpret_cast<const float2 *>(p + 2560 + q * 256);
+    return o;
 }
 
-// Start the load of staged row r of the item (lattice row b0 + r) into its slot.
-__device__ __forceinline__ void sl_issue(const AtrousS &t, const SlWarp &w, int r) {
-    const unsigned g = w.g0 + (unsigned)r;
-    unsigned char *p = w.ring + (g % SL_DEPTH) * SL_SLOT;
-    const int b = w.b0 + r, step = t.k.step;
-    if (t.use_tma) {
+// Start the load of group gi of the item (staged rows 2 gi, 2 gi + 1 = lattice rows b0 + 2 gi, + 1) into its slot.
+template <bool TMA>
+__device__ __forceinline__ void sl_issue(const AtrousS &t, const SlWarp &w, int gi) {
+    const unsigned g = w.g0 + (unsigned)gi;
+    unsigned char *p = w.ring + (g % SL_GROUPS) * SL_GROUP_BYTES;
+    const int b = w.b0 + 2 * gi;
+    if (TMA) {
         if (w.lane == 0) {
-            unsigned long long *bar = w.bars + (g % SL_DEPTH);
-            sl_mbar_expect(bar, SL_SLOT);
-            sl_tma_row(p, &t.tm_cv, 4 * w.X0, w.a0, w.yc, b, bar);
-            sl_tma_row(p + 512, &t.tm_np, 4 * w.X0, w.a0, w.yc, b, bar);
-            sl_tma_row(p + 1024, &t.tm_zl, 2 * w.X0, w.a0, w.yc, b, bar);
-            sl_tma_row(p + 1280, &t.tm_lv, 2 * w.X0, w.a0, w.yc, b, bar);
+            unsigned long long *bar = w.bars + (g % SL_GROUPS);
+            sl_mbar_expect(bar, SL_GROUP_BYTES);
+            sl_tma_rows(p, &t.tm_cv, 4 * w.X0, w.a0, w.yc, b, bar);
+            sl_tma_rows(p + 1024, &t.tm_np, 4 * w.X0, w.a0, w.yc, b, bar);
+            sl_tma_rows(p + 2048, &t.tm_zl, 2 * w.X0, w.a0, w.yc, b, bar);
+            sl_tma_rows(p + 2560, &t.tm_lv, 2 * w.X0, w.a0, w.yc, b, bar);
         }
-    } else {        // odd widths (8-byte planes need a 16-byte pitch for TMA): every lane fetches its own entry
-        const int y = w.yc + b * step;
-        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), np = cv; float2 zl = make_float2(0.f, 0.f), lv = make_float2(3e38f, 0.f);
-        if (w.xv && b >= 0 && y < t.k.H) {
-            const size_t q = (size_t)w.x + (size_t)y * t.k.W;
-            cv = __ldg(&t.k.cv_in[q]); np = __ldg(&t.k.gnp[q]); zl = __ldg(&t.k.gzl[q]); lv = __ldg(&t.k.lv_in[q]);
+    } else {        // odd widths (8-byte planes need a 16-byte pitch for TMA): every lane fetches its own entries
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int y = w.yc + (b + q) * t.k.step;
+            float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), np = cv; float2 zl = make_float2(0.f, 0.f), lv = make_float2(3e38f, 0.f);
+            if (w.xv && b + q >= 0 && y < t.k.H) {
+                const size_t i = (size_t)w.x + (size_t)y * t.k.W;
+                cv = __ldg(&t.k.cv_in[i]); np = __ldg(&t.k.gnp[i]); zl = __ldg(&t.k.gzl[i]); lv = __ldg(&t.k.lv_in[i]);
+            }
+            reinterpret_cast<float4 *>(p + q * 512)[w.lane] = cv; reinterpret_cast<float4 *>(p + 1024 + q * 512)[w.lane] = np;
+            reinterpret_cast<float2 *>(p + 2048 + q * 256)[w.lane] = zl; reinterpret_cast<float2 *>(p + 2560 + q * 256)[w.lane] = lv;
         }
-        reinterpret_cast<float4 *>(p)[w.lane] = cv; reinterpret_cast<float4 *>(p + 512)[w.lane] = np;
-        reinterpret_cast<float2 *>(p + 1024)[w.lane] = zl; reinterpret_cast<float2 *>(p + 1280)[w.lane] = lv;
     }
 }
 
-// Staged row r has landed (and columns outside the image carry lum = 3e38, which zeroes every weight of such a tap).
-__device__ __forceinline__ void sl_wait(const AtrousS &t, const SlWarp &w, int r) {
-    const unsigned g = w.g0 + (unsigned)r;
-    if (t.use_tma) {
-        sl_mbar_wait(w.bars + (g % SL_DEPTH), (g / SL_DEPTH) & 1u);
+// Group gi has landed (and columns outside the image carry lum = 3e38, which zeroes every weight of such a tap).
+template <bool TMA>
+__device__ __forceinline__ void sl_wait(const SlWarp &w, int gi) {
+    const unsigned g = w.g0 + (unsigned)gi;
+    if (TMA) {
+        sl_mbar_wait(w.bars + (g % SL_GROUPS), (g / SL_GROUPS) & 1u);
         if (w.need_fix) {           // cells left of the image are zero-filled, cells right of it alias the next row
-            if (!w.xv) reinterpret_cast<float2 *>(w.ring + (g % SL_DEPTH) * SL_SLOT + 1280)[w.lane].x = 3e38f;
+            if (!w.xv) {
+                float2 *lv = reinterpret_cast<float2 *>(w.ring + (g % SL_GROUPS) * SL_GROUP_BYTES + 2560);
+                lv[w.lane].x = 3e38f; lv[SL_ROW + w.lane].x = 3e38f;
+            }
             __syncwarp();
         }
     } else {
@@ -592,31 +604,40 @@ __device__ __forceinline__ void sl_wait(const AtrousS &t, const SlWarp &w, int r
     }
 }
 
-template <int PHI>
-__device__ __forceinline__ void sl_step(const AtrousS &t, const SlWarp &w, SlLane &L, int rt, int rows, const int (&e)[5], float kl_enter) {
+// Sharded frames: rows a neighbour taps at the next level also go into its planes (halo_sync.cuh). Out of line: the single-GPU
+// path should not carry this code in its five step bodies.
+__device__ __noinline__ void sl_halo_store(const AtrousS &t, bool ok, int yo, int p, float4 c, float2 lvo) {
+    if (!ok) return;
+    for (unsigned m = halo_targets(t.ho.peers, yo); m; m &= m - 1) {
+        const int i = __ffs(m) - 1;
+        t.cv_peer[i][p] = c; t.lv_peer[i][p] = lvo;
+    }
+}
+
+// One step: tap row rt of the item (pixel row y_t) against the five centres in flight.
+template <int PHI, bool TMA, bool LAST>
+__device__ __forceinline__ void sl_step(const AtrousS &t, const SlWarp &w, SlLane &L, int rt, int rows, int y_t, const int (&e)[5], float kl_enter,
+                                        bool interior) {
     constexpr int KE = sl_set(PHI, 2), KX = sl_set(PHI, -2);
     const AtrousK &k = t.k;
-    // the centre two rows below the tap row enters flight
-    sl_wait(t, w, rt + 2);
-    sl_enter<KE>(L, sl_slot(w, w.g0 + rt + 2), w.lane, kl_enter);
-    const int b = w.b0 + rt, y = w.yc + b * k.step;
-    if (b >= 0 && y < k.H) {        // tap rows outside the image have no pairs (warp-uniform)
-        const SlRow row = sl_slot(w, w.g0 + rt);
+    // the centre two rows below the tap row enters flight; its group is new on even steps
+    if (!(rt & 1)) sl_wait<TMA>(w, (rt >> 1) + 1);
+    sl_enter<KE>(L, sl_row(w, rt + 2), w.lane, kl_enter);
+    if (y_t >= 0 && y_t < k.H) {        // tap rows outside the image have no pairs (warp-uniform)
+        const SlRow row = sl_row(w, rt);
         // what the lanes owning the neighbouring columns hold for this lane's centres above the tap row (registers written one
         // and two steps ago: the shuffles depend on nothing in this step)
         float r1[5], r2[5], s[2], bk[2];
-#pragma unroll
-        for (int ti = 0; ti < 5; ti++) {
-            const int i = ti - 2;
-            if (i == 0) { r1[2] = sl_offer_r1<PHI>(L, 0); r2[2] = sl_offer_r2<PHI>(L, 0); continue; }
-            r1[ti] = __shfl_sync(0xffffffffu, sl_offer_r1<PHI>(L, i), w.lane + 2 * i);
-            r2[ti] = __shfl_sync(0xffffffffu, sl_offer_r2<PHI>(L, i), w.lane + 2 * i);
-        }
+        r1[2] = sl_offer_r1<PHI>(L, 0); r2[2] = sl_offer_r2<PHI>(L, 0);
+        r1[0] = __shfl_up_sync(0xffffffffu, sl_offer_r1<PHI>(L, -2), 4); r2[0] = __shfl_up_sync(0xffffffffu, sl_offer_r2<PHI>(L, -2), 4);
+        r1[1] = __shfl_up_sync(0xffffffffu, sl_offer_r1<PHI>(L, -1), 2); r2[1] = __shfl_up_sync(0xffffffffu, sl_offer_r2<PHI>(L, -1), 2);
+        r1[3] = __shfl_down_sync(0xffffffffu, sl_offer_r1<PHI>(L, 1), 2); r2[3] = __shfl_down_sync(0xffffffffu, sl_offer_r2<PHI>(L, 1), 2);
+        r1[4] = __shfl_down_sync(0xffffffffu, sl_offer_r1<PHI>(L, 2), 4); r2[4] = __shfl_down_sync(0xffffffffu, sl_offer_r2<PHI>(L, 2), 4);
         {   // same-row pairs: to the right computed, to the left received
             const SlTap t3 = sl_load_tap(row, e[3]), t4 = sl_load_tap(row, e[4]);
             sl_same_row<PHI>(L, t3, t4, s);
-            bk[0] = __shfl_sync(0xffffffffu, s[0], w.lane - 2);
-            bk[1] = __shfl_sync(0xffffffffu, s[1], w.lane - 4);
+            bk[0] = __shfl_up_sync(0xffffffffu, s[0], 2);
+            bk[1] = __shfl_up_sync(0xffffffffu, s[1], 4);
             sl_tap<PHI, 3>(L, t3, r1[3], r2[3], s[0]);
             sl_tap<PHI, 4>(L, t4, r1[4], r2[4], s[1]);
         }
@@ -624,55 +645,64 @@ __device__ __forceinline__ void sl_step(const AtrousS &t, const SlWarp &w, SlLan
         sl_tap<PHI, 1>(L, sl_load_tap(row, e[1]), r1[1], r2[1], bk[0]);
         sl_tap<PHI, 0>(L, sl_load_tap(row, e[0]), r1[0], r2[0], bk[1]);
     }
-    // the centre two rows above the tap row is complete
-    const int bo = b - 2, yo = w.yc + bo * k.step;
-    const int a = w.lane >> 1;
-    if (rt >= 4 && rt < rows + 4 && a >= SL_EDGE && a < SL_COLS - SL_EDGE && w.x < k.W && yo >= k.row_begin && yo < k.row_end) {
+    // the centre two rows above the tap row is complete: straight-line arithmetic, predicated stores
+    {
+        const int yo = y_t - 2 * k.step;
+        const bool ok = rt >= 4 && interior && w.x < k.W && yo >= k.row_begin && yo < k.row_end;
         const SlAccS o = sl_exit<KX>(L);
         // sum w >= h(0,0) always (the centre tap), so the reference's `else` branch (denoise.cu:162-164) is dead
         const float rw = __frcp_rn(o.w);
         float4 c = make_float4(o.r * rw, o.g * rw, o.b * rw, __fdividef(o.v, o.w2));
-        const int p = w.x + yo * k.W;
-        if (k.is_last) {
+        const int p = ok ? w.x + yo * k.W : 0;
+        if (LAST) {
             if (k.addcolor) { const float4 al = __ldg(&k.alb[p]); c.x *= al.x; c.y *= al.y; c.z *= al.z; }
-            float *d = k.denoised_out + 3 * (size_t)p;
-            d[0] = c.x; d[1] = c.y; d[2] = c.z;
-            k.var_out[p] = c.w;
-        }
-        if (k.cv_out) {
-            const float2 lvo = make_float2(lum_ref(c.x, c.y, c.z), c.w);
-            k.cv_out[p] = c; k.lv_out[p] = lvo;
-            for (unsigned m = halo_targets(t.ho.peers, yo); m; m &= m - 1) {       // rows a neighbour taps at the next level
-                const int i = __ffs(m) - 1;
-                t.cv_peer[i][p] = c; t.lv_peer[i][p] = lvo;
+            if (ok) {
+                float *d = k.denoised_out + 3 * (size_t)p;
+                d[0] = c.x; d[1] = c.y; d[2] = c.z;
+                k.var_out[p] = c.w;
             }
         }
+        if (!LAST || k.cv_out) {
+            const float2 lvo = make_float2(lum_ref(c.x, c.y, c.z), c.w);
+            if (ok) {
+                k.cv_out[p] = c; k.lv_out[p] = lvo;
+            }
+            if (t.ho.peers.n) sl_halo_store(t, ok, yo, p, c, lvo);       // sharded frames only (warp-uniform)
+        }
     }
-    // tap row rt is not read again: its slot takes the row SL_DEPTH further down
-    __syncwarp();
-    if (rt + SL_DEPTH < rows + 6) sl_issue(t, w, rt + SL_DEPTH);
+    // both rows of the tap row's group are done after an odd step: its slot takes the group SL_GROUPS further down
+    if (rt & 1) {
+        __syncwarp();
+        if ((rt >> 1) + SL_GROUPS < w.ngroups) sl_issue<TMA>(t, w, (rt >> 1) + SL_GROUPS);
+    }
 }
 
+template <bool TMA, bool LAST>
 __global__ void __launch_bounds__(SL_WARPS * 32, 3)
 atrous_slide_kernel(const __grid_constant__ AtrousS t) {
     extern __shared__ __align__(1024) unsigned char sl_smem_raw[];
     const AtrousK &k = t.k;
     SlWarp w;
-    const int wid = threadIdx.x >> 5;
+    // (the shuffle tells the compiler that the warp index -- and with it every item parameter, ring address and TMA coordinate
+    // derived from it -- is uniform across the warp, so they live in uniform registers instead of being broadcast lane by lane)
+    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     w.lane = threadIdx.x & 31;
-    w.ring = sl_smem_raw + wid * (SL_DEPTH * SL_SLOT);
-    w.bars = reinterpret_cast<unsigned long long *>(sl_smem_raw + SL_WARPS * SL_DEPTH * SL_SLOT) + wid * SL_DEPTH;
-    if (w.lane == 0) {
-        for (int i = 0; i < SL_DEPTH; i++) sl_mbar_init(w.bars + i);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    w.ring = sl_smem_raw + wid * SL_RING_BYTES;
+    w.bars = reinterpret_cast<unsigned long long *>(sl_smem_raw + SL_WARPS * SL_RING_BYTES) + wid * SL_GROUPS;
+    if (TMA) {
+        if (w.lane == 0) {
+            for (int i = 0; i < SL_GROUPS; i++) sl_mbar_init(w.bars + i);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
     }
-    __syncwarp();
     w.g0 = 0;
     int e[5];
 #pragma unroll
     for (int ti = 0; ti < 5; ti++) e[ti] = min(max(w.lane + 2 * (ti - 2), 0), SL_ROW - 1);       // edge lanes: any entry, their sums are dropped
     const int items = t.g.items(), a = w.lane >> 1, c = w.lane & 1;
+    const bool interior = a >= SL_EDGE && a < SL_COLS - SL_EDGE;
     for (int n = blockIdx.x * SL_WARPS + wid; n < items; n += gridDim.x * SL_WARPS) {
         const SlItem it = t.g.item(n);
         const int rows = it.b_hi - it.b_lo;             // centre rows of the band; staged rows: rows + 6, steps: rows + 4
@@ -681,31 +711,30 @@ atrous_slide_kernel(const __grid_constant__ AtrousS t) {
         w.x = it.X0 + (it.a0 + a) * k.step + c;
         w.xv = (it.a0 + a >= 0) && (w.x < k.W);
         w.need_fix = (it.a0 < 0) || (it.X0 + (it.a0 + SL_COLS - 1) * k.step + 1 >= k.W);
-        const int staged = rows + 6;
-        for (int r = 0; r < SL_DEPTH - 1 && r < staged; r++) sl_issue(t, w, r);
+        w.ngroups = (rows + 7) >> 1;
+        for (int gi = 0; gi < SL_GROUPS && gi < w.ngroups; gi++) sl_issue<TMA>(t, w, gi);
         SlLane L;
         memset(&L, 0, sizeof(L));
-        // luminance-weight scale of the centres, fetched two steps before they enter flight
-        auto kl_of = [&](int r) -> float {              // staged row r
-            const int y = w.yc + (w.b0 + r) * k.step;
-            return (w.xv && w.b0 + r >= 0 && y < k.H) ? __ldg(&t.kl[w.x + (size_t)y * k.W]) : 0.f;
-        };
-        float q0 = kl_of(2), q1 = kl_of(3);
-        sl_wait(t, w, 0); sl_enter<0>(L, sl_slot(w, w.g0 + 0), w.lane, kl_of(0));
-        sl_wait(t, w, 1); sl_enter<1>(L, sl_slot(w, w.g0 + 1), w.lane, kl_of(1));
+        // luminance-weight scale of the centres (pre-pass), requested two steps before they enter flight
+        int y_t = w.yc + w.b0 * k.step;                 // pixel row of tap row 0
+        auto kl_at = [&](int y) -> float { return (w.xv && y >= 0 && y < k.H) ? __ldg(&t.kl[w.x + (size_t)y * k.W]) : 0.f; };
+        float q0 = kl_at(y_t + 2 * k.step), q1 = kl_at(y_t + 3 * k.step);
+        sl_wait<TMA>(w, 0);
+        sl_enter<0>(L, sl_row(w, 0), w.lane, kl_at(y_t));
+        sl_enter<1>(L, sl_row(w, 1), w.lane, kl_at(y_t + k.step));
         const int steps = rows + 4;
         for (int rt = 0; rt < steps; rt += 5) {
             // five steps = one turn of the register rotation. The centre entering at step r lies in staged row r + 2; its kl is
             // requested two steps earlier and waits in q0/q1.
             float kq;
-            kq = q0; q0 = kl_of(rt + 4); sl_step<0>(t, w, L, rt, rows, e, kq);
-            if (rt + 1 < steps) { kq = q1; q1 = kl_of(rt + 5); sl_step<1>(t, w, L, rt + 1, rows, e, kq); }
-            if (rt + 2 < steps) { kq = q0; q0 = kl_of(rt + 6); sl_step<2>(t, w, L, rt + 2, rows, e, kq); }
-            if (rt + 3 < steps) { kq = q1; q1 = kl_of(rt + 7); sl_step<3>(t, w, L, rt + 3, rows, e, kq); }
-            if (rt + 4 < steps) { kq = q0; q0 = kl_of(rt + 8); sl_step<4>(t, w, L, rt + 4, rows, e, kq); }
+            kq = q0; q0 = kl_at(y_t + 4 * k.step); sl_step<0, TMA, LAST>(t, w, L, rt, rows, y_t, e, kq, interior); y_t += k.step;
+            if (rt + 1 < steps) { kq = q1; q1 = kl_at(y_t + 4 * k.step); sl_step<1, TMA, LAST>(t, w, L, rt + 1, rows, y_t, e, kq, interior); y_t += k.step; }
+            if (rt + 2 < steps) { kq = q0; q0 = kl_at(y_t + 4 * k.step); sl_step<2, TMA, LAST>(t, w, L, rt + 2, rows, y_t, e, kq, interior); y_t += k.step; }
+            if (rt + 3 < steps) { kq = q1; q1 = kl_at(y_t + 4 * k.step); sl_step<3, TMA, LAST>(t, w, L, rt + 3, rows, y_t, e, kq, interior); y_t += k.step; }
+            if (rt + 4 < steps) { kq = q0; q0 = kl_at(y_t + 4 * k.step); sl_step<4, TMA, LAST>(t, w, L, rt + 4, rows, y_t, e, kq, interior); y_t += k.step; }
             kq = q0; q0 = q1; q1 = kq;
         }
-        w.g0 += (unsigned)staged;
+        w.g0 += (unsigned)w.ngroups;
     }
     halo_block_done(t.ho);
 }
@@ -808,7 +837,7 @@ int atrous_build_tensor_maps(svgf_ctx *c) {
 }
 
 // Tensor maps of the sliding kernel: one per (plane, level), 4-D {floats of an s-pixel cell | cell | row in band | band}; a staged
-// row is the box {2 pixels, SL_COLS cells, 1, 1}. Same rounding-up of the extents (and the same padding behind the planes) as above.
+// pair of rows is the box {2 pixels, SL_COLS cells, 1, 2}. Same rounding-up of the extents (and the same padding behind the planes) as above.
 static inline CUtensorMap *tmap_slide(svgf_ctx *c, int plane, int level) {
     return static_cast<CUtensorMap *>(c->tmaps_slide) + (plane * TM_LEVELS + level);
 }
@@ -823,7 +852,7 @@ static int atrous_build_slide_maps(svgf_ctx *c, encode_fn_t encode) {
             const cuuint64_t s = 1ull << level, W = c->W, H = c->H, f = fpp[pl];
             const cuuint64_t dims[4] = {f * s, (W + s - 1) / s, s, (H + s - 1) / s};
             const cuuint64_t strides[3] = {f * 4 * s, f * 4 * W, f * 4 * s * W};
-            const cuuint32_t box[4] = {(cuuint32_t)(f * 2), (cuuint32_t)SL_COLS, 1, 1};
+            const cuuint32_t box[4] = {(cuuint32_t)(f * 2), (cuuint32_t)SL_COLS, 1, 2};
             const cuuint32_t estr[4] = {1, 1, 1, 1};
             CUresult r = encode(tmap_slide(c, pl, level), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, planes[pl], dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -897,15 +926,20 @@ static cudaError_t launch_atrous_slide(svgf_ctx *c, const AtrousK &k, const Atro
         t.cv_peer[i] = on ? c->p_cv[a.dst_slot].p[a.ho.peers.rank[i]] : nullptr;
         t.lv_peer[i] = on ? c->p_lv[a.dst_slot].p[a.ho.peers.rank[i]] : nullptr;
     }
-    t.use_tma = c->tma_ok && a.src_slot >= 0;
-    if (t.use_tma) {
+    const bool use_tma = c->tma_ok && a.src_slot >= 0;
+    if (use_tma) {
         t.tm_cv = *tmap_slide(c, a.src_slot, a.level); t.tm_lv = *tmap_slide(c, SVGF_NCV + a.src_slot, a.level);
         t.tm_np = *tmap_slide(c, 2 * SVGF_NCV, a.level); t.tm_zl = *tmap_slide(c, 2 * SVGF_NCV + 1, a.level);
     }
+    const void *fns[4] = {(const void *)atrous_slide_kernel<false, false>, (const void *)atrous_slide_kernel<false, true>,
+                          (const void *)atrous_slide_kernel<true, false>, (const void *)atrous_slide_kernel<true, true>};
     if (!c->atrous_slide_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(atrous_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(atrous_slide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->atrous_slide_blocks_per_sm, atrous_slide_kernel, SL_WARPS * 32, SL_SMEM);
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < 4 && e == cudaSuccess; i++) {
+            e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->atrous_slide_blocks_per_sm, atrous_slide_kernel<true, false>, SL_WARPS * 32, SL_SMEM);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         c->atrous_slide_sms = sms;
@@ -928,8 +962,20 @@ static cudaError_t launch_atrous_slide(svgf_ctx *c, const AtrousK &k, const Atro
     g.bands = (lat_rows + g.band_rows - 1) / g.band_rows;
     const int items = g.items();
     const int blocks = std::min((items + SL_WARPS - 1) / SL_WARPS, slots / SL_WARPS);
-    atrous_slide_kernel<<<std::max(blocks, 1), SL_WARPS * 32, SL_SMEM, c->stream>>>(t);
+    const dim3 grid(std::max(blocks, 1)), block(SL_WARPS * 32);
+    if (use_tma) { if (k.is_last) atrous_slide_kernel<true, true><<<grid, block, SL_SMEM, c->stream>>>(t); else atrous_slide_kernel<true, false><<<grid, block, SL_SMEM, c->stream>>>(t); }
+    else { if (k.is_last) atrous_slide_kernel<false, true><<<grid, block, SL_SMEM, c->stream>>>(t); else atrous_slide_kernel<false, false><<<grid, block, SL_SMEM, c->stream>>>(t); }
     return cudaGetLastError();
+}
+
+void preload_atrous_kernels() {
+    cudaFuncAttributes a;
+    for (int s = 0; s < AT_NSHAPES; s++) cudaFuncGetAttributes(&a, g_at_shapes[s].fn);
+    cudaFuncGetAttributes(&a, atrous_kl_kernel); cudaFuncGetAttributes(&a, atrous_direct_kernel); cudaFuncGetAttributes(&a, atrous_slide_kernel<true, false>); cudaFuncGetAttributes(&a, atrous_slide_kernel<true, true>);
+    cudaFuncGetAttributes(&a, atrous_slide_kernel<false, false>); cudaFuncGetAttributes(&a, atrous_slide_kernel<false, true>);
+    cudaFuncGetAttributes(&a, atrous_pair_kernel<16, 16, 2, 3>); cudaFuncGetAttributes(&a, atrous_pair_kernel<16, 16, 1, 3>);
+    cudaFuncGetAttributes(&a, atrous_pair_kernel<16, 12, 2, 3>); cudaFuncGetAttributes(&a, atrous_pair_kernel<16, 12, 1, 3>);
+    (void)cudaGetLastError();
 }
 
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {

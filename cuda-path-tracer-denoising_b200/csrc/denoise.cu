@@ -175,6 +175,40 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
     halo_block_done(push.ho);
 }
 
+// SURVEY.md 8(f) N4, "spatial_variance_estimate" (off by default). The reference's EstimateVariance is a stub (denoise.cu:320-329
+// writes 10.0) and BackProjection gives a pixel without history the constant 100 (denoise.cu:315), so freshly disoccluded
+// regions are filtered with a luminance weight that is switched off. With the option, a pixel whose history is shorter than
+// 4 frames takes its variance from the luminance moments of its 7x7 neighbourhood on the same surface (same geomId, normals
+// within ~10 degrees), boosted by 4 / history length -- the estimate of the SVGF paper (Schied et al. 2017, section 4.2).
+// Reads moments / normals / history lengths, writes only the pixel's own variance: no ordering between threads is needed.
+__global__ void __launch_bounds__(256)
+spatial_variance_kernel(int W, int H, const int *__restrict__ hlen, const float2 *__restrict__ mom, const float4 *__restrict__ nrm,
+                        float4 *__restrict__ cv, float2 *__restrict__ lv) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int p = x + y * W;
+    const int h = hlen[p];
+    const float4 nc = nrm[p];
+    if (h >= 4 || __float_as_int(nc.w) == -1) return;
+    float sw = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int dy = -3; dy <= 3; dy++)
+        for (int dx = -3; dx <= 3; dx++) {
+            const int qx = x + dx, qy = y + dy;
+            if (qx < 0 || qy < 0 || qx >= W || qy >= H) continue;
+            const int q = qx + qy * W;
+            const float4 nq = nrm[q];
+            if (__float_as_int(nq.w) != __float_as_int(nc.w)) continue;
+            const float d = nc.x * nq.x + nc.y * nq.y + nc.z * nq.z;
+            if (!(d > 0.985f)) continue;
+            const float2 m = mom[q];
+            sw += 1.f; s1 += m.x; s2 += m.y;
+        }
+    if (sw < 2.f) return;       // nothing but the pixel itself: keep the reference's value
+    const float m1 = s1 / sw, m2 = s2 / sw;
+    const float var = fmaxf(m2 - m1 * m1, 0.f) * (4.0f / (float)max(h, 1));
+    cv[p].w = var; lv[p].y = var;
+}
+
 __global__ void __launch_bounds__(256)
 no_temporal_kernel(int W, int row_begin, int row_end, const float *__restrict__ image, float4 *__restrict__ acc_cv,
                    float2 *__restrict__ acc_lv) {
@@ -306,6 +340,16 @@ inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (
 
 }  // namespace
 
+void preload_denoise_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, temporal_kernel); cudaFuncGetAttributes(&a, no_temporal_kernel); cudaFuncGetAttributes(&a, spatial_variance_kernel);
+    cudaFuncGetAttributes(&a, pack_pbo_kernel); cudaFuncGetAttributes(&a, debug_view_kernel); cudaFuncGetAttributes(&a, cv_to_outputs_kernel);
+    cudaFuncGetAttributes(&a, aos_to_soa_kernel); cudaFuncGetAttributes(&a, soa_to_aos_kernel); cudaFuncGetAttributes(&a, copy_f3_kernel);
+    cudaFuncGetAttributes(&a, signal_kernel); cudaFuncGetAttributes(&a, wait_kernel);
+    cudaFuncGetAttributes(&a, halo_push_kernel<uint4>); cudaFuncGetAttributes(&a, halo_push_kernel<uint2>);
+    (void)cudaGetLastError();
+}
+
 // Ranks whose strips lie within `reach` rows of this rank's strip, with the rows of MY strip each of them taps.
 HaloPeers halo_peers(const svgf_ctx *c, int reach) {
     HaloPeers h; h.n = 0;
@@ -354,6 +398,12 @@ cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_c
     temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
                                                                  nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lv, mom_acc,
                                                                  hlen_out, vm, color_alpha, moment_alpha, clip_rx, clip_ry, c->opt_history_cap, push);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_spatial_variance(svgf_ctx *c, const int *hlen, const float2 *mom, const float4 *nrm, float4 *cv, float2 *lv) {
+    dim3 b(32, 8);
+    spatial_variance_kernel<<<grid2d(c->W, c->H, b), b, 0, c->stream>>>(c->W, c->H, hlen, mom, nrm, cv, lv);
     return cudaGetLastError();
 }
 

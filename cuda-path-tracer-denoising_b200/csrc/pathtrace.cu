@@ -128,8 +128,32 @@ __device__ __forceinline__ F3 sphere_normal(const GeomD &sphere, F3 osi, bool ou
     return outside ? n : -n;
 }
 
+// A Geom record in shared memory. In the exact-test loop every lane reads the SAME field of a DIFFERENT geom; at the record's
+// natural 256-byte stride all those words share one bank (ncu: 32 % of the kernel's shared-memory wavefronts were conflicts).
+// 16 bytes of padding per record (68-word stride) rotate the records by four banks each -- a 16-byte matrix row of eight
+// different geoms is conflict-free -- and keep the 16-byte alignment the compiler's LDS.128 of the matrices relies on (a
+// 65-word stride was measured first: it forced scalar loads and DOUBLED the kernel time).
+struct alignas(16) GeomS : GeomD { int bank_pad_[4]; };
+static_assert(sizeof(GeomS) == 272, "GeomS");
+
+// Copies the scene tables into shared memory (all threads of the block; caller synchronises).
+__device__ __forceinline__ void stage_scene(unsigned char *smem, const GeomD *g_geoms, int n_geoms, const svgf_material *g_materials,
+                                            int n_materials, int tid, int nt, GeomS *&s_geoms, svgf_material *&s_mats) {
+    s_geoms = reinterpret_cast<GeomS *>(smem);
+    s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomS) * n_geoms);
+    const int gw = sizeof(GeomD) / 4 * n_geoms, mw = sizeof(svgf_material) / 4 * n_materials;
+    const int *src = reinterpret_cast<const int *>(g_geoms); int *dst = reinterpret_cast<int *>(s_geoms);
+    for (int i = tid; i < gw; i += nt) dst[(i >> 6) * 68 + (i & 63)] = src[i];
+    src = reinterpret_cast<const int *>(g_materials); dst = reinterpret_cast<int *>(s_mats);
+    for (int i = tid; i < mw; i += nt) dst[i] = src[i];
+}
+__host__ __device__ inline size_t scene_smem_bytes(int n_geoms, int n_materials) { return sizeof(GeomS) * n_geoms + sizeof(svgf_material) * n_materials; }
+
 struct SceneView {
-    const GeomD *geoms; int n_geoms;            // shared memory
+    // The shadow query may stop at the first occluder (see computeIntersection) when geoms[0] is a cube or a sphere and every
+    // triangle belongs to a MESH geom's range (always so for scenes of the reference's loader; checked at upload).
+    bool light_query_ok;
+    const GeomS *geoms; int n_geoms;            // shared memory
     const svgf_material *materials;             // shared memory
     const float4 *bvh; int n_nodes;
     const float4 *tri_hot, *tri_cold;
@@ -144,7 +168,10 @@ struct TriBest { float t, bx, by; int slot; };
 // slab entry lies beyond it -- or beyond the closest triangle found so far -- are skipped. The reference visits them
 // (no t-culling in AABBIntersect2) and then discards what it finds there: a triangle inside a node cannot be hit before
 // the ray enters the node's box, so with a conservative margin the closest triangle is the same.
-__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, float t_bound, TriBest &best) {
+// `t_any` > 0: occlusion query -- return at the first triangle hit strictly in front of t_any (0 < t < t_any); which one is
+// irrelevant to the caller. (The closest-hit search would reject the mesh if its CLOSEST triangle sat at exactly t == 0; that
+// this differs needs a triangle hit at exactly 0 and another one before t_any on the same ray.)
+__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, float t_bound, TriBest &best, float t_any = 0.f) {
     if (sc.n_nodes == 0) return false;
     bool hit = false;
     const int neg[3] = {ray.direction.x < 0.f, ray.direction.y < 0.f, ray.direction.z < 0.f};
@@ -185,6 +212,7 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
                     if (!(bz >= 0.0f)) continue;
                     hit = true;
                     if (bz < best.t) { best.t = bz; best.bx = bx; best.by = by; best.slot = slot; }
+                    if (bz > 0.0f && bz < t_any) return true;
                 }
                 if (top == 0) break;
                 cur = stack[--top];
@@ -214,7 +242,18 @@ struct Isect {      // the live part of ShadeableIntersection (sceneStructs.h:10
 // spheres its own ray can reach (slab test against conservative world bounds), then pops them one by one, so in every trip
 // of the exact-test loops all lanes are busy -- each with a different geom. The tie rule is applied explicitly, so the
 // winner is the reference's. Normals are computed for the winner only.
-__device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &is) {
+//
+// `light_query`: the shadow ray of pathtrace.cu:358-384 only asks "is geoms[0], the light, the closest hit?" (lightIdx == 0;
+// geom 0 wins every tie by index). For such a query the light is tested FIRST -- a miss answers the question -- and its
+// distance then bounds everything else: candidates entered beyond it are dropped by the bounds test, and the first hit strictly
+// in front of it ends the query (an any-hit search instead of a closest-hit one; no normal is computed). The answer to the
+// question, and with it every output bit, is the reference's. The flag is per-lane DATA, so path and shadow queries still
+// share the one call site.
+// `light` < 0: path query. >= 0: light query for that geom (0 in the reference; any emissive cube/sphere under the
+// "light_sampling_all" option, where a geom of LOWER index at exactly the light's distance wins the tie as in the closest-hit
+// search; the measure-zero tie between the light and a triangle is not reproduced there).
+__device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &is, int light) {
+    const bool lq = light >= 0 && light < 32 && sc.light_query_ok;
     float t_min = FLT_MAX;
     int hit_geom = -1;
     // what the winner's deferred normal needs
@@ -253,6 +292,10 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
         // neither beat nor tie t_min (margin far above rounding). The reference tests them and discards the result; the
         // explicit tie rule below makes the winner independent of the order.
         unsigned cand = cubes | spheres;
+        if (lq && base == 0) {
+            if (!((cand >> light) & 1u)) { is.t = -1.0f; is.geomId = -1; return false; }        // the ray misses the light's bounds
+            near_j = light;
+        }
         while (true) {
             int j = -1;
             while (cand) {      // next candidate that can still matter (cheap; lanes reconverge before the exact test)
@@ -279,10 +322,20 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
             const bool is_cube = (cubes >> j) & 1u;
             float tobj = 0.f; int axis = 0; float sign = 0.f; bool outside = true;
             const bool ok = is_cube ? box_slabs(q, tobj, axis, sign) : sphere_roots(q, tobj, outside);
-            if (!ok) continue;
+            if (!ok) {
+                if (lq && i == light) { is.t = -1.0f; is.geomId = -1; return false; }
+                continue;
+            }
             const F3 osi = getPointOnRay(q, tobj);
             const F3 ip = multiplyMV(g.transform, osi, 1.0f);
             const float t = length(ray.origin - ip);
+            if (lq) {
+                if (i == light) {
+                    if (!(t > 0.0f)) { is.t = -1.0f; is.geomId = -1; return false; }
+                    t_min = t; hit_geom = light;
+                } else if (t > 0.0f && (t < t_min || (t == t_min && i < light))) { is.t = -1.0f; is.geomId = -1; return false; }     // occluded
+                continue;
+            }
             if (t > 0.0f && (t < t_min || (t == t_min && i < hit_geom))) {
                 t_min = t; hit_geom = i; w_kind = is_cube ? 1 : 0; w_axis = axis; w_sign = sign; w_osi = osi; w_outside = outside;
             }
@@ -293,6 +346,11 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
     // sphere cannot win (margin for the tie rule), which bounds the traversal.
     float mesh_u = 0.f, mesh_v = 0.f; int mesh_owner = -1;
     TriBest tb; tb.t = FLT_MAX; tb.slot = -1; tb.bx = tb.by = 0.f;
+    if (lq) {       // the light is hit at t_min; a triangle in front of it?
+        if (any_mesh && intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb, t_min)) { is.t = -1.0f; is.geomId = -1; return false; }
+        is.t = t_min; is.geomId = light; is.materialId = sc.geoms[light].materialid;     // normal and uv are not read by the caller
+        return true;
+    }
     if (any_mesh && intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb)) {
         const int tri_id = __float_as_int(__ldg(&sc.tri_hot[3 * tb.slot]).w);
 #pragma unroll 1
@@ -462,7 +520,10 @@ struct RtPush {
     float4 *gnp[SVGF_MAX_RANKS - 1]; float2 *gzl[SVGF_MAX_RANKS - 1];
 };
 
-template <int MINB, bool PUSH>
+// ML: "light_sampling_all" (the reference samples geoms[0] only, pathtrace.cu:359-361): every shadow ray
+// picks one of the emissive cubes/spheres uniformly (one more random number per shadow ray) and its contribution is scaled by
+// their number. A separate instantiation: the default kernel carries none of it.
+template <int MINB, bool PUSH, bool ML>
 __global__ void __launch_bounds__(RT_BX *RT_BY, MINB)
 rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf_material *__restrict__ g_materials,
           int n_materials, const float4 *__restrict__ bvh, int n_nodes, const float4 *__restrict__ tri_hot,
@@ -471,16 +532,8 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
           float *__restrict__ image, float4 *__restrict__ stale_nm, float2 *__restrict__ stale_uv,
           float4 *__restrict__ gnp_out, float2 *__restrict__ gzl_out, const __grid_constant__ RtPush push) {
     extern __shared__ __align__(16) unsigned char smem[];
-    GeomD *s_geoms = reinterpret_cast<GeomD *>(smem);
-    svgf_material *s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomD) * n_geoms);
-    {
-        const int tid = threadIdx.y * RT_BX + threadIdx.x, nt = RT_BX * RT_BY;
-        const int gw = sizeof(GeomD) / 4 * n_geoms, mw = sizeof(svgf_material) / 4 * n_materials;
-        const int *src = reinterpret_cast<const int *>(g_geoms); int *dst = reinterpret_cast<int *>(s_geoms);
-        for (int i = tid; i < gw; i += nt) dst[i] = src[i];
-        src = reinterpret_cast<const int *>(g_materials); dst = reinterpret_cast<int *>(s_mats);
-        for (int i = tid; i < mw; i += nt) dst[i] = src[i];
-    }
+    GeomS *s_geoms; svgf_material *s_mats;
+    stage_scene(smem, g_geoms, n_geoms, g_materials, n_materials, threadIdx.y * RT_BX + threadIdx.x, RT_BX * RT_BY, s_geoms, s_mats);
     __syncthreads();
     const int x = blockIdx.x * RT_BX + threadIdx.x;
     const int y = P.row_begin + blockIdx.y * RT_BY + threadIdx.y;
@@ -489,6 +542,7 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
 
     SceneView sc;
     sc.geoms = s_geoms; sc.n_geoms = n_geoms; sc.materials = s_mats; sc.bvh = bvh; sc.n_nodes = n_nodes;
+    sc.light_query_ok = s_geoms[0].pad_ != 0.f;      // set at upload (api.cu: upload_scene)
     sc.tri_hot = tri_hot; sc.tri_cold = tri_cold; sc.textures = textures;
 
     // generateRayFromCamera, pathtrace.cu:187-208
@@ -510,14 +564,17 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
     Ray cur = seg.ray;
     // shading context carried across a shadow query (pathtrace.cu:358-392 uses them after the shadow test)
     unsigned int seed = 0; F3 ipos = mk(0, 0, 0), inrm = mk(0, 0, 0); float expectDist = 0.f;
+    int shadow_light = 0;   // the geom the shadow ray in flight aims at (ML only; otherwise geoms[0])
 
     while (true) {
         Isect res; res.geomId = -2; res.materialId = 0; res.t = 0.f; res.n = mk(0, 0, 0); res.u = res.v = 0.f;
-        const bool hit = computeIntersection(sc, cur, res);      // <- the only closest-hit call site
+        const int lightIdx = ML ? shadow_light : 0;
+        const bool hit = computeIntersection(sc, cur, res, kind == Q_SHADOW ? lightIdx : -1);      // <- the only closest-hit call site
         if (kind == Q_SHADOW) {
-            if (res.geomId == 0) {                               // pathtrace.cu:374-384 (lightIdx == 0)
+            if (res.geomId == lightIdx) {                        // pathtrace.cu:374-384 (lightIdx == 0)
                 const svgf_material &sm = sc.materials[res.materialId];
-                if (sm.emittance > 0.0f) acc = add_direct_light(acc, seg.color, sm, P.sintensity, expectDist, cur.direction, inrm);
+                const float si = ML ? P.sintensity * (float)P.n_lights : P.sintensity;
+                if (sm.emittance > 0.0f) acc = add_direct_light(acc, seg.color, sm, si, expectDist, cur.direction, inrm);
             }
         } else {
             // the path ray's result lands in the persistent record; a miss only touches t and geomId (pathtrace.cu:267-271)
@@ -562,7 +619,8 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
             const bool materialIsDiffuse = material.hasReflective < 1e-6 && material.hasRefractive < 1e-6;
             if (!(P.denoise && P.sepcolor) || depth > 1) seg.color = seg.color * materialAlbedo(sc, material, is.u, is.v);
             if (P.trace_shadowray && materialIsDiffuse) {        // pathtrace.cu:358-371
-                const GeomD &light = sc.geoms[0];
+                if (ML) shadow_light = P.lights[min((int)(nextRand(seed) * (float)P.n_lights), P.n_lights - 1)];
+                const GeomD &light = sc.geoms[ML ? shadow_light : 0];
                 computeShadowRay(cur, ipos, inrm, mk(light.translation[0], light.translation[1], light.translation[2]),
                                  P.lightradius, expectDist, seed);
                 kind = Q_SHADOW;
@@ -608,18 +666,12 @@ rt_persistent_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms,
                      float *__restrict__ image, float4 *__restrict__ stale_nm, float2 *__restrict__ stale_uv,
                      float4 *__restrict__ gnp_out, float2 *__restrict__ gzl_out, unsigned int *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem[];
-    GeomD *s_geoms = reinterpret_cast<GeomD *>(smem);
-    svgf_material *s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomD) * n_geoms);
-    {
-        const int gw = sizeof(GeomD) / 4 * n_geoms, mw = sizeof(svgf_material) / 4 * n_materials;
-        const int *src = reinterpret_cast<const int *>(g_geoms); int *dst = reinterpret_cast<int *>(s_geoms);
-        for (int i = threadIdx.x; i < gw; i += blockDim.x) dst[i] = src[i];
-        src = reinterpret_cast<const int *>(g_materials); dst = reinterpret_cast<int *>(s_mats);
-        for (int i = threadIdx.x; i < mw; i += blockDim.x) dst[i] = src[i];
-    }
+    GeomS *s_geoms; svgf_material *s_mats;
+    stage_scene(smem, g_geoms, n_geoms, g_materials, n_materials, threadIdx.x, blockDim.x, s_geoms, s_mats);
     __syncthreads();
     SceneView sc;
     sc.geoms = s_geoms; sc.n_geoms = n_geoms; sc.materials = s_mats; sc.bvh = bvh; sc.n_nodes = n_nodes;
+    sc.light_query_ok = s_geoms[0].pad_ != 0.f;      // set at upload (api.cu: upload_scene)
     sc.tri_hot = tri_hot; sc.tri_cold = tri_cold; sc.textures = textures;
     const svgf_camera &cam = P.cam;
     const int lane = threadIdx.x & 31;
@@ -670,7 +722,7 @@ rt_persistent_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms,
 
         // ---- one step of the path's state machine: intersect the current ray, act on the result ----
         Isect res; res.geomId = -2; res.materialId = 0; res.t = 0.f; res.n = mk(0, 0, 0); res.u = res.v = 0.f;
-        const bool hit = computeIntersection(sc, cur, res);      // <- the only closest-hit call site
+        const bool hit = computeIntersection(sc, cur, res, kind == Q_SHADOW ? 0 : -1);      // <- the only closest-hit call site
         bool finished = false, bounce = false;
         if (kind == Q_SHADOW) {
             if (res.geomId == 0) {                               // pathtrace.cu:374-384 (lightIdx == 0)
@@ -774,16 +826,12 @@ __device__ __forceinline__ void wf_push(int *queue, int *count, int slot, bool p
 __device__ __forceinline__ SceneView wf_scene(unsigned char *smem, const GeomD *g_geoms, int n_geoms, const svgf_material *g_materials,
                                               int n_materials, const float4 *bvh, int n_nodes, const float4 *tri_hot,
                                               const float4 *tri_cold, const TexD *textures) {
-    GeomD *s_geoms = reinterpret_cast<GeomD *>(smem);
-    svgf_material *s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomD) * n_geoms);
-    const int gw = sizeof(GeomD) / 4 * n_geoms, mw = sizeof(svgf_material) / 4 * n_materials;
-    const int *src = reinterpret_cast<const int *>(g_geoms); int *dst = reinterpret_cast<int *>(s_geoms);
-    for (int i = threadIdx.x; i < gw; i += blockDim.x) dst[i] = src[i];
-    src = reinterpret_cast<const int *>(g_materials); dst = reinterpret_cast<int *>(s_mats);
-    for (int i = threadIdx.x; i < mw; i += blockDim.x) dst[i] = src[i];
+    GeomS *s_geoms; svgf_material *s_mats;
+    stage_scene(smem, g_geoms, n_geoms, g_materials, n_materials, threadIdx.x, blockDim.x, s_geoms, s_mats);
     __syncthreads();
     SceneView sc;
     sc.geoms = s_geoms; sc.n_geoms = n_geoms; sc.materials = s_mats; sc.bvh = bvh; sc.n_nodes = n_nodes;
+    sc.light_query_ok = s_geoms[0].pad_ != 0.f;      // set at upload (api.cu: upload_scene)
     sc.tri_hot = tri_hot; sc.tri_cold = tri_cold; sc.textures = textures;
     return sc;
 }
@@ -811,7 +859,7 @@ wf_generate_kernel(RtParams P, WfBuffers B) {
 }
 
 __global__ void __launch_bounds__(128)
-wf_intersect_kernel(WfScene S, WfBuffers B, const int *queue, const int *count) {
+wf_intersect_kernel(WfScene S, WfBuffers B, const int *queue, const int *count, int light_query) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SceneView sc = wf_scene(smem, S.geoms, S.n_geoms, S.materials, S.n_materials, S.bvh, S.n_nodes, S.tri_hot, S.tri_cold, S.textures);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -820,7 +868,7 @@ wf_intersect_kernel(WfScene S, WfBuffers B, const int *queue, const int *count) 
     const float4 o = B.ray_o[slot], d = B.ray_d[slot];
     Ray r; r.origin = mk(o.x, o.y, o.z); r.direction = mk(d.x, d.y, d.z);
     Isect res; res.geomId = -2; res.materialId = 0; res.t = 0.f; res.n = mk(0, 0, 0); res.u = res.v = 0.f;
-    const bool hit = computeIntersection(sc, r, res);
+    const bool hit = computeIntersection(sc, r, res, light_query != 0 ? 0 : -1);
     B.hit0[slot] = make_float4(res.t, res.n.x, res.n.y, res.n.z);
     B.hit1[slot] = make_float4(res.u, res.v, __int_as_float(res.materialId), __int_as_float(hit ? res.geomId : -1));
 }
@@ -978,7 +1026,7 @@ static cudaError_t launch_pathtrace_wavefront(svgf_ctx *c, const RtParams &p, fl
     int *qi = reinterpret_cast<int *>(f4 + 10 * n);
     B.q_path[0] = qi; B.q_path[1] = qi + n; B.q_shadow = qi + 2 * n; B.counts = qi + 3 * n;
     WfScene S{s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, s.n_nodes, s.tri_hot, s.tri_cold, s.textures};
-    const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
+    const size_t smem = scene_smem_bytes(s.n_geoms, s.n_materials);
     if (smem > 48 * 1024) {
         cudaFuncSetAttribute(wf_intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(wf_shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -992,11 +1040,11 @@ static cudaError_t launch_pathtrace_wavefront(svgf_ctx *c, const RtParams &p, fl
     // finish every path (one round even for max_depth == 0: the primary hit still has to produce the G-buffer)
     const int rounds = p.max_depth > 1 ? p.max_depth : 1;
     for (int k = 0; k < rounds; k++) {
-        wf_intersect_kernel<<<blocks, 128, smem, st>>>(S, B, B.q_path[q], &B.counts[q]);
+        wf_intersect_kernel<<<blocks, 128, smem, st>>>(S, B, B.q_path[q], &B.counts[q], 0);
         wf_reset_counts_kernel<<<1, 32, 0, st>>>(B.counts, q ^ 1, 2);
         wf_shade_kernel<<<blocks, 128, smem, st>>>(p, S, B, q, nrm_out, c->pos, c->alb, c->gnp, c->gzl, c->image, c->stale_nm, c->stale_uv);
         if (p.trace_shadowray) {
-            wf_intersect_kernel<<<blocks, 128, smem, st>>>(S, B, B.q_shadow, &B.counts[2]);
+            wf_intersect_kernel<<<blocks, 128, smem, st>>>(S, B, B.q_shadow, &B.counts[2], 1);
             wf_shade_shadow_kernel<<<blocks, 128, smem, st>>>(p, S, B, q ^ 1, c->image, c->stale_nm);
         }
         q ^= 1;
@@ -1004,14 +1052,26 @@ static cudaError_t launch_pathtrace_wavefront(svgf_ctx *c, const RtParams &p, fl
     return cudaGetLastError();
 }
 
+// Loads every kernel of this file now (see svgf_preload_kernels, api.cu).
+void preload_pathtrace_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, rt_kernel<8, false, false>); cudaFuncGetAttributes(&a, rt_kernel<8, true, false>);
+    cudaFuncGetAttributes(&a, rt_kernel<4, false, false>); cudaFuncGetAttributes(&a, rt_kernel<4, true, false>);
+    cudaFuncGetAttributes(&a, rt_kernel<8, false, true>); cudaFuncGetAttributes(&a, rt_kernel<8, true, true>);
+    cudaFuncGetAttributes(&a, rt_persistent_kernel);
+    cudaFuncGetAttributes(&a, wf_generate_kernel); cudaFuncGetAttributes(&a, wf_intersect_kernel); cudaFuncGetAttributes(&a, wf_reset_counts_kernel);
+    cudaFuncGetAttributes(&a, wf_shade_kernel); cudaFuncGetAttributes(&a, wf_shade_shadow_kernel);
+    (void)cudaGetLastError();
+}
+
 // gbuf_reach > 0 (sharded frames, push mode): rows of the a-trous G-buffer view within that many rows of a neighbour's strip
 // also go into the neighbour's planes. The state-machine kernel stores them itself; *pushed says whether it did.
 cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, int gbuf_reach, bool *pushed) {
     if (pushed) *pushed = false;
-    if (c->rt_variant == 1) return launch_pathtrace_wavefront(c, p, nrm_out);
+    if (c->rt_variant == 1 && p.n_lights <= 1) return launch_pathtrace_wavefront(c, p, nrm_out);
     const DeviceScene &s = c->scene;
-    if (c->rt_variant == 2) {       // persistent state machine with work refill (A/B; slower: see the kernel's comment)
-        const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
+    if (c->rt_variant == 2 && p.n_lights <= 1) {       // persistent state machine with work refill (A/B; slower: see the kernel's comment)
+        const size_t smem = scene_smem_bytes(s.n_geoms, s.n_materials);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(rt_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -1032,7 +1092,7 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
                                                                c->stale_nm, c->stale_uv, c->gnp, c->gzl, c->rt_counter);
         return cudaGetLastError();
     }
-    const size_t smem = sizeof(GeomD) * s.n_geoms + sizeof(svgf_material) * s.n_materials;
+    const size_t smem = scene_smem_bytes(s.n_geoms, s.n_materials);
     const int rows = p.row_end - p.row_begin;
     if (rows <= 0) return cudaSuccess;
     dim3 block(RT_BX, RT_BY), grid((p.W + RT_BX - 1) / RT_BX, (rows + RT_BY - 1) / RT_BY);
@@ -1042,23 +1102,24 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
         for (int i = 0; i < push.peers.n; i++) { push.gnp[i] = c->p_gnp.p[push.peers.rank[i]]; push.gzl[i] = c->p_gzl.p[push.peers.rank[i]]; }
         if (pushed) *pushed = true;
     }
-#define RT_LAUNCH(MINB, PUSH)                                                                                                    \
+#define RT_LAUNCH(MINB, PUSH, ML)                                                                                                \
     do {                                                                                                                         \
         if (smem > 48 * 1024) {                                                                                                  \
-            cudaError_t e = cudaFuncSetAttribute(rt_kernel<MINB, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaError_t e = cudaFuncSetAttribute(rt_kernel<MINB, PUSH, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                                      \
         }                                                                                                                        \
-        rt_kernel<MINB, PUSH><<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh,        \
-                                                                s.n_nodes, s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos,   \
-                                                                c->alb, c->image, c->stale_nm, c->stale_uv, c->gnp, c->gzl, push); \
+        rt_kernel<MINB, PUSH, ML><<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh,    \
+                                                                    s.n_nodes, s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, \
+                                                                    c->alb, c->image, c->stale_nm, c->stale_uv, c->gnp, c->gzl, push); \
     } while (0)
     // Occupancy beats registers here: the kernel waits on dependent fp32 chains and BVH loads, so 8 blocks/SM (64 registers,
     // 84 B of spills) run 15-30 % faster than 4 blocks/SM (110 registers, none); 10 and 12 were slower again (measured on
     // B200: C2 0.93/0.80/0.86/0.89 ms, C3 3.73/2.82/2.85/2.92 ms for 4/8/10/12). SVGF_RT_MINBLOCKS=4 keeps the A/B.
     static const int minb = getenv("SVGF_RT_MINBLOCKS") ? atoi(getenv("SVGF_RT_MINBLOCKS")) : 8;
     const bool do_push = push.peers.n > 0;
-    if (minb == 4) { if (do_push) RT_LAUNCH(4, true); else RT_LAUNCH(4, false); }
-    else { if (do_push) RT_LAUNCH(8, true); else RT_LAUNCH(8, false); }
+    if (p.n_lights > 1) { if (do_push) RT_LAUNCH(8, true, true); else RT_LAUNCH(8, false, true); }
+    else if (minb == 4) { if (do_push) RT_LAUNCH(4, true, false); else RT_LAUNCH(4, false, false); }
+    else { if (do_push) RT_LAUNCH(8, true, false); else RT_LAUNCH(8, false, false); }
 #undef RT_LAUNCH
     return cudaGetLastError();
 }

@@ -170,6 +170,9 @@ struct svgf_ctx {
     // quality switches the reference leaves as TODOs; all off by default (parity), svgf_set_option
     int opt_reprojection_fov_aspect = 0;    // 1: the back-projection honours FOV and aspect ratio (denoise.cu:200-207 does not)
     int opt_history_cap = 0;                // > 0: history length saturates there (unbounded in the reference)
+    int opt_light_sampling_all = 0;         // 1: shadow rays sample every emissive cube/sphere (the reference: geoms[0] only)
+    int opt_spatial_variance = 0;           // 1: pixels with a history shorter than 4 frames estimate their variance spatially
+    int n_lights = 0, lights[8] = {0};      // emissive cubes/spheres of the uploaded scene
 
     float view_matrix_prev[16];         // denoise.cu:15; identity until the first denoise (glm::mat4())
     int last_variance_valid = 0;        // var_out holds the final variance of the last frame
@@ -205,6 +208,7 @@ struct RtParams {
     int trace_shadowray, reduce_var, denoise, sepcolor;
     float sintensity, lightradius;
     float kn, kx;                       // a-trous edge-stopping scales for the pre-scaled G-buffer planes
+    int n_lights, lights[8];            // "light_sampling_all": the emissive cubes/spheres (n_lights <= 1: the reference's geoms[0])
     svgf_camera cam;
 };
 void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx);
@@ -222,6 +226,7 @@ cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes
 cudaError_t launch_signal(svgf_ctx *c, int stage, int reach);                 // reach < 0: every connected rank
 cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq, int reach);
 cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float2 *acc_lv);
+cudaError_t launch_spatial_variance(svgf_ctx *c, const int *hlen, const float2 *mom, const float4 *nrm, float4 *cv, float2 *lv);
 struct AtrousArgs {
     int src_slot;                                   // cv/lum input = c->p_cv[src_slot] / c->p_lum[src_slot] (peer-readable)
     const float4 *cv_in; float4 *cv_out;            // cv_out may be null on the last level
@@ -244,4 +249,5 @@ cudaError_t launch_soa_to_aos(svgf_ctx *c, const float4 *nrm, const float4 *pos,
 cudaError_t launch_copy_f3(svgf_ctx *c, float *dst, const float *src);
 
 int atrous_build_tensor_maps(svgf_ctx *c);
+void preload_pathtrace_kernels(); void preload_denoise_kernels(); void preload_atrous_kernels();
 void svgf_view_matrix(const svgf_camera *cam, float *out16);

@@ -218,7 +218,13 @@ void *svgf_stream(svgf_ctx *ctx);
  *                                  leaves that term out (denoise.cu:200-207), so its history only lines up for FOVY 45 on
  *                                  square frames: at 16:9 a static camera maps x to cx + 1.78 (x - cx) and most of the
  *                                  frame never accumulates.
- *   "history_cap"             n    history_length saturates at n > 0 (unbounded in the reference, denoise.cu:290-294). */
+ *   "history_cap"             n    history_length saturates at n > 0 (unbounded in the reference, denoise.cu:290-294).
+ *   "spatial_variance_estimate" 0/1  pixels whose history is shorter than 4 frames estimate their variance from the luminance
+ *                                  moments of their 7x7 neighbourhood on the same surface (SVGF paper, section 4.2) instead of
+ *                                  the constants 100 / 10 the reference assigns (denoise.cu:315, 320-329: EstimateVariance is a
+ *                                  stub). Single-GPU, whole-frame contexts.
+ *   "light_sampling_all"      0/1  every shadow ray samples one of the scene's emissive cubes/spheres (uniformly, contribution
+ *                                  scaled by their number) instead of geoms[0] only (pathtrace.cu:359-361). */
 int svgf_set_option(svgf_ctx *ctx, const char *name, int value);
 
 /* ---- BVH build on the device -------------------------------------------------------------------- */

@@ -20,7 +20,7 @@ STRIP = None
 
 
 def run(m, wl, frames, env):
-    for k in ("SVGF_ATROUS_SHAPE", "SVGF_ATROUS_SHAPES", "SVGF_TMA_L2PROMO", "SVGF_ATROUS_VARIANT", "SVGF_ATROUS_BANDS"):
+    for k in ("SVGF_ATROUS_SHAPE", "SVGF_ATROUS_SHAPES", "SVGF_TMA_L2PROMO", "SVGF_ATROUS_VARIANT", "SVGF_ATROUS_BANDS", "SVGF_RT_ANYHIT", "SVGF_RT_MINBLOCKS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     W, H, nl = wl["W"], wl["H"], wl["nlevel"]
