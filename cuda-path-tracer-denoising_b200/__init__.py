@@ -23,7 +23,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvgf_b200.so")
+LIB_PATH = os.environ.get("SVGF_LIB_PATH") or os.path.join(_HERE, "libsvgf_b200.so")      # SVGF_LIB_PATH: A/B builds (tools/)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "svgf_b200.h")
 
 SVGF_OK = 0

@@ -253,6 +253,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     if (const char *v = getenv("SVGF_HALO")) c->halo_push = strcmp(v, "pull") != 0;      // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3 || atoi(v) == 4 || atoi(v) == 5) ? atoi(v) : 2;    // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_BANDS")) c->atrous_slide_bands = atoi(v);
+    if (const char *v = getenv("SVGF_CUDA_GRAPH")) c->opt_cuda_graph = atoi(v) != 0;
     if (const char *v = getenv("SVGF_ATROUS_SHAPE")) c->atrous_shape = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_PROBE")) c->atrous_probe = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_PAIR_ROWS")) c->atrous_pair_rows = atoi(v) == 1 ? 1 : 2;
@@ -306,6 +307,8 @@ int svgf_destroy(svgf_ctx *c) {
         cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->frame_done);
         cudaEventDestroy(c->copy_done[0]); cudaEventDestroy(c->copy_done[1]); cudaFree(c->denoised_alt);
     }
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->legacy_fence) cudaEventDestroy(c->legacy_fence);
     for (auto &pf : c->prof_pool) for (int i = 0; i < 12; i++) cudaEventDestroy(pf.ev[i]);
     for (auto &r : c->registered_hosts) cudaHostUnregister(r.first);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -470,6 +473,7 @@ int svgf_set_option(svgf_ctx *c, const char *name, int value) {
     if (!strcmp(name, "reprojection_fov_aspect")) { c->opt_reprojection_fov_aspect = value != 0; return SVGF_OK; }
     if (!strcmp(name, "history_cap")) { if (value < 0) return SVGF_ERR_INVALID; c->opt_history_cap = value; return SVGF_OK; }
     if (!strcmp(name, "light_sampling_all")) { c->opt_light_sampling_all = value != 0; return SVGF_OK; }
+    if (!strcmp(name, "cuda_graph")) { c->opt_cuda_graph = value != 0; return SVGF_OK; }
     if (!strcmp(name, "spatial_variance_estimate")) { c->opt_spatial_variance = value != 0; return SVGF_OK; }
     c->err = std::string("svgf_set_option: unknown option '") + name + "'";
     return SVGF_ERR_UNKNOWN_NAME;
@@ -668,29 +672,8 @@ static int order_after_copies(svgf_ctx *c) {
     return SVGF_OK;
 }
 
-static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, float *host_image, bool async) {
-    if (!c || !cam || !P) return SVGF_ERR_INVALID;
-    if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_render: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
-    if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS || P->tracedepth < 0) { c->err = "svgf_render: parameter out of range"; return SVGF_ERR_INVALID; }
-    CK(cudaSetDevice(c->device));
-    if (async && host_image) {
-        int rc = async_setup(c);
-        if (rc != SVGF_OK) return rc;
-        // the copy outlives this call, so the buffer must be page-locked; done here on first sight (documented in the header:
-        // the caller keeps it allocated until svgf_unregister_host / svgf_destroy)
-        if (!host_is_pinned(host_image) && svgf_register_host(c, host_image, c->px * 12) != SVGF_OK) {
-            c->err = "svgf_render_async: host_image cannot be page-locked"; return SVGF_ERR_INVALID;
-        }
-        // this frame writes the buffer whose copy was queued two frames ago: that copy must have drained
-        std::swap(c->denoised, c->denoised_alt);
-        c->copy_slot ^= 1;
-        if (c->copy_pending[c->copy_slot]) CK(cudaStreamWaitEvent(c->stream, c->copy_done[c->copy_slot], 0));
-    } else {
-        int rc = order_after_copies(c);
-        if (rc != SVGF_OK) return rc;
-    }
-    { int rc = comm_check(c); if (rc != SVGF_OK) return rc; }
-    cudaEvent_t *ev = prof_begin(c, P);
+// The launches of one frame, from the frame-boundary wait to the PBO pack (everything that can live in a CUDA graph).
+static int frame_body(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, cudaEvent_t *ev) {
     c->seq++;
     // before this frame overwrites planes that peers read in place (any rank: the reprojection may land in any strip), they
     // must have finished the previous frame
@@ -719,6 +702,65 @@ static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P
     unsigned char *pbo = pbo_dev ? static_cast<unsigned char *>(pbo_dev) : c->pbo_own;
     CK(launch_pack_pbo(c, pbo, c->image, c->denoised));
     if (ev) CK(cudaEventRecord(ev[10], c->stream));
+    return SVGF_OK;
+}
+
+static int render_impl(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P, int frame, void *pbo_dev, float *host_image, bool async) {
+    if (!c || !cam || !P) return SVGF_ERR_INVALID;
+    if (cam->resolution[0] != c->W || cam->resolution[1] != c->H) { c->err = "svgf_render: camera resolution differs from the context's"; return SVGF_ERR_INVALID; }
+    if (P->atrous_nlevel < 0 || P->atrous_nlevel > SVGF_MAX_LEVELS || P->tracedepth < 0) { c->err = "svgf_render: parameter out of range"; return SVGF_ERR_INVALID; }
+    CK(cudaSetDevice(c->device));
+    if (async && host_image) {
+        int rc = async_setup(c);
+        if (rc != SVGF_OK) return rc;
+        // the copy outlives this call, so the buffer must be page-locked; done here on first sight (documented in the header:
+        // the caller keeps it allocated until svgf_unregister_host / svgf_destroy)
+        if (!host_is_pinned(host_image) && svgf_register_host(c, host_image, c->px * 12) != SVGF_OK) {
+            c->err = "svgf_render_async: host_image cannot be page-locked"; return SVGF_ERR_INVALID;
+        }
+        // this frame writes the buffer whose copy was queued two frames ago: that copy must have drained
+        std::swap(c->denoised, c->denoised_alt);
+        c->copy_slot ^= 1;
+        if (c->copy_pending[c->copy_slot]) CK(cudaStreamWaitEvent(c->stream, c->copy_done[c->copy_slot], 0));
+    } else {
+        int rc = order_after_copies(c);
+        if (rc != SVGF_OK) return rc;
+    }
+    { int rc = comm_check(c); if (rc != SVGF_OK) return rc; }
+    cudaEvent_t *ev = prof_begin(c, P);
+    // the frame as a CUDA graph ("cuda_graph" option). The frame's launches are stream-captured every
+    // frame -- the host side of a capture is the cheap part, and the kernel arguments change every frame (frame number,
+    // camera, the rotating buffer roles, the sequence number of a sharded frame) -- and the captured graph UPDATES the
+    // instantiated one in place (same topology: cudaGraphExecUpdate only patches node parameters), which is then launched
+    // as one unit: the device runs the 13 kernels of a frame back to back without per-launch front-end gaps. Frames whose
+    // kernel sequence differs (other switches) re-instantiate. Not while profiling (event records between the stages) and
+    // not for the first two frames of a context (one-time function attributes are set outside any capture).
+    const bool graph = c->opt_cuda_graph && !ev && c->frames_rendered >= 2;
+    if (graph) CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    int body_rc = frame_body(c, cam, P, frame, pbo_dev, ev);
+    if (graph) {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (body_rc == SVGF_OK && e != cudaSuccess) { c->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); body_rc = SVGF_ERR_CUDA; }
+        if (body_rc == SVGF_OK && c->graph_exec) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(c->graph_exec, g, &info) != cudaSuccess) {      // another kernel sequence: start over
+                (void)cudaGetLastError();
+                cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr;
+            }
+        }
+        if (body_rc == SVGF_OK && !c->graph_exec) {
+            e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+            if (e != cudaSuccess) { c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); body_rc = SVGF_ERR_CUDA; }
+        }
+        if (g) cudaGraphDestroy(g);
+        if (body_rc == SVGF_OK) {
+            e = cudaGraphLaunch(c->graph_exec, c->stream);
+            if (e != cudaSuccess) { c->err = std::string("cudaGraphLaunch: ") + cudaGetErrorString(e); body_rc = SVGF_ERR_CUDA; }
+        }
+    }
+    if (body_rc != SVGF_OK) return body_rc;
+    c->frames_rendered++;
     const size_t off = (size_t)c->shard.row_begin * c->W * 3, n = (size_t)(c->shard.row_end - c->shard.row_begin) * c->W * 3;
     if (host_image && async) {
         if (ev) CK(cudaEventRecord(ev[11], c->stream));
@@ -774,6 +816,13 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     if (c->rows.world > 1 || c->shard.row_begin != 0 || c->shard.row_end != c->H) { c->err = "svgf_denoise: the AoS entry point is single-GPU; sharded frames go through svgf_render"; return SVGF_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
     { int rc = order_after_copies(c); if (rc != SVGF_OK) return rc; }
+    // The reference's denoise() launches into the legacy default stream, so whatever the caller queued there before the call --
+    // typically the cudaMemcpy that fills `input_dev` / `gbuffer_dev`, which for pageable host memory RETURNS BEFORE its DMA has
+    // landed -- is ordered before its kernels. This library's stream is non-blocking: take the same ordering explicitly.
+    // (Found by the drop-in test: the shim's denoise() behind the reference's harness read half-copied inputs.)
+    if (!c->legacy_fence) CK(cudaEventCreateWithFlags(&c->legacy_fence, cudaEventDisableTiming));
+    CK(cudaEventRecord(c->legacy_fence, cudaStreamLegacy));
+    CK(cudaStreamWaitEvent(c->stream, c->legacy_fence, 0));
     cudaEvent_t *ev = prof_begin(c, P);
     if (ev) { CK(cudaEventRecord(ev[0], c->stream)); CK(cudaEventRecord(ev[1], c->stream)); }
     float kn, kx;

@@ -133,8 +133,12 @@ __device__ __forceinline__ F3 sphere_normal(const GeomD &sphere, F3 osi, bool ou
 // 16 bytes of padding per record (68-word stride) rotate the records by four banks each -- a 16-byte matrix row of eight
 // different geoms is conflict-free -- and keep the 16-byte alignment the compiler's LDS.128 of the matrices relies on (a
 // 65-word stride was measured first: it forced scalar loads and DOUBLED the kernel time).
+#ifndef SVGF_RT_NO_PAD
 struct alignas(16) GeomS : GeomD { int bank_pad_[4]; };
 static_assert(sizeof(GeomS) == 272, "GeomS");
+#else       // A/B build (tools/build_rt_ab.sh): the record at its natural stride
+struct GeomS : GeomD {};
+#endif
 
 // Copies the scene tables into shared memory (all threads of the block; caller synchronises).
 __device__ __forceinline__ void stage_scene(unsigned char *smem, const GeomD *g_geoms, int n_geoms, const svgf_material *g_materials,
@@ -143,7 +147,7 @@ __device__ __forceinline__ void stage_scene(unsigned char *smem, const GeomD *g_
     s_mats = reinterpret_cast<svgf_material *>(smem + sizeof(GeomS) * n_geoms);
     const int gw = sizeof(GeomD) / 4 * n_geoms, mw = sizeof(svgf_material) / 4 * n_materials;
     const int *src = reinterpret_cast<const int *>(g_geoms); int *dst = reinterpret_cast<int *>(s_geoms);
-    for (int i = tid; i < gw; i += nt) dst[(i >> 6) * 68 + (i & 63)] = src[i];
+    for (int i = tid; i < gw; i += nt) dst[(i >> 6) * (int)(sizeof(GeomS) / 4) + (i & 63)] = src[i];
     src = reinterpret_cast<const int *>(g_materials); dst = reinterpret_cast<int *>(s_mats);
     for (int i = tid; i < mw; i += nt) dst[i] = src[i];
 }
@@ -212,7 +216,9 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
                     if (!(bz >= 0.0f)) continue;
                     hit = true;
                     if (bz < best.t) { best.t = bz; best.bx = bx; best.by = by; best.slot = slot; }
-                    if (bz > 0.0f && bz < t_any) return true;
+                    // occluder found: nothing else matters. Ends the search through DATA (everything still stacked is dropped,
+                    // every later box is culled) -- a `return` here changed where the warp reconverges and doubled the kernel time
+                    if (bz > 0.0f && bz < t_any) { top = 0; t_bound = -FLT_MAX; }
                 }
                 if (top == 0) break;
                 cur = stack[--top];
@@ -253,9 +259,14 @@ struct Isect {      // the live part of ShadeableIntersection (sceneStructs.h:10
 // "light_sampling_all" option, where a geom of LOWER index at exactly the light's distance wins the tie as in the closest-hit
 // search; the measure-zero tie between the light and a triangle is not reproduced there).
 __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &is, int light) {
+#ifdef SVGF_RT_LIGHT_QUERY      // A/B build (tools/build_rt_ab.sh). MEASURED SLOWER and therefore compiled out of the product, see below.
     const bool lq = light >= 0 && light < 32 && sc.light_query_ok;
+#else
+    const bool lq = false;
+#endif
     float t_min = FLT_MAX;
     int hit_geom = -1;
+    bool lq_miss = false;       // light query answered "no": the light is missed or something lies in front of it
     // what the winner's deferred normal needs
     int w_axis = 0; float w_sign = 0.f; F3 w_osi = mk(0, 0, 0); bool w_outside = true; int w_kind = -1;   // 1 cube, 0 sphere, 2 mesh
     // 1 / direction exactly as IntersectBVH forms it (intersections.h:276); also feeds the conservative bounds pre-test
@@ -292,10 +303,16 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
         // neither beat nor tie t_min (margin far above rounding). The reference tests them and discards the result; the
         // explicit tie rule below makes the winner independent of the order.
         unsigned cand = cubes | spheres;
+        // (a finished light query leaves through the loop's ordinary exit, cand == 0, and is answered after the loops: early
+        // `return`s from inside these loops moved the warp's reconvergence points and doubled the kernel time for ALL queries)
         if (lq && base == 0) {
-            if (!((cand >> light) & 1u)) { is.t = -1.0f; is.geomId = -1; return false; }        // the ray misses the light's bounds
+            if (!((cand >> light) & 1u)) { lq_miss = true; cand = 0; }        // the ray misses the light's bounds
             near_j = light;
         }
+        if (lq_miss) cand = 0;
+#ifdef SVGF_RT_LIGHT_FIRST      // A/B build: closest-hit search as ever, but a shadow query tests the light first so that its distance culls the rest
+        if (!lq && light >= 0 && light < 32 && base == 0 && ((cand >> light) & 1u)) near_j = light;
+#endif
         while (true) {
             int j = -1;
             while (cand) {      // next candidate that can still matter (cheap; lanes reconverge before the exact test)
@@ -323,7 +340,7 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
             float tobj = 0.f; int axis = 0; float sign = 0.f; bool outside = true;
             const bool ok = is_cube ? box_slabs(q, tobj, axis, sign) : sphere_roots(q, tobj, outside);
             if (!ok) {
-                if (lq && i == light) { is.t = -1.0f; is.geomId = -1; return false; }
+                if (lq && i == light) { lq_miss = true; cand = 0; }
                 continue;
             }
             const F3 osi = getPointOnRay(q, tobj);
@@ -331,9 +348,9 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
             const float t = length(ray.origin - ip);
             if (lq) {
                 if (i == light) {
-                    if (!(t > 0.0f)) { is.t = -1.0f; is.geomId = -1; return false; }
+                    if (!(t > 0.0f)) { lq_miss = true; cand = 0; }
                     t_min = t; hit_geom = light;
-                } else if (t > 0.0f && (t < t_min || (t == t_min && i < light))) { is.t = -1.0f; is.geomId = -1; return false; }     // occluded
+                } else if (t > 0.0f && (t < t_min || (t == t_min && i < light))) { lq_miss = true; cand = 0; }     // occluded
                 continue;
             }
             if (t > 0.0f && (t < t_min || (t == t_min && i < hit_geom))) {
@@ -346,12 +363,21 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
     // sphere cannot win (margin for the tie rule), which bounds the traversal.
     float mesh_u = 0.f, mesh_v = 0.f; int mesh_owner = -1;
     TriBest tb; tb.t = FLT_MAX; tb.slot = -1; tb.bx = tb.by = 0.f;
-    if (lq) {       // the light is hit at t_min; a triangle in front of it?
-        if (any_mesh && intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb, t_min)) { is.t = -1.0f; is.geomId = -1; return false; }
+    // One traversal call site for both kinds of query. A light query that is still open (the light is hit at t_min) asks for
+    // any triangle strictly in front of it; an answered one skips the traversal.
+#ifndef SVGF_RT_LQ_NO_BVH_ANY
+    const float t_any = lq ? t_min : 0.f;
+#else
+    const float t_any = 0.f;
+#endif
+    const bool tri_hit = any_mesh && !lq_miss && intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb, t_any);
+    if (lq) {
+        // (closest-hit rule for the bounded traversal: a triangle wins with 0 < t < t_min; t == t_min loses to geom 0 by index)
+        if (lq_miss || (tri_hit && tb.t > 0.0f && tb.t < t_min)) { is.t = -1.0f; is.geomId = -1; return false; }
         is.t = t_min; is.geomId = light; is.materialId = sc.geoms[light].materialid;     // normal and uv are not read by the caller
         return true;
     }
-    if (any_mesh && intersectBVH(sc, ray, invdir, t_min * 1.0001f + 1e-4f, tb)) {
+    if (tri_hit) {
         const int tri_id = __float_as_int(__ldg(&sc.tri_hot[3 * tb.slot]).w);
 #pragma unroll 1
         for (int i = 0; i < sc.n_geoms && mesh_owner < 0; i++) {

@@ -170,6 +170,9 @@ struct svgf_ctx {
     // quality switches the reference leaves as TODOs; all off by default (parity), svgf_set_option
     int opt_reprojection_fov_aspect = 0;    // 1: the back-projection honours FOV and aspect ratio (denoise.cu:200-207 does not)
     int opt_history_cap = 0;                // > 0: history length saturates there (unbounded in the reference)
+    int opt_cuda_graph = 0;                 // 1: the frame's launches run as one CUDA graph, updated in place every frame (N1)
+    cudaGraphExec_t graph_exec = nullptr; int frames_rendered = 0;
+    cudaEvent_t legacy_fence = nullptr;     // svgf_denoise: orders the library's stream after the caller's legacy default stream
     int opt_light_sampling_all = 0;         // 1: shadow rays sample every emissive cube/sphere (the reference: geoms[0] only)
     int opt_spatial_variance = 0;           // 1: pixels with a history shorter than 4 frames estimate their variance spatially
     int n_lights = 0, lights[8] = {0};      // emissive cubes/spheres of the uploaded scene

@@ -177,7 +177,9 @@ int svgf_wait_image(svgf_ctx *ctx, const float *host_image);
 int svgf_register_host(svgf_ctx *ctx, void *host, size_t bytes);
 int svgf_unregister_host(svgf_ctx *ctx, void *host);
 /* == denoise(output, input, gbuffer), denoise.cu:349-402, on caller-owned DEVICE buffers in the reference's
- * AoS layouts (vec3 colour, 52-byte texels). */
+ * AoS layouts (vec3 colour, 52-byte texels). Stream semantics are the reference's: the work is ordered after everything the
+ * caller queued in the legacy default stream before the call (e.g. the cudaMemcpy that filled the inputs, which may return
+ * before its DMA has landed), and has completed when the call returns (denoise.cu:401). */
 int svgf_denoise(svgf_ctx *ctx, float *output_dev, const float *input_dev, const svgf_gbuffer_texel *gbuffer_dev,
                  const svgf_camera *cam, const svgf_params *params);
 int svgf_sync(svgf_ctx *ctx);
@@ -223,6 +225,8 @@ void *svgf_stream(svgf_ctx *ctx);
  *                                  moments of their 7x7 neighbourhood on the same surface (SVGF paper, section 4.2) instead of
  *                                  the constants 100 / 10 the reference assigns (denoise.cu:315, 320-329: EstimateVariance is a
  *                                  stub). Single-GPU, whole-frame contexts.
+ *   "cuda_graph"              0/1  (frame driver) the frame's kernels are launched as one CUDA graph that is
+ *                                  re-captured and updated in place every frame; results are bit-identical.
  *   "light_sampling_all"      0/1  every shadow ray samples one of the scene's emissive cubes/spheres (uniformly, contribution
  *                                  scaled by their number) instead of geoms[0] only (pathtrace.cu:359-361). */
 int svgf_set_option(svgf_ctx *ctx, const char *name, int value);

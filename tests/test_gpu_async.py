@@ -75,3 +75,36 @@ def test_mixed_blocking_and_async_and_reset():
             assert np.array_equal(got[f].view(np.uint32), want[f].view(np.uint32)), "round %d frame %d differs" % (rnd, f)
         R.reset()
     R.close()
+
+
+@pytest.mark.parametrize("scene,moving", [("cornell", False), ("bunny", True)])
+def test_cuda_graph_frames_are_bit_identical(scene, moving):
+    """with the "cuda_graph" option the frame's launches are captured, the instantiated graph is updated in
+    place and launched as one unit. Same kernels, same arguments: every buffer bit-identical to the plain launches, across a
+    parameter change (another kernel sequence: the graph is re-instantiated) and a reset."""
+    m = svgf()
+    W, H = 160, 96
+    outs = []
+    for on in (0, 1):
+        blob, R = m.open_scene(scene, W, H)
+        R.set_option("cuda_graph", on)
+        drv = blob.camera_driver(W, H, automate=moving)
+        host = np.zeros((H, W, 3), np.float32)
+        got = []
+        for f in range(9):
+            P = m.default_params(atrous_nlevel=5 if f < 5 else 3, history_level=1 if f < 7 else 2)
+            if f == 4:
+                R.pathtrace_async(drv.step(), P, f, host); R.wait_image(host)
+            else:
+                R.pathtrace(drv.step(), P, f, host_image=host)
+            got.append((host.copy(), R.fetch("variance"), R.fetch("history_length"), R.fetch("pbo")))
+        R.reset()
+        P = m.default_params()
+        drv = blob.camera_driver(W, H, automate=moving)
+        for f in range(4):
+            R.pathtrace(drv.step(), P, f, host_image=host)
+        got.append((host.copy(), R.fetch("variance"), R.fetch("history_length"), R.fetch("pbo")))
+        outs.append(got); R.close()
+    for f, (a, b) in enumerate(zip(*outs)):
+        for x, y, what in zip(a, b, ("image", "variance", "history_length", "pbo")):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), "frame %d: %s differs with the CUDA graph" % (f, what)

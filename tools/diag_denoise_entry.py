@@ -19,8 +19,10 @@ def frames(scene, W, H, n, nl, **over):
         out.append((o.fetch("image").copy(), o.fetch("gbuffer").copy(), cam.as_array().copy()))
     return out
 
-def run(scene, W, H, fr, nl, **over):
+def run(scene, W, H, fr, nl, reset=False, **over):
     blob, R = m.open_scene(scene, W, H)
+    if reset:
+        R.reset()
     P = m.default_params(atrous_nlevel=nl, **over)
     res = [R.denoise(i, g, m.Camera.from_array(c), P) for i, g, c in fr]
     R.close()
@@ -32,7 +34,9 @@ for over in ({"temporal_enable": 0}, {}):
     a = run(scene, W, H, fr, nl, **over)
     junk = torch.full((1 << 28,), float("nan"), device="cuda"); torch.cuda.synchronize(); del junk; torch.cuda.empty_cache()
     b = run(scene, W, H, fr, nl, **over)
-    for f in range(3):
-        d = (a[f].view(np.uint32) != b[f].view(np.uint32)).any(axis=2)
-        rows = np.nonzero(d.any(axis=1))[0]
-        print(over, "frame", f, "differing pixels", int(d.sum()), "rows", rows[:5], "...", rows[-5:] if rows.size else "", "nan in b", int(np.isnan(b[f]).sum()))
+    c = run(scene, W, H, fr, nl, reset=True, **over)     # the shim's order: svgf_create, then svgf_reset (denoiseInit)
+    for tag, b in (("nan-filled", b), ("reset-first", c)):
+        for f in range(3):
+            d = (a[f].view(np.uint32) != b[f].view(np.uint32)).any(axis=2)
+            rows = np.nonzero(d.any(axis=1))[0]
+            print(over, tag, "frame", f, "differing pixels", int(d.sum()), "rows", rows[:5], "...", rows[-5:] if rows.size else "", "nan in b", int(np.isnan(b[f]).sum()))
