@@ -306,10 +306,17 @@ def run_ours(args, wl, rank, world, local_rank):
                       "what": "the same workload unsharded on ONE GPU (rank 0's), same run, device-resident"}
             R1.close()
         barrier()
+    stages_per_rank = None
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e, ms_blk], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e, ms_blk = t.tolist()
+        # every rank's own stage intervals (the per-level ones include its waits for the neighbours): where the frame goes
+        mine = torch.tensor([float(v) for v in stage[:11]], device="cuda", dtype=torch.float64)
+        alls = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(alls, mine)
+        stages_per_rank = [{"rows": rows[r + 1] - rows[r], "pathtrace": round(a[0], 4), "temporal": round(a[1], 4), "atrous": [round(v, 4) for v in a[2:2 + nl]],
+                            "pbo_pack": round(a[9], 4), "frame": round(a[10], 4)} for r, a in enumerate(x.tolist() for x in alls)]
     if rank != 0:
         return
     px = W * H
@@ -357,6 +364,8 @@ def run_ours(args, wl, rank, world, local_rank):
     }
     if cb:
         line["cpu_baseline"] = cb
+    if stages_per_rank:
+        line["stages_ms_per_rank"] = stages_per_rank
     if anchor:
         line["anchor_1gpu"] = anchor
         line["speedup_vs_1gpu_same_run"] = line["value"] / anchor["value"]

@@ -690,7 +690,11 @@ static int frame_body(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P,
     c->gbuf_nrm = c->cur_nrm;            // where this frame's normals/geomIds live (svgf_fetch("gbuffer"))
     const bool filter = P->denoise_enable && P->right_view_option == 0 && P->atrous_nlevel > 0 && P->spatial_enable;
     bool gbuf_pushed = false;
-    CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm], (filter && c->halo_push && c->rows.world > 1) ? (2 << P->atrous_nlevel) : 0, &gbuf_pushed));
+    // The G-buffer rows the neighbours tap leave through a copy kernel after the path tracer. Dual stores from inside rt_kernel
+    // (SVGF_RT_PUSH=1, A/B) save that launch but cost the kernel 15 % (1.80 vs 1.57 ms for half a 4K frame on 2 x B200): the
+    // extra live state does not fit its 64 registers.
+    static const bool rt_push = getenv("SVGF_RT_PUSH") && atoi(getenv("SVGF_RT_PUSH")) != 0;
+    CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm], (rt_push && filter && c->halo_push && c->rows.world > 1) ? (2 << P->atrous_nlevel) : 0, &gbuf_pushed));
     if (ev) CK(cudaEventRecord(ev[1], c->stream));
     if (P->denoise_enable) {
         int rc = denoise_soa(c, c->image, cam, P, ev, gbuf_pushed);

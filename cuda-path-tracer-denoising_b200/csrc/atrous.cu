@@ -408,6 +408,8 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     const int a0 = tile_x * AT_LX - 2, b0 = t.b_first + tile_y * LY - 2;
     const int tid = threadIdx.x;
 
+    // does this block store edge rows into a neighbour's planes? (block-uniform; only such blocks fence at system scope)
+    const bool pushes = k.cv_out != nullptr && halo_rows_touch(t.ho.peers, yc + (b0 + 2) * step, yc + (b0 + 1 + LY) * step);
     const bool tma = at_stage_tile<SH>(t, s_cv, s_np, s_zl, s_lv, bar, X0, a0, b0, yc, tid);
 
     const int c = tid & 1, ap = (tid >> 1) % (AT_LX / 2), bq = tid / AT_LX;
@@ -436,7 +438,8 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
         at_thread_compute<SH>(c, ap, bq, s_cv, s_np, s_zl, s_lv, c_kl, A);
         at_write_outputs<AT_TY>(t, A, X0, a0, b0, yc, ap, bq, c);
     }
-    halo_block_done(t.ho);
+    // the block's centres lie in pixel rows yc + (b0 + 2 .. b0 + 2 + LY - 1) * step
+    halo_block_done(t.ho, pushes);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -493,7 +496,7 @@ atrous_pair_kernel(const __grid_constant__ AtrousT t) {
         pair_phase2_thread<SH>(c, ap, bq, s_cv, s_lv, s_g, c_kl, A);
         at_write_outputs<PR>(t, A, X0, a0, b0, yc, ap, bq, c);
     }
-    halo_block_done(t.ho);
+    halo_block_done(t.ho, true);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -736,7 +739,7 @@ atrous_slide_kernel(const __grid_constant__ AtrousS t) {
         }
         w.g0 += (unsigned)w.ngroups;
     }
-    halo_block_done(t.ho);
+    halo_block_done(t.ho, true);
 }
 
 }  // namespace
@@ -1013,6 +1016,9 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
         t.p_gnp.p[r] = peer ? c->p_gnp.p[r] : a.gnp; t.p_gzl.p[r] = peer ? c->p_gzl.p[r] : a.gzl;
         pv.p[r] = t.p_lv.p[r];
     }
+    // Pre-pass: kl per pixel. (Computing it per centre inside the tile kernel instead -- 9 gathers from the {lum, var} plane --
+    // was measured on B200 and is SLOWER, C2 level 1: 115 vs 98 us: at coarse levels every lane's gather is its own 128-byte
+    // line, ~400 L1 wavefronts per warp on the pipe the tile's shared-memory reads also use. Parity was green; removed.)
     {
         dim3 b(32, 8), g(((c->W + 3) / 4 + 31) / 32, (rows + 7) / 8);
         atrous_kl_kernel<<<g, b, 0, c->stream>>>(pv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c, a.wait);

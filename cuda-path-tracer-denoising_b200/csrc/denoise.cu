@@ -172,7 +172,10 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
             push.cv[i][p] = o.cv; push.lv[i][p] = o.lv;
         }
     }
-    halo_block_done(push.ho);
+    {
+        const int by0 = row_begin + blockIdx.y * blockDim.y;
+        halo_block_done(push.ho, halo_rows_touch(push.ho.peers, by0, by0 + (int)blockDim.y - 1));
+    }
 }
 
 // SURVEY.md 8(f) N4, "spatial_variance_estimate" (off by default). The reference's EstimateVariance is a stub (denoise.cu:320-329

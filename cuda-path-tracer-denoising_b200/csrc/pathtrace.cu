@@ -591,6 +591,7 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
     // shading context carried across a shadow query (pathtrace.cu:358-392 uses them after the shadow test)
     unsigned int seed = 0; F3 ipos = mk(0, 0, 0), inrm = mk(0, 0, 0); float expectDist = 0.f;
     int shadow_light = 0;   // the geom the shadow ray in flight aims at (ML only; otherwise geoms[0])
+    bool pushed_rows = false;   // PUSH: this thread stored G-buffer rows into a neighbour's planes
 
     while (true) {
         Isect res; res.geomId = -2; res.materialId = 0; res.t = 0.f; res.n = mk(0, 0, 0); res.u = res.v = 0.f;
@@ -625,10 +626,9 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
                 gnp_out[idx] = gnp; gzl_out[idx] = gzl;
                 if (PUSH) {     // compile-time: the single-GPU kernel carries none of this
                     unsigned m = halo_targets(push.peers, y);
-                    if (m) {
-                        for (; m; m &= m - 1) { const int i = __ffs(m) - 1; push.gnp[i][idx] = gnp; push.gzl[i][idx] = gzl; }
-                        __threadfence_system();     // in the neighbours' memory before any later flag of this rank
-                    }
+                    // (the system-scope fence that publishes these rows is taken once, after the path has ended: inside this
+                    // divergent loop it held up the whole warp for an NVLink round trip, +13 % kernel time on 2 GPUs at 4K)
+                    for (; m; m &= m - 1) { const int i = __ffs(m) - 1; push.gnp[i][idx] = gnp; push.gzl[i][idx] = gzl; pushed_rows = true; }
                 }
             }
             depth++;
@@ -671,6 +671,7 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
         stale_nm[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.materialId));
         stale_uv[idx] = make_float2(is.u, is.v);
     }
+    if (PUSH && pushed_rows) __threadfence_system();     // in the neighbours' memory before any later flag of this rank
 }
 
 

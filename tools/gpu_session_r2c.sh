@@ -5,13 +5,13 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi_multi.txt 2>&1
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) "$@"; }
+run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) "$@"; }
 for w in c4 c5 c3; do
-  timeout 300 run bench.py --gpus $N --verify --workload $w --steps 6 > gpurun_out/verify_${N}gpu_$w.json 2> gpurun_out/verify_${N}gpu_$w.err
+  run bench.py --gpus $N --verify --workload $w --steps 6 > gpurun_out/verify_${N}gpu_$w.json 2> gpurun_out/verify_${N}gpu_$w.err
   echo "verify $w: $(tail -1 gpurun_out/verify_${N}gpu_$w.json | cut -c1-200)"; grep -E "^rank|Error|error" gpurun_out/verify_${N}gpu_$w.err | head -5
 done
 for w in c4 ${EXTRA_WORKLOADS}; do
-  timeout 300 run bench.py --gpus $N --workload $w --steps 60 --warmup 10 > gpurun_out/bench_${N}gpu_$w.json 2> gpurun_out/bench_${N}gpu_$w.err
+  run bench.py --gpus $N --workload $w --steps 60 --warmup 10 > gpurun_out/bench_${N}gpu_$w.json 2> gpurun_out/bench_${N}gpu_$w.err
   python - gpurun_out/bench_${N}gpu_$w.json <<'PY'
 import json,sys
 try:
