@@ -147,6 +147,22 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
         cold[4 * i + 2] = make_float4(n2[0], n2[1], n2[2], t.verts[1].uv[0]);
         cold[4 * i + 3] = make_float4(t.verts[1].uv[1], t.verts[2].uv[0], t.verts[2].uv[1], 0.f);
     }
+    {   // NaN normals: normalize(b0 n0 + b1 n1 + b2 n2) of a triangle is NaN when the combination can vanish or is not finite. With
+        // all pairwise dot products of the three vertex normals positive no convex combination vanishes; anything else is "possible".
+        bool nan_possible = getenv("SVGF_ATROUS_NAN_GUARD") && atoi(getenv("SVGF_ATROUS_NAN_GUARD")) != 0;      // A/B: force the guard
+        for (int i = 0; i < d->n_triangles && !nan_possible; i++) {
+            const float *n[3] = {d->triangles[i].verts[0].normal, d->triangles[i].verts[1].normal, d->triangles[i].verts[2].normal};
+            for (int a = 0; a < 3; a++) {
+                const int b = (a + 1) % 3;
+                const float dot = n[a][0] * n[b][0] + n[a][1] * n[b][1] + n[a][2] * n[b][2];
+                if (!(dot > 0.0f) || !std::isfinite(dot)) nan_possible = true;
+            }
+        }
+        for (int g = 0; g < d->n_geoms && !nan_possible; g++)
+            for (int e = 0; e < 16; e++)
+                if (!std::isfinite(d->geoms[g].transform[e]) || !std::isfinite(d->geoms[g].inverseTransform[e]) || !std::isfinite(d->geoms[g].invTranspose[e])) nan_possible = true;
+        c->scene_nan_possible = nan_possible;
+    }
     CK(dalloc(&s.tri_hot, hot.size())); CK(dalloc(&s.tri_cold, cold.size()));
     if (!hot.empty()) {
         CK(cudaMemcpy(s.tri_hot, hot.data(), hot.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -254,6 +270,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3 || atoi(v) == 4 || atoi(v) == 5) ? atoi(v) : 2;    // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_BANDS")) c->atrous_slide_bands = atoi(v);
     if (const char *v = getenv("SVGF_CUDA_GRAPH")) c->opt_cuda_graph = atoi(v) != 0;
+    if (const char *v = getenv("SVGF_ATROUS_FUSED")) c->atrous_fused = atoi(v) != 0;        // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_SHAPE")) c->atrous_shape = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_PROBE")) c->atrous_probe = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_PAIR_ROWS")) c->atrous_pair_rows = atoi(v) == 1 ? 1 : 2;
@@ -309,6 +326,7 @@ int svgf_destroy(svgf_ctx *c) {
     }
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->legacy_fence) cudaEventDestroy(c->legacy_fence);
+    cudaFree(c->stage_ctr);
     for (auto &pf : c->prof_pool) for (int i = 0; i < 12; i++) cudaEventDestroy(pf.ev[i]);
     for (auto &r : c->registered_hosts) cudaHostUnregister(r.first);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -411,6 +429,9 @@ int svgf_peer_connect_local(svgf_ctx **ctxs, int world, const int *row_starts) {
         int rc = set_rows(c, r, world, row_starts);
         if (rc) return rc;
         for (int q = 0; q < world; q++) {
+            // Two ranks on ONE device: the persistent blocks of a rank's stage kernel fill the GPU and poll the other rank's flags,
+            // whose kernel could then never be scheduled. Such ranks (tests) run the stage level by level.
+            if (q != r && ctxs[q]->device == c->device) c->atrous_fused = 0;
             if (ctxs[q]->device != c->device) {
                 cudaSetDevice(c->device);
                 cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
@@ -592,6 +613,7 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
         CK(launch_cv_to_outputs(c, acc, c->denoised, c->var_out));
     } else {
         int src = acc_slot;
+        AtrousArgs largs[SVGF_MAX_LEVELS];
         for (int level = 1; level <= P->atrous_nlevel; level++) {
             const bool last = level == P->atrous_nlevel;
             const bool is_hist = level == P->history_level;
@@ -614,10 +636,20 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             a.wait = halo_in(c, prev_stage, sharded ? (2 << level) : 0, c->seq);
             a.ho = halo_out(c, SVGF_STAGE_LEVEL0 + level, (sharded && !last) ? (4 << level) : 0, true);
             if (!push) memset(&a.ho.peers.lo, 0, sizeof(a.ho.peers.lo)), memset(&a.ho.peers.hi, 0, sizeof(a.ho.peers.hi));
-            CK(launch_atrous(c, a));
-            if (ev && level <= SVGF_MAX_LEVELS) CK(cudaEventRecord(ev[2 + level], c->stream));
+            largs[level - 1] = a;
             if (is_hist) new_hist = dst;     // denoise.cu:391: colour history := this level's output
             src = dst;
+        }
+        // One launch for the whole stage where possible (atrous.cu: atrous_stage_kernel), else level by level. (Per-level event
+        // records: with the single launch they all follow it, so the first level's interval is the stage's.)
+        if (atrous_stage_possible(c, largs, P->atrous_nlevel)) {
+            CK(launch_atrous_stage(c, largs, P->atrous_nlevel));
+            if (ev) for (int level = 1; level <= P->atrous_nlevel; level++) CK(cudaEventRecord(ev[2 + level], c->stream));
+        } else {
+            for (int level = 1; level <= P->atrous_nlevel; level++) {
+                CK(launch_atrous(c, largs[level - 1]));
+                if (ev) CK(cudaEventRecord(ev[2 + level], c->stream));
+            }
         }
     }
     // denoise.cu:396-399 by rotation
@@ -694,6 +726,7 @@ static int frame_body(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P,
     // (SVGF_RT_PUSH=1, A/B) save that launch but cost the kernel 15 % (1.80 vs 1.57 ms for half a 4K frame on 2 x B200): the
     // extra live state does not fit its 64 registers.
     static const bool rt_push = getenv("SVGF_RT_PUSH") && atoi(getenv("SVGF_RT_PUSH")) != 0;
+    c->gbuf_nan_possible = c->scene_nan_possible;      // this frame's G-buffer comes from our own path tracer
     CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm], (rt_push && filter && c->halo_push && c->rows.world > 1) ? (2 << P->atrous_nlevel) : 0, &gbuf_pushed));
     if (ev) CK(cudaEventRecord(ev[1], c->stream));
     if (P->denoise_enable) {
@@ -832,6 +865,7 @@ extern "C" int svgf_denoise(svgf_ctx *c, float *output_dev, const float *input_d
     float kn, kx;
     atrous_scales(P->sigman, P->sigmax, &kn, &kx);
     c->gbuf_nrm = c->cur_nrm;
+    c->gbuf_nan_possible = true;            // a caller's G-buffer: anything may be in it
     CK(launch_aos_to_soa(c, gbuffer_dev, c->nrm[c->cur_nrm], c->pos, c->alb, kn, kx));
     int rc = denoise_soa(c, input_dev, cam, P, ev, false);
     if (rc != SVGF_OK) return rc;
@@ -874,6 +908,7 @@ extern "C" int svgf_atrous_host(svgf_ctx *c, float *color_out, float *variance_o
     CK(cudaMemcpyAsync(c->aos_g, gbuffer, px * sizeof(svgf_gbuffer_texel), cudaMemcpyHostToDevice, c->stream));
     float kn, kx;
     atrous_scales(P->sigman, P->sigmax, &kn, &kx);
+    c->gbuf_nan_possible = true;            // a caller's G-buffer
     CK(launch_aos_to_soa(c, c->aos_g, c->nrm[0], c->pos, c->alb, kn, kx));
     {
         std::vector<float2> lm(px);
@@ -934,6 +969,10 @@ extern "C" int svgf_fetch(svgf_ctx *c, const char *name, void *host, size_t byte
         CK(launch_soa_to_aos(c, c->nrm[c->gbuf_nrm], c->pos, c->alb, c->aos_g));
         CK(cudaStreamSynchronize(c->stream));
         return d2h(c->aos_g, px * sizeof(svgf_gbuffer_texel));
+    }
+    if (!strcmp(name, "stage_timers")) {        // diagnostic builds (SVGF_STAGE_TIMERS): eight 64-bit clock sums behind the stage kernel's counters
+        if (!c->stage_ctr) { memset(host, 0, bytes); return SVGF_OK; }
+        return d2h(c->stage_ctr + 8 + SVGF_MAX_LEVELS * (2 * 192 + 8), 64);
     }
     if (!strcmp(name, "bvh_packed")) return d2h(c->scene.bvh, (size_t)c->scene.n_nodes * 32);        // 2 x float4 per node
     if (!strcmp(name, "triangle_ids")) {        // load-order id of the triangle in every slot, in the current (BVH) order

@@ -170,21 +170,14 @@ struct AtrousT {
 // Pre-pass of a level: per-pixel luminance-weight scale  kl = log2(e) / (sqrt(max(blur3x3(variance), 0)) * sigma_l + 1e-6)
 // (denoise.cu:100-118,143). The 3x3 Gaussian lives in PIXEL space, i.e. across residue classes, so it is done here where
 // it is coalesced instead of per lattice point inside the tiled kernel. 8 B read (L1-shared) + 4 B written per pixel.
-__global__ void __launch_bounds__(256)
-atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_constant__ RowOwner ro, float *__restrict__ kl,
-                 int W, int H, int row_begin, int row_end, int blur_variance, float sigma_c, const __grid_constant__ HaloIn wait) {
-    // Sharded frames: the rows beyond the strip were stored into this GPU's planes by the neighbours' producers. Only the
-    // first and the last block row read such rows here (+-1 row); they wait for the neighbours' flags -- for every neighbour in
-    // reach of the level, so that the tile kernel, which starts after this grid has drained, finds its whole apron in place.
-    // Interior blocks start at once; the waiting blocks are a few dozen, so they cannot keep a producer off the SMs.
-    if (wait.n > 0 && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {
-        if (threadIdx.x == 0 && threadIdx.y == 0) halo_wait(wait);
-        __syncthreads();
-    }
-    // one thread = 4 consecutive pixels of a row: 3 rows x (left neighbour, 4 pixels, right neighbour)
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
-    if (x0 >= W || y >= row_end) return;
+// COHERENT: loads that must see what OTHER blocks of the same launch stored (the fused stage kernel): L2 only, never L1.
+template <bool COHERENT> __device__ __forceinline__ float4 at_ld4(const float4 *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+template <bool COHERENT> __device__ __forceinline__ float at_ld1(const float *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+
+// one thread = 4 consecutive pixels x0 .. x0 + 3 of row y: 3 rows x (left neighbour, 4 pixels, right neighbour)
+template <bool COHERENT>
+__device__ __forceinline__ void at_kl_job(const PeerPtr<const float2> &lv, const RowOwner &ro, float *__restrict__ kl, int W, int H,
+                                          int blur_variance, float sigma_c, int x0, int y) {
     float v[3][6];
     bool rok[3];
 #pragma unroll
@@ -196,11 +189,11 @@ atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_
         if (rok[r]) {
             const float2 *row = lv.p[owner_of(ro, ly)] + (size_t)ly * W;
             if (((W & 1) == 0) && x0 + 3 < W) {
-                const float4 m0 = __ldg(reinterpret_cast<const float4 *>(row + x0)), m1 = __ldg(reinterpret_cast<const float4 *>(row + x0 + 2));
+                const float4 m0 = at_ld4<COHERENT>(reinterpret_cast<const float4 *>(row + x0)), m1 = at_ld4<COHERENT>(reinterpret_cast<const float4 *>(row + x0 + 2));
                 v[r][1] = m0.y; v[r][2] = m0.w; v[r][3] = m1.y; v[r][4] = m1.w;
-            } else for (int i = 0; i < 4; i++) if (x0 + i < W) v[r][1 + i] = __ldg(&row[x0 + i].y);
-            if (x0 > 0) v[r][0] = __ldg(&row[x0 - 1].y);
-            if (x0 + 4 < W) v[r][5] = __ldg(&row[x0 + 4].y);
+            } else for (int i = 0; i < 4; i++) if (x0 + i < W) v[r][1 + i] = at_ld1<COHERENT>(&row[x0 + i].y);
+            if (x0 > 0) v[r][0] = at_ld1<COHERENT>(&row[x0 - 1].y);
+            if (x0 + 4 < W) v[r][5] = at_ld1<COHERENT>(&row[x0 + 4].y);
         }
     }
     float out[4];
@@ -245,15 +238,34 @@ atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_
     else for (int i = 0; i < 4; i++) if (x0 + i < W) dst[i] = out[i];
 }
 
+__global__ void __launch_bounds__(256)
+atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_constant__ RowOwner ro, float *__restrict__ kl,
+                 int W, int H, int row_begin, int row_end, int blur_variance, float sigma_c, const __grid_constant__ HaloIn wait) {
+    // Sharded frames: the rows beyond the strip were stored into this GPU's planes by the neighbours' producers. Only the
+    // first and the last block row read such rows here (+-1 row); they wait for the neighbours' flags -- for every neighbour in
+    // reach of the level, so that the tile kernel, which starts after this grid has drained, finds its whole apron in place.
+    // Interior blocks start at once; the waiting blocks are a few dozen, so they cannot keep a producer off the SMs.
+    if (wait.n > 0 && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) halo_wait(wait);
+        __syncthreads();
+    }
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= W || y >= row_end) return;
+    at_kl_job<false>(lv, ro, kl, W, H, blur_variance, sigma_c, x0, y);
+}
+
 namespace cde = cuda::device::experimental;
 
 using barrier_t = cuda::barrier<cuda::thread_scope_block>;
 
 // Stage tile + apron of one residue class into shared memory (shape SH: AtShape or PairShape). Returns true when the TMA path
 // was taken (the data has landed), false when cp.async copies are still in flight (caller: cp.async.wait_group + barrier).
-template <class SH>
+struct AtNoMid { __device__ __forceinline__ void operator()() const {} };
+// `mid`: work to do while the copies are in flight (after this thread's arrival at the barrier, before its wait).
+template <class SH, bool INIT_BAR = true, class MID = AtNoMid>
 __device__ __forceinline__ bool at_stage_tile(const AtrousT &t, float4 *s_cv, float4 *s_np, float2 *s_zl, float2 *s_lv, barrier_t &bar,
-                                              int X0, int a0, int b0, int yc, int tid) {
+                                              int X0, int a0, int b0, int yc, int tid, MID mid = MID()) {
     constexpr int AT_SW = SH::SW, AT_SH = SH::SH, AT_THREADS = SH::THREADS, TILE = SH::TILE, HALF = SH::HALF;
     const AtrousK &k = t.k;
     const int W = k.W, H = k.H, step = k.step;
@@ -268,11 +280,16 @@ __device__ __forceinline__ bool at_stage_tile(const AtrousT &t, float4 *s_cv, fl
     if (t.probe == 1) return tma;       // timing probe: arithmetic on whatever shared memory holds
 #endif
     if (tma) {
-        if (tid == 0) {
-            init(&bar, AT_THREADS);
+        if (INIT_BAR) {
+            if (tid == 0) {
+                init(&bar, AT_THREADS);
+                cde::fence_proxy_async_shared_cta();
+            }
+            __syncthreads();
+        } else if (tid == 0) {
+            // persistent block: the barrier lives on; shared memory was last touched through the generic proxy (reads, border fix-up)
             cde::fence_proxy_async_shared_cta();
         }
-        __syncthreads();
         barrier_t::arrival_token token;
         if (tid == 0) {
 #pragma unroll
@@ -286,6 +303,7 @@ __device__ __forceinline__ bool at_stage_tile(const AtrousT &t, float4 *s_cv, fl
         } else {
             token = bar.arrive();
         }
+        mid();
         bar.wait(std::move(token));
         // border tiles: the hardware zero-filled what lies outside the tensor; taps outside the IMAGE (columns >= W inside
         // the rounded-up lattice, padded rows >= H) get zeros too, and every invalid tap gets lum = 3e38
@@ -390,7 +408,7 @@ __device__ __forceinline__ void at_write_outputs(const AtrousT &t, const AtAcc2 
         }
 }
 
-template <int LX, int LY, int AT_TY, int MINB>
+template <int LX, int LY, int AT_TY, int MINB, bool NS = true>
 __global__ void __launch_bounds__((AtShape<LX, LY, AT_TY>::THREADS), MINB)
 atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     using SH = AtShape<LX, LY, AT_TY>;
@@ -435,11 +453,308 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
 #endif
     if (live) {
         AtAcc2 A[AT_TY];
-        at_thread_compute<SH>(c, ap, bq, s_cv, s_np, s_zl, s_lv, c_kl, A);
+        at_thread_compute<SH, NS>(c, ap, bq, s_cv, s_np, s_zl, s_lv, c_kl, A);
         at_write_outputs<AT_TY>(t, A, X0, a0, b0, yc, ap, bq, c);
     }
     // the block's centres lie in pixel rows yc + (b0 + 2 .. b0 + 2 + LY - 1) * step
     halo_block_done(t.ho, pushes);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The whole a-trous stage of a frame as ONE launch (SVGF_ATROUS_FUSED=1; bit-identical to the level-by-level launches,
+// tests/test_gpu_atrous.py). MEASURED SLOWER ON B200 AND THEREFORE NOT THE DEFAULT: C2 650 us against 479 us, 4K 2203 against
+// 1582, a 270-row strip of a 4K frame 405 against 295 (profiles/r2_ab_atrous_stage_one_launch.jsonl). The idea: launched level
+// by level, a level costs 26 us + 30.5 us/Mpixel (89 us at 1080p, 279 us at 4K, 55 us for the strip): the kl pre-pass (11 us),
+// two kernel boundaries, and half a wave of tiles at the end (5.5 waves of 12 us blocks). What it costs instead, from clock64
+// sums of thread 0 of every block (tools/stage_timers.py, share of a block's life at C2): tile compute 40 %, tile load 24 %,
+// WAITING FOR DEPENDENCIES 23 % -- at every level's start all blocks sit out the first bands' K items, and a band's tiles
+// need ALL tiles of the band D further up to have finished their share of its K work, which 1000 queue positions of
+// look-ahead (1.4 waves) only just cover -- claim/decode 5.5 %, K items 5 %. A tile costs 12.8 us here and 12.3 us in its own
+// launch, so even with every wait removed the stage would come out at ~460 us: the per-level kernels lose little more than the
+// kl pre-pass to their launch structure, and a persistent block pays for it again in claim, dependency probe and signal
+// (~2 us per item, 40 items per block and frame). Kept as a measured negative result. The levels' work items -- "K": the luminance-weight scale of 8 pixel rows, "T": one
+// lattice tile, the very code of atrous_tiled_kernel -- stand in one queue in dependency order, persistent blocks take them in
+// order, and an item starts as soon as the items it reads from have finished: a T item of level L needs the K items of its own
+// band of rows and the T items of level L - 1 whose rows its taps reach, a K item the T items of level L - 1 around its rows.
+// Levels overlap: while the last tiles of level L drain, tiles of level L + 1 further up the frame are already running.
+//   * order: per level, group g = {K items of band g} then {T items of band g - D}: a band's kl is queued D bands -- at least a
+//     thousand items, more than the blocks in flight -- ahead of its tiles, so the tiles find it finished (with D = 1 every tile
+//     sat out the 20 us its band's K items took: the stage ran 3x SLOWER than level by level). Every dependency points to an
+//     EARLIER queue position, and blocks fetch in order, so waiting cannot deadlock;
+//   * completion counters per (level, band) in global memory: writers __syncthreads + __threadfence + atomicAdd, readers poll
+//     (one thread), fence, __syncthreads; data written by other blocks of the same launch is read through L2 only (TMA, ld.cg);
+//   * sharded frames: items that read rows beyond the strip, or store edge rows into a neighbour's planes, poll the
+//     neighbours' stage flags first (halo_sync.cuh); the block that completes a level's last tile raises this rank's flag.
+// Results are bit-identical to the level-by-level launches (same per-thread code, same operands).
+enum { ST_MAXBANDS = 192, ST_KJOBS = 512, ST_CTR_PER_LEVEL = 2 * ST_MAXBANDS + 8 };
+struct StageLevel {
+    int begin;          // queue position of the level's first item
+    int bands, ahead;   // bands of the level; D = min(bands, lookahead): how many bands the K items run ahead of the T items
+    int items;          // D * nK + bands * nT: {K items of bands 0..D-1} {T items band by band}; a T item of band b also does
+                        // its share (one job per thread) of the K work of band b + D while its tile is in flight
+    int nK, nT;         // K / T items per group (a K item = ST_KJOBS jobs of 4 pixels each, 4 per thread)
+    int gx;             // tiles per lattice row of tiles x column groups (the per-level kernel's gridDim.x)
+    int ly;             // lattice rows per tile
+    int band0, band_h;  // pixel row of band 0, pixel rows per band (ly * step)
+    int shape;          // 0: 16 x 16 tiles, 1: 32 x 8 tiles
+    int total_T;        // T items of the level
+};
+struct StageArgs {
+    AtrousT lvl[SVGF_MAX_LEVELS];
+    StageLevel sl[SVGF_MAX_LEVELS];
+    HaloIn wait[SVGF_MAX_LEVELS];
+    int nlevels, total_items;
+    unsigned *ctr;      // [0] queue head, then per level {tdone[ST_MAXBANDS], kdone[ST_MAXBANDS], level_done, ...}
+    unsigned *err;
+};
+
+__device__ __forceinline__ void st_wait_counter(const unsigned *ctr, unsigned target, unsigned *err) {
+    const volatile unsigned *p = ctr;
+    const long long t0 = clock64();
+    while (*p < target) {
+        if (clock64() - t0 > 4000000000LL) { if (err) *reinterpret_cast<volatile unsigned *>(err) = 2u; break; }      // a bug, not a hang
+        __nanosleep(64);
+    }
+}
+// Bands of level P whose pixel rows meet [ya, yb] (clipped to the strip) must be complete. BLOCK = false: only look (the counters
+// are read all together: independent loads, one round trip to L2); BLOCK = true: wait for every one of them.
+template <bool BLOCK>
+__device__ __forceinline__ bool st_rows_done(const StageArgs &S, int P, int ya, int yb) {
+    const StageLevel &sp = S.sl[P];
+    const AtrousK &kp = S.lvl[P].k;
+    ya = max(ya, kp.row_begin); yb = min(yb, kp.row_end - 1);
+    if (ya > yb) return true;
+    const unsigned *tdone = S.ctr + 8 + P * ST_CTR_PER_LEVEL;
+    const int j0 = (ya - sp.band0) / sp.band_h, j1 = (yb - sp.band0) / sp.band_h;
+    bool ok = true;
+    for (int j = j0; j <= j1; j++) {
+        if (BLOCK) st_wait_counter(tdone + j, (unsigned)sp.nT, S.err);
+        else ok &= *reinterpret_cast<const volatile unsigned *>(tdone + j) >= (unsigned)sp.nT;
+    }
+    return ok;
+}
+template <bool BLOCK>
+__device__ __forceinline__ bool st_halo_done(const HaloIn &w) {
+    if (BLOCK) { halo_wait(w); return true; }
+    bool ok = true;
+    for (int i = 0; i < w.n; i++) ok &= (int)(*reinterpret_cast<const volatile unsigned *>(w.flag[i]) - w.seq) >= 0;
+    return ok;
+}
+
+// Tile geometry of a T item, shared by the dependency check (scheduler thread) and the tile code (all threads).
+template <class SH>
+__device__ __forceinline__ void st_tile_rows(const AtrousT &t, int by, int &yc, int &b0, int &y_first, int &y_last, bool &pushes) {
+    constexpr int LY = SH::SH - 4;
+    const int step = t.k.step;
+    yc = by % step; b0 = t.b_first + (by / step) * LY - 2;
+    y_first = yc + b0 * step; y_last = yc + (b0 + SH::SH - 1) * step;
+    pushes = t.k.cv_out != nullptr && halo_rows_touch(t.ho.peers, yc + (b0 + 2) * step, yc + (b0 + 1 + LY) * step);
+}
+
+struct StItem { int kind, L, band, r; };        // kind: -1 end of queue, 1 K item, 2 T item
+__device__ __forceinline__ StItem st_decode(const StageArgs &S, int item) {
+    StItem d; d.kind = -1; d.L = 0; d.band = 0; d.r = 0;
+    if (item >= S.total_items) return d;
+    int L = 0;
+    while (L + 1 < S.nlevels && item >= S.sl[L + 1].begin) L++;
+    const StageLevel &sl = S.sl[L];
+    const int pre = sl.ahead * sl.nK;
+    int i = item - sl.begin;
+    d.L = L;
+    if (i < pre) { d.kind = 1; d.band = i / sl.nK; d.r = i % sl.nK; }
+    else { i -= pre; d.kind = 2; d.band = i / sl.nT; d.r = i % sl.nT; }
+    return d;
+}
+// What the item reads has been produced? (BLOCK: wait until it has.)
+template <bool BLOCK>
+__device__ __forceinline__ bool st_deps(const StageArgs &S, const StItem &d) {
+    if (d.kind < 0) return true;
+    const StageLevel &sl = S.sl[d.L];
+    const AtrousT &t = S.lvl[d.L];
+    const AtrousK &k = t.k;
+    bool ok = true;
+    if (d.kind == 1) {
+        const int b_lo = max(k.row_begin, sl.band0 + d.band * sl.band_h), b_hi = min(k.row_end, sl.band0 + (d.band + 1) * sl.band_h);
+        const int jobs_x = (k.W + 3) >> 2, jobs = jobs_x * max(b_hi - b_lo, 0);
+        const int j0 = d.r * ST_KJOBS, j1 = min(jobs, j0 + ST_KJOBS);
+        if (j0 < j1) {
+            const int r0 = b_lo + j0 / jobs_x, r1 = b_lo + (j1 - 1) / jobs_x + 1;
+            if (d.L > 0) ok &= st_rows_done<BLOCK>(S, d.L - 1, r0 - 1, r1);
+            if (S.wait[d.L].n > 0 && (r0 - 1 < k.row_begin || r1 >= k.row_end)) ok &= st_halo_done<BLOCK>(S.wait[d.L]);
+        }
+    } else {
+        const int by = d.band * k.step + d.r / sl.gx;
+        int yc, b0, y_first, y_last; bool pushes;
+        if (sl.shape == 0) st_tile_rows<AtShape<16, 16, 2>>(t, by, yc, b0, y_first, y_last, pushes);
+        else st_tile_rows<AtShape<32, 8, 2>>(t, by, yc, b0, y_first, y_last, pushes);
+        const unsigned *kdone = S.ctr + 8 + d.L * ST_CTR_PER_LEVEL + ST_MAXBANDS + d.band;
+        const unsigned ktarget = (unsigned)(d.band < sl.ahead ? sl.nK : sl.nT);     // who did the band's K work: K items, or the tiles D bands up
+        if (BLOCK) st_wait_counter(kdone, ktarget, S.err);
+        else ok &= *reinterpret_cast<const volatile unsigned *>(kdone) >= ktarget;
+        // the K work this tile carries: rows of band + D (and one row either side of them)
+        const bool carries = d.band + sl.ahead < sl.bands;
+        const int ka = sl.band0 + (d.band + sl.ahead) * sl.band_h - 1, kb = sl.band0 + (d.band + sl.ahead + 1) * sl.band_h;
+        if (d.L > 0) {
+            ok &= st_rows_done<BLOCK>(S, d.L - 1, y_first, y_last);
+            if (carries) ok &= st_rows_done<BLOCK>(S, d.L - 1, ka, kb);
+        }
+        if (S.wait[d.L].n > 0 && (pushes || y_first < k.row_begin || y_last >= k.row_end || (carries && (ka < k.row_begin || kb >= k.row_end))))
+            ok &= st_halo_done<BLOCK>(S.wait[d.L]);
+    }
+    if (ok) __threadfence();        // acquire side: the data behind the counters is read after this
+    return ok;
+}
+// The item's outputs are complete (all threads' stores precede a __syncthreads the caller has passed): publish.
+__device__ __forceinline__ void st_signal(const StageArgs &S, const StItem &d) {
+    if (d.kind < 0) return;
+    __threadfence();
+    unsigned *base = S.ctr + 8 + d.L * ST_CTR_PER_LEVEL;
+    if (d.kind == 1) { atomicAdd(base + ST_MAXBANDS + d.band, 1u); return; }
+    atomicAdd(base + d.band, 1u);
+    if (d.band + S.sl[d.L].ahead < S.sl[d.L].bands) atomicAdd(base + ST_MAXBANDS + d.band + S.sl[d.L].ahead, 1u);      // its share of that band's K work
+    const AtrousT &t = S.lvl[d.L];
+    if (atomicAdd(base + 2 * ST_MAXBANDS, 1u) == (unsigned)S.sl[d.L].total_T - 1u && t.ho.peers.n > 0 && t.ho.signal) {
+        __threadfence_system();
+        for (int i = 0; i < t.ho.peers.n; i++) *reinterpret_cast<volatile unsigned *>(t.ho.flag[i]) = t.ho.seq;
+    }
+}
+
+#ifdef SVGF_STAGE_TIMERS      // diagnostic build (tools/build_stage_timers.sh): where a persistent block's time goes, clock64 sums of thread 0
+#define ST_T(i) if (tid == 0) { const long long now_ = clock64(); s_tm[i] += now_ - t_last; t_last = now_; }
+#else
+#define ST_T(i)
+#endif
+
+// One tile (the per-level kernel's block (bx, by)) by the 128 threads of a persistent block; its dependencies are complete.
+template <class SH, bool NS>
+__device__ __forceinline__ void st_tile_item(const StageArgs &S, int L, int bx, int by, int band, int ti, unsigned char *smem, barrier_t &bar, int tid
+#ifdef SVGF_STAGE_TIMERS
+                                             , long long *s_tm, long long &t_last
+#endif
+                                             ) {
+    constexpr int AT_LX = SH::SW - 4, AT_TY = SH::TY, TILE = SH::TILE;
+    const AtrousT &t = S.lvl[L];
+    const AtrousK &k = t.k;
+    float4 *s_cv = reinterpret_cast<float4 *>(smem), *s_np = s_cv + TILE;
+    float2 *s_zl = reinterpret_cast<float2 *>(s_np + TILE), *s_lv = s_zl + TILE;
+    const int W = k.W, step = k.step;
+    const int cg = bx % t.ncg, tile_x = bx / t.ncg;
+    const int X0 = cg * AT_C, a0 = tile_x * AT_LX - 2;
+    int yc, b0, y_first, y_last; bool pushes;
+    st_tile_rows<SH>(t, by, yc, b0, y_first, y_last, pushes);
+    if (tid == 0) asm volatile("fence.proxy.async.global;" ::: "memory");     // other blocks' stores (generic proxy) before this thread's TMA reads
+    // While the tile is in flight: this tile's share of the K work of the band D bands further down (about one job per thread).
+    const StageLevel &sl = S.sl[L];
+    const int kband = band + sl.ahead;
+    auto k_share = [&]() {
+        if (kband >= sl.bands) return;
+        const int b_lo = max(k.row_begin, sl.band0 + kband * sl.band_h), b_hi = min(k.row_end, sl.band0 + (kband + 1) * sl.band_h);
+        const int jobs_x = (k.W + 3) >> 2, jobs = jobs_x * max(b_hi - b_lo, 0);
+        const int per = (jobs + sl.nT - 1) / sl.nT, j0 = ti * per, j1 = min(jobs, j0 + per);
+        for (int j = j0 + tid; j < j1; j += 128)
+            at_kl_job<true>(t.p_lv, t.ro, const_cast<float *>(t.kl), k.W, k.H, k.blur_variance, k.sigma_c, (j % jobs_x) * 4, b_lo + j / jobs_x);
+    };
+    at_stage_tile<SH, false>(t, s_cv, s_np, s_zl, s_lv, bar, X0, a0, b0, yc, tid, k_share);
+
+    const int c = tid & 1, ap = (tid >> 1) % (AT_LX / 2), bq = tid / AT_LX;
+    float c_kl[AT_TX][AT_TY];
+    bool live = false;
+#pragma unroll
+    for (int ca = 0; ca < AT_TX; ca++)
+#pragma unroll
+        for (int cb = 0; cb < AT_TY; cb++) {
+            const int x = X0 + (a0 + 2 * ap + ca + 2) * step + c, y = yc + (b0 + AT_TY * bq + cb + 2) * step;
+            const bool ok = x < W && y >= k.row_begin && y < k.row_end;
+            live |= ok;
+            c_kl[ca][cb] = ok ? __ldcg(&t.kl[x + y * W]) : 0.f;
+        }
+    __syncthreads();
+    ST_T(3)
+    if (live) {
+        AtAcc2 A[AT_TY];
+        at_thread_compute<SH, NS>(c, ap, bq, s_cv, s_np, s_zl, s_lv, c_kl, A);
+        at_write_outputs<AT_TY>(t, A, X0, a0, b0, yc, ap, bq, c);
+    }
+    if (pushes) __threadfence_system();
+    ST_T(4)
+}
+
+using StShapeA = AtShape<16, 16, 2>;
+using StShapeB = AtShape<32, 8, 2>;
+static_assert(StShapeA::THREADS == 128 && StShapeB::THREADS == 128, "both tile shapes of the stage kernel run on 128 threads");
+constexpr int ST_SMEM = (StShapeA::SMEM > StShapeB::SMEM ? StShapeA::SMEM : StShapeB::SMEM) + 112;
+
+template <bool NS>
+__global__ void __launch_bounds__(128, 5)
+atrous_stage_kernel(const __grid_constant__ StageArgs S) {
+    extern __shared__ __align__(128) unsigned char at_smem_raw[];
+    barrier_t &bar = *reinterpret_cast<barrier_t *>(at_smem_raw + ST_SMEM - 112);
+    int *s_slots = reinterpret_cast<int *>(at_smem_raw + ST_SMEM - 96);      // two slots {kind, level, band, r}: what thread 0 decoded
+    const int tid = threadIdx.x;
+#ifdef SVGF_STAGE_TIMERS
+    long long *s_tm = reinterpret_cast<long long *>(at_smem_raw + ST_SMEM - 64);     // 8 accumulators
+    long long t_last = clock64();
+    if (tid == 0) for (int i = 0; i < 8; i++) s_tm[i] = 0;
+#endif
+    // Thread 0 claims items (always one ahead, so the atomic's round trip to L2 hides behind an item's work), decodes them and
+    // waits for what they read; the other threads wait at the barrier. Items are claimed in queue order and only ever wait for
+    // earlier ones, so the early claim cannot deadlock.
+    int next = 0;
+    if (tid == 0) {
+        init(&bar, 128);
+        cde::fence_proxy_async_shared_cta();
+        next = (int)atomicAdd(S.ctr, 1u);
+    }
+    for (int it = 0;; it++) {
+        int *slot = s_slots + (it & 1) * 4;
+        if (tid == 0) {
+            const StItem d = st_decode(S, next);
+            if (d.kind >= 0) next = (int)atomicAdd(S.ctr, 1u);
+            ST_T(0)
+            if (!st_deps<false>(S, d)) st_deps<true>(S, d);
+            ST_T(1)
+            slot[0] = d.kind; slot[1] = d.L; slot[2] = d.band; slot[3] = d.r;
+        }
+        __syncthreads();
+        const int kind = slot[0], L = slot[1], band = slot[2], r = slot[3];
+        if (kind < 0) break;
+        const StageLevel &sl = S.sl[L];
+        const AtrousT &t = S.lvl[L];
+        const AtrousK &k = t.k;
+        if (kind == 1) {
+            // ---- K item: jobs [r * ST_KJOBS, (r + 1) * ST_KJOBS) of the band (a job = 4 pixels of a row) ----
+            const int b_lo = max(k.row_begin, sl.band0 + band * sl.band_h), b_hi = min(k.row_end, sl.band0 + (band + 1) * sl.band_h);
+            const int jobs_x = (k.W + 3) >> 2, jobs = jobs_x * max(b_hi - b_lo, 0);
+            const int j0 = r * ST_KJOBS, j1 = min(jobs, j0 + ST_KJOBS);
+#pragma unroll 2
+            for (int j = j0 + tid; j < j1; j += 128)
+                at_kl_job<true>(t.p_lv, t.ro, const_cast<float *>(t.kl), k.W, k.H, k.blur_variance, k.sigma_c, (j % jobs_x) * 4, b_lo + j / jobs_x);
+            __syncthreads();
+            ST_T(2)
+        } else {
+            // ---- T item: tile (bx, by) of the band ----
+            const int bx = r % sl.gx, by = band * k.step + r / sl.gx;
+#ifdef SVGF_STAGE_TIMERS
+            if (sl.shape == 0) st_tile_item<StShapeA, NS>(S, L, bx, by, band, r, at_smem_raw, bar, tid, s_tm, t_last);
+            else st_tile_item<StShapeB, NS>(S, L, bx, by, band, r, at_smem_raw, bar, tid, s_tm, t_last);
+#else
+            if (sl.shape == 0) st_tile_item<StShapeA, NS>(S, L, bx, by, band, r, at_smem_raw, bar, tid);
+            else st_tile_item<StShapeB, NS>(S, L, bx, by, band, r, at_smem_raw, bar, tid);
+#endif
+            __syncthreads();        // all stores issued, all shared-memory reads done: the next item may overwrite the tile
+            ST_T(5)
+        }
+        // publishing the finished item (fence + atomics, ~1.5 us) is another thread's job, so that it runs next to thread 0's
+        // claim / dependency check of the next item instead of in front of it
+        if (tid == 32) {
+            StItem d; d.kind = kind; d.L = L; d.band = band; d.r = r;
+            st_signal(S, d);
+        }
+        ST_T(6)
+    }
+#ifdef SVGF_STAGE_TIMERS
+    if (tid == 0) for (int i = 0; i < 8; i++) atomicAdd(reinterpret_cast<unsigned long long *>(S.ctr + 8 + SVGF_MAX_LEVELS * ST_CTR_PER_LEVEL) + i, (unsigned long long)s_tm[i]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -768,6 +1083,11 @@ template <int LX, int LY, int TY, int MINB> static AtShapeInfo at_info() {
     return AtShapeInfo{LX, LY, TY, SH::THREADS, SH::SMEM, (32 / LX > 0 ? 32 / LX : 1) * TY,
                        (const void *)atrous_tiled_kernel<LX, LY, TY, MINB>, at_launch<LX, LY, TY, MINB>};
 }
+// the two default shapes once more without the NaN guard of the distances (frames whose G-buffer cannot hold a NaN)
+template <int LX, int LY, int TY, int MINB> static void at_launch_nonan(dim3 grid, cudaStream_t st, const AtrousT &t) {
+    using SH = AtShape<LX, LY, TY>;
+    atrous_tiled_kernel<LX, LY, TY, MINB, false><<<grid, SH::THREADS, SH::SMEM, st>>>(t);
+}
 enum { AT_NSHAPES = 11 };
 static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
     at_info<16, 32, 4, 3>(),    // 0: 128 threads, 69 KB, 3 blocks/SM
@@ -974,6 +1294,7 @@ static cudaError_t launch_atrous_slide(svgf_ctx *c, const AtrousK &k, const Atro
 void preload_atrous_kernels() {
     cudaFuncAttributes a;
     for (int s = 0; s < AT_NSHAPES; s++) cudaFuncGetAttributes(&a, g_at_shapes[s].fn);
+    cudaFuncGetAttributes(&a, atrous_tiled_kernel<16, 16, 2, 5, false>); cudaFuncGetAttributes(&a, atrous_tiled_kernel<16, 12, 2, 6, false>);
     cudaFuncGetAttributes(&a, atrous_kl_kernel); cudaFuncGetAttributes(&a, atrous_direct_kernel); cudaFuncGetAttributes(&a, atrous_slide_kernel<true, false>); cudaFuncGetAttributes(&a, atrous_slide_kernel<true, true>);
     cudaFuncGetAttributes(&a, atrous_slide_kernel<false, false>); cudaFuncGetAttributes(&a, atrous_slide_kernel<false, true>);
     cudaFuncGetAttributes(&a, atrous_pair_kernel<16, 16, 2, 3>); cudaFuncGetAttributes(&a, atrous_pair_kernel<16, 16, 1, 3>);
@@ -981,9 +1302,8 @@ void preload_atrous_kernels() {
     (void)cudaGetLastError();
 }
 
-cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
-    const int rows = c->shard.row_end - c->shard.row_begin;
-    if (rows <= 0) return cudaSuccess;
+// The kernel-side description of one level (everything but the tile shape's tensor maps).
+static void at_fill_level(svgf_ctx *c, const AtrousArgs &a, AtrousT &t) {
     AtrousK k;
     k.cv_in = a.cv_in; k.cv_out = a.cv_out; k.lv_in = a.lv_in; k.lv_out = a.lv_out;
     k.nrm = a.nrm; k.pos = a.pos; k.alb = a.alb;
@@ -993,12 +1313,6 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     k.is_last = a.is_last; k.blur_variance = a.blur_variance; k.addcolor = a.addcolor;
     k.sigma_c = a.sigma_c;
     atrous_scales(a.sigma_n, a.sigma_x, &k.kn, &k.kx);
-    if (c->atrous_variant == 1 && c->rows.world == 1) {
-        dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
-        atrous_direct_kernel<<<g, b, 0, c->stream>>>(k);
-        return cudaGetLastError();
-    }
-    AtrousT t;
     t.k = k; t.kl = c->kl; t.ro = c->rows; t.me = c->shard.rank;
     t.ho = a.ho;
     for (int i = 0; i < SVGF_MAX_RANKS - 1; i++) {
@@ -1009,13 +1323,108 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     // push mode: the neighbours' rows this level taps were copied into this rank's planes by their producers (api.cu)
     const bool local_only = c->halo_push || c->rows.world <= 1;
     if (local_only) { t.ro.world = 1; t.me = 0; }
-    PeerPtr<const float2> pv;
     for (int r = 0; r < SVGF_MAX_RANKS; r++) {
         const bool peer = !local_only && r < c->rows.world && a.src_slot >= 0;
         t.p_cv.p[r] = peer ? c->p_cv[a.src_slot].p[r] : a.cv_in; t.p_lv.p[r] = peer ? c->p_lv[a.src_slot].p[r] : a.lv_in;
         t.p_gnp.p[r] = peer ? c->p_gnp.p[r] : a.gnp; t.p_gzl.p[r] = peer ? c->p_gzl.p[r] : a.gzl;
-        pv.p[r] = t.p_lv.p[r];
     }
+    t.b_first = k.row_begin / k.step;
+    t.ncg = k.step / AT_C;
+    t.use_tma = 0;
+#ifdef SVGF_ATROUS_PROBES
+    t.probe = c->atrous_probe;
+#endif
+    memset(&t.tm_cv, 0, sizeof(CUtensorMap)); memset(&t.tm_lv, 0, sizeof(CUtensorMap));
+    memset(&t.tm_np, 0, sizeof(CUtensorMap)); memset(&t.tm_zl, 0, sizeof(CUtensorMap));
+}
+static void at_set_maps(svgf_ctx *c, const AtrousArgs &a, AtrousT &t, int shape) {
+    t.use_tma = 1;
+    t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, SVGF_NCV + a.src_slot, a.level, shape);
+    t.tm_np = *tmap_at(c, 2 * SVGF_NCV, a.level, shape); t.tm_zl = *tmap_at(c, 2 * SVGF_NCV + 1, a.level, shape);
+}
+
+// Can the whole stage go out as one launch (atrous_stage_kernel)? TMA staging for every level, no in-place peer reads (single
+// GPU, or push mode), a band table that fits.
+bool atrous_stage_possible(const svgf_ctx *c, const AtrousArgs *a, int n) {
+    if (c->atrous_variant != 2 || !c->atrous_fused || !c->tma_ok || n < 1 || n > SVGF_MAX_LEVELS) return false;
+    if (c->atrous_shape >= 0) return false;                             // a forced tile shape: A/B runs of the per-level kernel
+    if (!(c->halo_push || c->rows.world <= 1)) return false;
+    const int rows = c->shard.row_end - c->shard.row_begin;
+    if (rows <= 0) return false;
+    for (int i = 0; i < n; i++) {
+        if (a[i].src_slot < 0 || a[i].level != i + 1) return false;
+        if (rows / (8 << a[i].level) + 3 > ST_MAXBANDS) return false;
+    }
+    return true;
+}
+
+cudaError_t launch_atrous_stage(svgf_ctx *c, const AtrousArgs *a, int n) {
+    static StageArgs S;             // ~10 KB: built in place, passed by value (kernel parameters up to 32 KB, CUDA 12.1+)
+    memset(&S, 0, sizeof(S));
+    const int rows = c->shard.row_end - c->shard.row_begin;
+    int pos = 0;
+    for (int i = 0; i < n; i++) {
+        AtrousT &t = S.lvl[i];
+        at_fill_level(c, a[i], t);
+        const int step = t.k.step;
+        const int lat_w = (c->W + step - 1) / step, lat_rows = (t.k.row_end - 1) / step - t.b_first + 1;
+        StageLevel &sl = S.sl[i];
+        sl.shape = lat_rows >= 100 ? 0 : 1;
+        at_set_maps(c, a[i], t, sl.shape == 0 ? 2 : 8);             // g_at_shapes[2] = 16 x 16, [8] = 32 x 8
+        const int lx = sl.shape == 0 ? 16 : 32;
+        sl.ly = sl.shape == 0 ? 16 : 8;
+        sl.gx = ((lat_w + lx - 1) / lx) * t.ncg;
+        sl.bands = (lat_rows + sl.ly - 1) / sl.ly;
+        sl.band0 = t.b_first * step; sl.band_h = sl.ly * step;
+        sl.nK = (((c->W + 3) / 4) * sl.band_h + ST_KJOBS - 1) / ST_KJOBS; sl.nT = sl.gx * step;
+        sl.ahead = std::min(sl.bands, 1 + (1000 + sl.nT - 1) / sl.nT);      // a band's K work is queued >= 1000 items (> the blocks in flight) before its tiles
+        sl.total_T = sl.bands * sl.nT;
+        sl.items = sl.ahead * sl.nK + sl.bands * sl.nT;
+        sl.begin = pos;
+        pos += sl.items;
+        S.wait[i] = a[i].wait;
+        (void)rows;
+    }
+    S.nlevels = n; S.total_items = pos;
+    if (!c->stage_ctr) {
+        cudaError_t e = cudaMalloc((void **)&c->stage_ctr, sizeof(unsigned) * (8 + SVGF_MAX_LEVELS * ST_CTR_PER_LEVEL + 16));
+        if (e == cudaSuccess) e = cudaMemset(c->stage_ctr, 0, sizeof(unsigned) * (8 + SVGF_MAX_LEVELS * ST_CTR_PER_LEVEL + 16));
+        if (e != cudaSuccess) return e;
+    }
+    S.ctr = c->stage_ctr; S.err = c->comm_err_dev;
+    cudaError_t e = cudaMemsetAsync(c->stage_ctr, 0, sizeof(unsigned) * (8 + SVGF_MAX_LEVELS * ST_CTR_PER_LEVEL), c->stream);       // (the 16 words behind: SVGF_STAGE_TIMERS sums)
+    if (e != cudaSuccess) return e;
+    if (!c->stage_attr_set) {
+        for (int ns = 0; ns < 2; ns++) {
+            const void *fn = ns ? (const void *)atrous_stage_kernel<true> : (const void *)atrous_stage_kernel<false>;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        c->stage_blocks = 5 * (sms > 0 ? sms : 148);
+        c->stage_attr_set = true;
+    }
+    const int grid = std::min(c->stage_blocks, S.total_items);
+    if (c->gbuf_nan_possible) atrous_stage_kernel<true><<<grid, 128, ST_SMEM, c->stream>>>(S);
+    else atrous_stage_kernel<false><<<grid, 128, ST_SMEM, c->stream>>>(S);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
+    const int rows = c->shard.row_end - c->shard.row_begin;
+    if (rows <= 0) return cudaSuccess;
+    AtrousT t;
+    at_fill_level(c, a, t);
+    const AtrousK &k = t.k;
+    if (c->atrous_variant == 1 && c->rows.world == 1) {
+        dim3 b(32, 8), g((c->W + 31) / 32, (rows + 7) / 8);
+        atrous_direct_kernel<<<g, b, 0, c->stream>>>(k);
+        return cudaGetLastError();
+    }
+    PeerPtr<const float2> pv;
+    for (int r = 0; r < SVGF_MAX_RANKS; r++) pv.p[r] = t.p_lv.p[r];
     // Pre-pass: kl per pixel. (Computing it per centre inside the tile kernel instead -- 9 gathers from the {lum, var} plane --
     // was measured on B200 and is SLOWER, C2 level 1: 115 vs 98 us: at coarse levels every lane's gather is its own 128-byte
     // line, ~400 L1 wavefronts per warp on the pipe the tile's shared-memory reads also use. Parity was green; removed.)
@@ -1024,34 +1433,31 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
         atrous_kl_kernel<<<g, b, 0, c->stream>>>(pv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c, a.wait);
     }
     const int step = k.step;
-    t.b_first = k.row_begin / step;
-    t.ncg = step / AT_C;
     const int lat_w = (c->W + step - 1) / step;                                 // lattice columns per class
     const int lat_rows = (k.row_end - 1) / step - t.b_first + 1;                // lattice rows touching the strip
     if (c->atrous_variant == 4) return launch_atrous_pair(c, t, a, lat_w, lat_rows);
     if (c->atrous_variant == 5) return launch_atrous_slide(c, k, a);
     const int shape = at_pick_shape(c, a.level, lat_w, lat_rows);
     const AtShapeInfo &si = g_at_shapes[shape];
-    t.use_tma = c->tma_ok && a.src_slot >= 0 && c->atrous_variant != 3;
-#ifdef SVGF_ATROUS_PROBES
-    t.probe = c->atrous_probe;
-#endif
-    if (t.use_tma) {
-        t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, SVGF_NCV + a.src_slot, a.level, shape);
-        t.tm_np = *tmap_at(c, 2 * SVGF_NCV, a.level, shape); t.tm_zl = *tmap_at(c, 2 * SVGF_NCV + 1, a.level, shape);
-    } else {
-        memset(&t.tm_cv, 0, sizeof(CUtensorMap)); memset(&t.tm_lv, 0, sizeof(CUtensorMap));
-        memset(&t.tm_np, 0, sizeof(CUtensorMap)); memset(&t.tm_zl, 0, sizeof(CUtensorMap));
-    }
+    if (c->tma_ok && a.src_slot >= 0 && c->atrous_variant != 3) at_set_maps(c, a, t, shape);
     if (!c->atrous_attr_set) {      // per context (= per device)
         for (int s = 0; s < AT_NSHAPES; s++) {
             cudaError_t e = cudaFuncSetAttribute(g_at_shapes[s].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_at_shapes[s].smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(g_at_shapes[s].fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
         }
+        const void *nn[2] = {(const void *)atrous_tiled_kernel<16, 16, 2, 5, false>, (const void *)atrous_tiled_kernel<16, 12, 2, 6, false>};
+        const int nn_smem[2] = {g_at_shapes[2].smem, g_at_shapes[9].smem};
+        for (int s = 0; s < 2; s++) {
+            cudaError_t e = cudaFuncSetAttribute(nn[s], cudaFuncAttributeMaxDynamicSharedMemorySize, nn_smem[s]);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(nn[s], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
         c->atrous_attr_set = true;
     }
     dim3 g(((lat_w + si.lx - 1) / si.lx) * t.ncg, ((lat_rows + si.ly - 1) / si.ly) * step);
-    si.launch(g, c->stream, t);
+    if (!c->gbuf_nan_possible && shape == 2) at_launch_nonan<16, 16, 2, 5>(g, c->stream, t);
+    else if (!c->gbuf_nan_possible && shape == 9) at_launch_nonan<16, 12, 2, 6>(g, c->stream, t);
+    else si.launch(g, c->stream, t);
     return cudaGetLastError();
 }

@@ -11,7 +11,9 @@
 // (denoise.cu:144-145; CUDA's min = fminf, which drops a NaN operand): for d >= 0 that is the identity, but a NaN distance --
 // a mesh without vertex normals interpolates normalize(0) = NaN (sceneStructs.h:168-172) -- yields weight 1, not NaN. fmaxf
 // drops the NaN here (one FMNMX on the ALU pipe, which has slack), so such a pair is filtered as if the two normals agreed.
-PAIR_FN float dist_of(float d2) { return fmaxf(pair_sqrt(d2), 0.0f); }
+// NS = false: the caller guarantees that no normal or position in the frame is NaN (svgf_ctx::gbuf_nan_possible, decided from
+// the scene at upload); the two FMNMX per pair go away.
+template <bool NS = true> PAIR_FN float dist_of(float d2) { return NS ? fmaxf(pair_sqrt(d2), 0.0f) : pair_sqrt(d2); }
 
 constexpr int AT_C = 2, AT_TX = 2;
 // Tile shape <LX, LY, TY>: LX x LY lattice points (x 2 columns) per block, every thread a 2 x TY patch of them.
@@ -58,9 +60,10 @@ PAIR_FN float2 at_dist2(const AtTap &T, float2 cx, float2 cy, float2 cz) {      
 }
 
 // one tap against both centres of a patch row; h = {h of centre 0, h of centre 1}
+template <bool NS = true>
 PAIR_FN void at_twin(const AtTap &T, const AtCentre2 &C, AtAcc2 &A, float2 h) {
     const float2 d0 = at_dist2(T, C.nx_px[0], C.ny_py[0], C.nz_pz[0]), d1 = at_dist2(T, C.nx_px[1], C.ny_py[1], C.nz_pz[1]);
-    const float2 dn = make_float2(dist_of(d0.x), dist_of(d1.x)), dp = make_float2(dist_of(d0.y), dist_of(d1.y));
+    const float2 dn = make_float2(dist_of<NS>(d0.x), dist_of<NS>(d1.x)), dp = make_float2(dist_of<NS>(d0.y), dist_of<NS>(d1.y));
     const float2 dl = __fadd2_rn(make_float2(T.lum, T.lum), make_float2(-C.lum.x, -C.lum.y));
     const float2 e = __fadd2_rn(__ffma2_rn(make_float2(fabsf(dl.x), fabsf(dl.y)), C.kl, dn), dp);
     const float2 w = __fmul2_rn(make_float2(pair_ex2(-e.x), pair_ex2(-e.y)), h);
@@ -74,10 +77,10 @@ PAIR_FN void at_twin(const AtTap &T, const AtCentre2 &C, AtAcc2 &A, float2 h) {
 }
 
 // one tap against ONE centre of the row (tap columns 0 and 5 reach one centre column only): same operations per lane
-template <int CA>
+template <int CA, bool NS = true>
 PAIR_FN void at_single(const AtTap &T, const AtCentre2 &C, AtAcc2 &A, float h) {
     const float2 d2 = at_dist2(T, C.nx_px[CA], C.ny_py[CA], C.nz_pz[CA]);
-    const float dn = dist_of(d2.x), dp = dist_of(d2.y);
+    const float dn = dist_of<NS>(d2.x), dp = dist_of<NS>(d2.y);
     const float lum = CA ? C.lum.y : C.lum.x, kl = CA ? C.kl.y : C.kl.x;
     const float e = fmaf(fabsf(T.lum - lum), kl, dn) + dp;
     const float w = pair_ex2(-e) * h, w2 = w * w;
@@ -87,7 +90,7 @@ PAIR_FN void at_single(const AtTap &T, const AtCentre2 &C, AtAcc2 &A, float h) {
 
 // One tap column (window column `tt` of the thread's 6) against the thread's 2 x TY centres. DO0/DO1 select which of the
 // two centre columns the tap column reaches (|i| <= 2), so the edge columns are peeled without wasted work.
-template <class SH, bool DO0, bool DO1>
+template <class SH, bool DO0, bool DO1, bool NS = true>
 PAIR_FN void at_column(const float4 *s_cv, const float4 *s_np, const float2 *s_zl, const float2 *s_lv, int c, int row0, int col,
                                           const AtCentre2 (&C)[SH::TY], AtAcc2 (&A)[SH::TY], float hi0, float hi1) {
     // h = hi * hj with hj in {3/8, 1/4, 1/16} for |j| = 0, 1, 2
@@ -103,16 +106,16 @@ PAIR_FN void at_column(const float4 *s_cv, const float4 *s_np, const float2 *s_z
         for (int cb = 0; cb < SH::TY; cb++) {
             const int j = u - 2 - cb, aj = j < 0 ? -j : j;
             if (aj > 2) continue;       // compile-time
-            if (DO0 && DO1) at_twin(T, C[cb], A[cb], hh[aj]);
-            else if (DO0) at_single<0>(T, C[cb], A[cb], hh[aj].x);
-            else at_single<1>(T, C[cb], A[cb], hh[aj].y);
+            if (DO0 && DO1) at_twin<NS>(T, C[cb], A[cb], hh[aj]);
+            else if (DO0) at_single<0, NS>(T, C[cb], A[cb], hh[aj].x);
+            else at_single<1, NS>(T, C[cb], A[cb], hh[aj].y);
         }
     }
 }
 
 // Everything one thread does between the tile having landed and the sums being complete: its 2 x TY centres against the
 // 6 x (TY + 4) tap window.
-template <class SH>
+template <class SH, bool NS = true>
 PAIR_FN void at_thread_compute(int c, int ap, int bq, const float4 *s_cv, const float4 *s_np, const float2 *s_zl, const float2 *s_lv,
                                const float (&c_kl)[AT_TX][SH::TY], AtAcc2 (&A)[SH::TY]) {
     constexpr int AT_TY = SH::TY;
@@ -137,14 +140,14 @@ PAIR_FN void at_thread_compute(int c, int ap, int bq, const float4 *s_cv, const 
     // columns 0 and 5 reach one centre column each and are peeled. The centre tap takes the generic path: all
     // differences are 0, sqrt(0) = 0, ex2(-0) = 1 exactly. ----
     const int row0 = AT_TY * bq, col0 = 2 * ap;
-    at_column<SH, true, false>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + 0, C, A, 0.0625f, 0.f);        // i = -2 for centre column 0
+    at_column<SH, true, false, NS>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + 0, C, A, 0.0625f, 0.f);        // i = -2 for centre column 0
 #pragma unroll 1
     for (int tt = 1; tt <= 4; tt++) {
         const int i0 = tt - 2, i1 = tt - 3;
         const float hi0 = i0 == 0 ? 0.375f : ((i0 == 1 || i0 == -1) ? 0.25f : 0.0625f);
         const float hi1 = i1 == 0 ? 0.375f : ((i1 == 1 || i1 == -1) ? 0.25f : 0.0625f);
-        at_column<SH, true, true>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + tt, C, A, hi0, hi1);
+        at_column<SH, true, true, NS>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + tt, C, A, hi0, hi1);
     }
-    at_column<SH, false, true>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + 5, C, A, 0.f, 0.0625f);        // i = +2 for centre column 1
+    at_column<SH, false, true, NS>(s_cv, s_np, s_zl, s_lv, c, row0, col0 + 5, C, A, 0.f, 0.0625f);        // i = +2 for centre column 1
 
 }

@@ -170,6 +170,12 @@ struct svgf_ctx {
     // quality switches the reference leaves as TODOs; all off by default (parity), svgf_set_option
     int opt_reprojection_fov_aspect = 0;    // 1: the back-projection honours FOV and aspect ratio (denoise.cu:200-207 does not)
     int opt_history_cap = 0;                // > 0: history length saturates there (unbounded in the reference)
+    // Can a normal or position of this frame's G-buffer be NaN? Decided from the scene at upload (a mesh whose vertex normals can
+    // interpolate to zero shades with normalize(0), sceneStructs.h:168-172; a non-finite matrix), always true for G-buffers handed
+    // in through svgf_denoise. false: the a-trous tile kernel drops the NaN guard of its distances (atrous_tile_core.h: dist_of).
+    bool scene_nan_possible = true, gbuf_nan_possible = true;
+    int atrous_fused = 0;                   // SVGF_ATROUS_FUSED=1 (A/B): the a-trous stage as one launch (atrous_stage_kernel); measured slower, see atrous.cu
+    unsigned *stage_ctr = nullptr; int stage_blocks = 0; bool stage_attr_set = false;
     int opt_cuda_graph = 0;                 // 1: the frame's launches run as one CUDA graph, updated in place every frame (N1)
     cudaGraphExec_t graph_exec = nullptr; int frames_rendered = 0;
     cudaEvent_t legacy_fence = nullptr;     // svgf_denoise: orders the library's stream after the caller's legacy default stream
@@ -244,6 +250,8 @@ struct AtrousArgs {
     HaloOut ho{};                                   // ... and who gets this level's edge rows and its flag
 };
 cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a);
+bool atrous_stage_possible(const svgf_ctx *c, const AtrousArgs *a, int n);         // all levels of the stage in one launch?
+cudaError_t launch_atrous_stage(svgf_ctx *c, const AtrousArgs *a, int n);
 cudaError_t launch_cv_to_outputs(svgf_ctx *c, const float4 *cv, float *denoised, float *var_out);
 cudaError_t launch_debug_view(svgf_ctx *c, int option, const int *hlen, const float4 *cv, float *denoised);
 cudaError_t launch_pack_pbo(svgf_ctx *c, unsigned char *pbo, const float *left, const float *right);

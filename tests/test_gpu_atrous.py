@@ -93,6 +93,37 @@ def test_tile_shapes_in_the_frame_path(shape, monkeypatch):
     assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
 
 
+@pytest.mark.parametrize("case", [("cornell", 640, 360, 5, {}, None, False), ("cornell", 1920, 1080, 5, {}, None, False), ("bunny", 512, 288, 5, {"history_level": 3}, None, True),
+                                  ("room", 320, 200, 3, {"blurvariance": 0}, None, False), ("cornell", 256, 256, 1, {}, None, False),
+                                  ("cornell", 1280, 720, 5, {}, (300, 471), False), ("cornell", 96, 64, 7, {}, None, False)],
+                         ids=lambda c: "%s-%dx%d-L%d%s%s" % (c[0], c[1], c[2], c[3], "-strip" if c[5] else "", "-moving" if c[6] else ""))
+def test_stage_in_one_launch_equals_level_by_level(case, monkeypatch):
+    """atrous_stage_kernel (SVGF_ATROUS_FUSED=1: all levels of the a-trous stage as one launch of persistent blocks over a
+    dependency-ordered work queue, csrc/atrous.cu; measured slower than the default, kept for A/B) runs the per-level kernels' own
+    tile code on the same operands: every buffer of every frame must be bit-identical to the level-by-level launches, for tall and
+    short lattices (both tile shapes of the
+    stage kernel), one to seven levels, a strip of a frame, a moving camera and the history taken from a middle level."""
+    scene, W, H, nl, over, strip, moving = case
+    out = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SVGF_ATROUS_FUSED", fused)
+        m = svgf()
+        blob, R = m.open_scene(scene, W, H)
+        if strip:
+            R.set_shard(0, 1, strip[0], strip[1])
+        P = m.default_params(atrous_nlevel=nl, **over)
+        drv = blob.camera_driver(W, H, automate=moving)
+        got = []
+        for f in range(4):
+            R.pathtrace(drv.step(), P, f)
+            got.append((R.fetch("denoised"), R.fetch("variance"), R.fetch("history_length")))
+        out.append(got); R.close()
+    r0, r1 = (strip if strip else (0, H))
+    for f, (a, b) in enumerate(zip(*out)):
+        for x, y, what in zip(a, b, ("denoised", "variance", "history_length")):
+            assert np.array_equal(x[r0:r1].view(np.uint32), y[r0:r1].view(np.uint32)), "frame %d: %s differs between the one-launch stage and the per-level launches" % (f, what)
+
+
 @pytest.mark.parametrize("over", [{}, {"blurvariance": 0}, {"addcolor": 0}, {"sigmal": 2.0, "sigman": 1.0, "sigmax": 1.0},
                                   {"sigmal": 0.01, "sigman": 0.01, "sigmax": 0.01}])
 def test_last_level_and_parameter_variants(over):
