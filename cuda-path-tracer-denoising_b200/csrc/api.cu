@@ -270,6 +270,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3 || atoi(v) == 4 || atoi(v) == 5) ? atoi(v) : 2;    // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_BANDS")) c->atrous_slide_bands = atoi(v);
     if (const char *v = getenv("SVGF_CUDA_GRAPH")) c->opt_cuda_graph = atoi(v) != 0;
+    if (const char *v = getenv("SVGF_HALO_COPY_FROM")) c->halo_copy_from_rows = atoi(v);        // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_FUSED")) c->atrous_fused = atoi(v) != 0;        // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_SHAPE")) c->atrous_shape = atoi(v);
     if (const char *v = getenv("SVGF_ATROUS_PROBE")) c->atrous_probe = atoi(v);
@@ -614,6 +615,7 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
     } else {
         int src = acc_slot;
         AtrousArgs largs[SVGF_MAX_LEVELS];
+        bool post_push[SVGF_MAX_LEVELS] = {false}; HaloOut post_ho[SVGF_MAX_LEVELS];
         for (int level = 1; level <= P->atrous_nlevel; level++) {
             const bool last = level == P->atrous_nlevel;
             const bool is_hist = level == P->history_level;
@@ -636,6 +638,11 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             a.wait = halo_in(c, prev_stage, sharded ? (2 << level) : 0, c->seq);
             a.ho = halo_out(c, SVGF_STAGE_LEVEL0 + level, (sharded && !last) ? (4 << level) : 0, true);
             if (!push) memset(&a.ho.peers.lo, 0, sizeof(a.ho.peers.lo)), memset(&a.ho.peers.hi, 0, sizeof(a.ho.peers.hi));
+            // From level 3 on the rows a neighbour taps next (4 * step either side: a quarter, then half of a 270-row strip) leave
+            // through the dense copy kernel instead of the tile kernel's dual stores: those are 16-byte stores `step` pixels
+            // apart, which crawl over NVLink (8 x B200, 4K: level 4 took 137 us against 61 us for the strip's own work).
+            post_push[level - 1] = push && !last && (4 << level) >= c->halo_copy_from_rows;
+            if (post_push[level - 1]) { post_ho[level - 1] = a.ho; memset(&a.ho, 0, sizeof(a.ho)); }
             largs[level - 1] = a;
             if (is_hist) new_hist = dst;     // denoise.cu:391: colour history := this level's output
             src = dst;
@@ -643,11 +650,17 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
         // One launch for the whole stage where possible (atrous.cu: atrous_stage_kernel), else level by level. (Per-level event
         // records: with the single launch they all follow it, so the first level's interval is the stage's.)
         if (atrous_stage_possible(c, largs, P->atrous_nlevel)) {
+            for (int l = 0; l < P->atrous_nlevel; l++) if (post_push[l]) largs[l].ho = post_ho[l];        // the stage kernel pushes and signals by itself
             CK(launch_atrous_stage(c, largs, P->atrous_nlevel));
             if (ev) for (int level = 1; level <= P->atrous_nlevel; level++) CK(cudaEventRecord(ev[2 + level], c->stream));
         } else {
             for (int level = 1; level <= P->atrous_nlevel; level++) {
-                CK(launch_atrous(c, largs[level - 1]));
+                const AtrousArgs &a = largs[level - 1];
+                CK(launch_atrous(c, a));
+                if (post_push[level - 1]) {
+                    const HaloPlane h[2] = {halo_plane(c->cv[a.dst_slot], c->p_cv[a.dst_slot]), halo_plane(c->lv[a.dst_slot], c->p_lv[a.dst_slot])};
+                    CK(launch_halo_push(c, 4 << level, h, 2, &post_ho[level - 1]));
+                }
                 if (ev) CK(cudaEventRecord(ev[2 + level], c->stream));
             }
         }

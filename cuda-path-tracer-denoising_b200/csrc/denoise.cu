@@ -331,12 +331,13 @@ struct PushArgs { PushSeg seg[SVGF_PUSH_MAXSEG]; };
 
 template <class V>
 __global__ void __launch_bounds__(256)
-halo_push_kernel(const __grid_constant__ PushArgs a) {
+halo_push_kernel(const __grid_constant__ PushArgs a, const __grid_constant__ HaloOut sig) {
     const PushSeg &s = a.seg[blockIdx.y];
     const V *__restrict__ src = static_cast<const V *>(s.src);
     V *__restrict__ dst = static_cast<V *>(s.dst);
     const size_t n = s.bytes / sizeof(V), stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+    halo_block_done(sig, true);         // sig.peers.n == 0: no flag follows from here
 }
 
 inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (rows + b.y - 1) / b.y); }
@@ -429,9 +430,12 @@ cudaError_t launch_pack_pbo(svgf_ctx *c, unsigned char *pbo, const float *left, 
 
 // Copies this rank's rows that lie within `halo_rows` of another rank's strip into that rank's copy of the plane(s): the
 // stand-alone form of the dual stores, for producers that do not push by themselves.
-cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes) {
+// `sig` (optional): the stage flag the kernel's last block raises in the peers' memory once all rows are on their way.
+cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes, const HaloOut *sig) {
     const HaloPeers hp = halo_peers(c, halo_rows);
     if (hp.n == 0) return cudaSuccess;
+    HaloOut so; memset(&so, 0, sizeof(so));
+    if (sig) so = *sig;
     PushArgs a; int nseg = 0; unsigned long long longest = 0; bool v16 = true;
     for (int i = 0; i < hp.n; i++) {
         const int r = hp.rank[i];
@@ -447,12 +451,19 @@ cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes
             nseg++;
         }
     }
-    if (nseg == 0) return cudaSuccess;
+    if (nseg == 0) {        // nothing to copy (planes not connected): the flag alone
+        if (so.peers.n > 0 && so.signal) {
+            FlagList l; l.n = 0;
+            for (int i = 0; i < so.peers.n; i++) l.flag[l.n++] = so.flag[i];
+            signal_kernel<<<1, 32, 0, c->stream>>>(l, so.seq);
+        }
+        return cudaGetLastError();
+    }
     const unsigned long long per_block = 256ull * (v16 ? 16 : 8) * 4;        // ~4 vectors per thread
     const unsigned gx = (unsigned)std::min<unsigned long long>((longest + per_block - 1) / per_block, 1024ull);
     dim3 g(gx ? gx : 1, nseg);
-    if (v16) halo_push_kernel<uint4><<<g, 256, 0, c->stream>>>(a);
-    else halo_push_kernel<uint2><<<g, 256, 0, c->stream>>>(a);
+    if (v16) halo_push_kernel<uint4><<<g, 256, 0, c->stream>>>(a, so);
+    else halo_push_kernel<uint2><<<g, 256, 0, c->stream>>>(a, so);
     return cudaGetLastError();
 }
 

@@ -535,7 +535,13 @@ __device__ __noinline__ F3 hit_point(F3 origin, F3 direction, float t) { return 
 // every trip of the loop intersects "the current ray" -- the path ray or the shadow ray -- so lanes that are in
 // different phases of their path still execute the same intersection code together, and the whole kernel fits the
 // instruction cache. Per-pixel results are unchanged: the RNG is re-seeded from (pixel, frame + depth) at every depth.
-constexpr int RT_BX = 8, RT_BY = 16;
+// Block (and with it warp) shape in pixels: a warp covers RT_BX x 32/RT_BX pixels. 8 x 4 measured best on B200 (tools/build_rt_ab.sh
+// builds 4 x 8, 16 x 2 and 32 x 1 through these macros; profiles/r2_ab_rt_warp_shape.jsonl).
+#ifndef SVGF_RT_BX
+#define SVGF_RT_BX 8
+#define SVGF_RT_BY 16
+#endif
+constexpr int RT_BX = SVGF_RT_BX, RT_BY = SVGF_RT_BY;
 enum { Q_PATH = 0, Q_SHADOW = 1 };
 
 // Sharded frames: the a-trous view of the G-buffer is needed up to 2 * 2^levels rows beyond a strip. The rows of MY strip

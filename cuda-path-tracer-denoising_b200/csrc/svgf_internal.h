@@ -176,6 +176,7 @@ struct svgf_ctx {
     bool scene_nan_possible = true, gbuf_nan_possible = true;
     int atrous_fused = 0;                   // SVGF_ATROUS_FUSED=1 (A/B): the a-trous stage as one launch (atrous_stage_kernel); measured slower, see atrous.cu
     unsigned *stage_ctr = nullptr; int stage_blocks = 0; bool stage_attr_set = false;
+    int halo_copy_from_rows = 32;           // sharded frames: levels whose next-level halo is at least this many rows push it with the copy kernel
     int opt_cuda_graph = 0;                 // 1: the frame's launches run as one CUDA graph, updated in place every frame (N1)
     cudaGraphExec_t graph_exec = nullptr; int frames_rendered = 0;
     cudaEvent_t legacy_fence = nullptr;     // svgf_denoise: orders the library's stream after the caller's legacy default stream
@@ -231,7 +232,7 @@ HaloPeers halo_peers(const svgf_ctx *c, int reach);
 HaloOut halo_out(svgf_ctx *c, int stage, int reach, bool fused_signal);
 HaloIn halo_in(svgf_ctx *c, int stage, int reach, unsigned seq);
 struct HaloPlane { const void *local; void *peer[SVGF_MAX_RANKS]; int esz; };     // esz = bytes per pixel (multiple of 8)
-cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes);
+cudaError_t launch_halo_push(svgf_ctx *c, int halo_rows, const HaloPlane *planes, int nplanes, const HaloOut *sig = nullptr);
 cudaError_t launch_signal(svgf_ctx *c, int stage, int reach);                 // reach < 0: every connected rank
 cudaError_t launch_wait(svgf_ctx *c, int stage, unsigned seq, int reach);
 cudaError_t launch_no_temporal(svgf_ctx *c, const float *image, float4 *acc_cv, float2 *acc_lv);
