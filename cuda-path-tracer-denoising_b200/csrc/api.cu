@@ -213,9 +213,13 @@ static int alloc_frame_buffers(svgf_ctx *c) {
         CK(cudaMemset(c->cv[i], 0, ppx * sizeof(float4))); CK(cudaMemset(c->lv[i], 0, ppx * sizeof(float2)));
     }
     for (int i = 0; i < 2; i++) { CK(dalloc(&c->nrm[i], px)); CK(dalloc(&c->mom[i], px)); CK(dalloc(&c->hlen[i], px)); }
-    CK(dalloc(&c->pos, px)); CK(dalloc(&c->alb, px)); CK(dalloc(&c->gnp, ppx)); CK(dalloc(&c->gzl, ppx));
-    CK(cudaMemset(c->gnp, 0, ppx * sizeof(float4))); CK(cudaMemset(c->gzl, 0, ppx * sizeof(float2)));
-    CK(dalloc(&c->image, 3 * px)); CK(dalloc(&c->denoised, 3 * px)); CK(dalloc(&c->var_out, px));
+    CK(dalloc(&c->pos, px));
+    for (int g = 0; g < 2; g++) {       // two sets of what the path tracer writes and the rest of the previous frame still reads (svgf_internal.h)
+        CK(dalloc(&c->alb_set[g], px)); CK(dalloc(&c->gnp_set[g], ppx)); CK(dalloc(&c->gzl_set[g], ppx)); CK(dalloc(&c->image_set[g], 3 * px));
+        CK(cudaMemset(c->gnp_set[g], 0, ppx * sizeof(float4))); CK(cudaMemset(c->gzl_set[g], 0, ppx * sizeof(float2)));
+    }
+    c->gset = 0; c->alb = c->alb_set[0]; c->gnp = c->gnp_set[0]; c->gzl = c->gzl_set[0]; c->image = c->image_set[0];
+    CK(dalloc(&c->denoised, 3 * px)); CK(dalloc(&c->var_out, px));
     CK(dalloc(&c->stale_nm, px)); CK(dalloc(&c->stale_uv, px)); CK(dalloc(&c->kl, px));
     CK(cudaMalloc((void **)&c->pbo_own, px * 8));
     CK(cudaMalloc((void **)&c->flags, SVGF_MAX_RANKS * SVGF_NUM_STAGES * sizeof(unsigned)));
@@ -270,6 +274,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3 || atoi(v) == 4 || atoi(v) == 5) ? atoi(v) : 2;    // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_BANDS")) c->atrous_slide_bands = atoi(v);
     if (const char *v = getenv("SVGF_CUDA_GRAPH")) c->opt_cuda_graph = atoi(v) != 0;
+    if (const char *v = getenv("SVGF_FRAME_OVERLAP")) c->frame_overlap = atoi(v) != 0;      // A/B testing
     if (const char *v = getenv("SVGF_HALO_COPY_FROM")) c->halo_copy_from_rows = atoi(v);        // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_FUSED")) c->atrous_fused = atoi(v) != 0;        // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_SHAPE")) c->atrous_shape = atoi(v);
@@ -316,7 +321,9 @@ int svgf_destroy(svgf_ctx *c) {
     cudaFree(c->done_count);
     if (c->comm_err) cudaFreeHost(c->comm_err);
     for (int i = 0; i < 2; i++) { cudaFree(c->nrm[i]); cudaFree(c->mom[i]); cudaFree(c->hlen[i]); }
-    cudaFree(c->pos); cudaFree(c->alb); cudaFree(c->gnp); cudaFree(c->gzl); cudaFree(c->image); cudaFree(c->denoised); cudaFree(c->var_out);
+    cudaFree(c->pos); cudaFree(c->denoised); cudaFree(c->var_out);
+    for (int g = 0; g < 2; g++) { cudaFree(c->alb_set[g]); cudaFree(c->gnp_set[g]); cudaFree(c->gzl_set[g]); cudaFree(c->image_set[g]); }
+    if (c->rt_stream) { cudaStreamSynchronize(c->rt_stream); cudaStreamDestroy(c->rt_stream); cudaEventDestroy(c->ev_rt_done); cudaEventDestroy(c->ev_temporal_done); }
     cudaFree(c->stale_nm); cudaFree(c->stale_uv); cudaFree(c->pbo_own); cudaFree(c->kl); cudaFree(c->flags); cudaFree(c->wf_mem); cudaFree(c->rt_counter);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c->aos_in); cudaFree(c->aos_out); cudaFree(c->aos_g);
@@ -352,9 +359,16 @@ int svgf_reset(svgf_ctx *c) {
         CK(cudaMemsetAsync(c->mom[i], 0, px * sizeof(float2), st));
         CK(cudaMemsetAsync(c->hlen[i], 0, px * sizeof(int), st));
     }
-    CK(cudaMemsetAsync(c->pos, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->alb, 0, px * sizeof(float4), st));
-    CK(cudaMemsetAsync(c->gnp, 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->gzl, 0, px * sizeof(float2), st));
-    CK(cudaMemsetAsync(c->image, 0, px * 12, st)); CK(cudaMemsetAsync(c->denoised, 0, px * 12, st));
+    if (c->rt_stream) CK(cudaStreamSynchronize(c->rt_stream));
+    c->temporal_done_valid = false;
+    CK(cudaMemsetAsync(c->pos, 0, px * sizeof(float4), st));
+    for (int g = 0; g < 2; g++) {
+        CK(cudaMemsetAsync(c->alb_set[g], 0, px * sizeof(float4), st));
+        CK(cudaMemsetAsync(c->gnp_set[g], 0, px * sizeof(float4), st)); CK(cudaMemsetAsync(c->gzl_set[g], 0, px * sizeof(float2), st));
+        CK(cudaMemsetAsync(c->image_set[g], 0, px * 12, st));
+    }
+    c->gset = 0; c->alb = c->alb_set[0]; c->gnp = c->gnp_set[0]; c->gzl = c->gzl_set[0]; c->image = c->image_set[0];
+    CK(cudaMemsetAsync(c->denoised, 0, px * 12, st));
     CK(cudaMemsetAsync(c->var_out, 0, px * 4, st));
     if (c->copy_stream) {       // images still in flight belong to the history being discarded
         CK(cudaStreamSynchronize(c->copy_stream));
@@ -496,6 +510,7 @@ int svgf_set_option(svgf_ctx *c, const char *name, int value) {
     if (!strcmp(name, "history_cap")) { if (value < 0) return SVGF_ERR_INVALID; c->opt_history_cap = value; return SVGF_OK; }
     if (!strcmp(name, "light_sampling_all")) { c->opt_light_sampling_all = value != 0; return SVGF_OK; }
     if (!strcmp(name, "cuda_graph")) { c->opt_cuda_graph = value != 0; return SVGF_OK; }
+    if (!strcmp(name, "frame_overlap")) { c->frame_overlap = value != 0; return SVGF_OK; }
     if (!strcmp(name, "spatial_variance_estimate")) { c->opt_spatial_variance = value != 0; return SVGF_OK; }
     c->err = std::string("svgf_set_option: unknown option '") + name + "'";
     return SVGF_ERR_UNKNOWN_NAME;
@@ -602,6 +617,8 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
         if (sharded) CK(launch_signal(c, SVGF_STAGE_TEMPORAL, 4));
     }
     if (ev) CK(cudaEventRecord(ev[2], c->stream));
+    // the next frame's path tracer may start from here (cross-frame overlap, frame_body): nothing below reads what it writes
+    if (c->ev_temporal_done) { CK(cudaEventRecord(c->ev_temporal_done, c->stream)); c->temporal_done_valid = true; }
     int new_hist = acc_slot;        // denoise.cu:366/370: colour history := accumulated (or input) colour
     if (P->right_view_option == 1) {
         // DebugView shows dev_history_length, i.e. the length BEFORE this frame's update (denoise.cu:374)
@@ -627,7 +644,7 @@ static int denoise_soa(svgf_ctx *c, const float *image, const svgf_camera *cam, 
             a.cv_in = c->cv[src];
             a.cv_out = (!last || is_hist) ? c->cv[dst] : nullptr;
             a.lv_in = c->lv[src]; a.lv_out = c->lv[dst]; a.dst_slot = dst;
-            a.nrm = c->nrm[c->cur_nrm]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
+            a.nrm = c->nrm[c->cur_nrm]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl; a.gset = c->gset;
             a.denoised_out = last ? c->denoised : nullptr; a.var_out = last ? c->var_out : nullptr;
             a.level = level; a.is_last = last; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
             a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;
@@ -740,7 +757,37 @@ static int frame_body(svgf_ctx *c, const svgf_camera *cam, const svgf_params *P,
     // extra live state does not fit its 64 registers.
     static const bool rt_push = getenv("SVGF_RT_PUSH") && atoi(getenv("SVGF_RT_PUSH")) != 0;
     c->gbuf_nan_possible = c->scene_nan_possible;      // this frame's G-buffer comes from our own path tracer
-    CK(launch_pathtrace(c, rp, c->nrm[c->cur_nrm], (rt_push && filter && c->halo_push && c->rows.world > 1) ? (2 << P->atrous_nlevel) : 0, &gbuf_pushed));
+    // Cross-frame overlap: this frame's path tracer goes to its own stream and starts as soon as the PREVIOUS frame's temporal
+    // pass -- the last reader of the buffers it writes that exist only once (normals of two frames ago, positions) -- has finished,
+    // next to that frame's a-trous stage (which is short of issue slots at every launch boundary and tail, while the path tracer
+    // never runs out of blocks). Frames of a single GPU in the denoising configuration only; not under the stage timers (whose
+    // intervals assume one stream) and not inside a captured graph.
+    const bool overlap = c->frame_overlap && c->rows.world == 1 && c->shard.row_begin == 0 && c->shard.row_end == c->H && !ev && !c->opt_cuda_graph &&
+                         P->denoise_enable && c->atrous_variant == 2 && c->rt_variant == 0;
+    if (overlap) {
+        if (!c->rt_stream) {
+            CK(cudaStreamCreateWithFlags(&c->rt_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c->ev_rt_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_temporal_done, cudaEventDisableTiming));
+        }
+        c->gset ^= 1;
+        c->alb = c->alb_set[c->gset]; c->gnp = c->gnp_set[c->gset]; c->gzl = c->gzl_set[c->gset]; c->image = c->image_set[c->gset];
+        // after the previous frame's temporal pass (if that frame ran without overlap, after all of it)
+        if (!c->temporal_done_valid) CK(cudaEventRecord(c->ev_temporal_done, c->stream));
+        CK(cudaStreamWaitEvent(c->rt_stream, c->ev_temporal_done, 0));
+        c->rt_launch_stream = c->rt_stream;
+    } else if (c->rt_stream) {
+        CK(cudaStreamWaitEvent(c->stream, c->ev_rt_done, 0));      // (defensive: every overlapped path tracer was already waited for)
+    }
+    c->temporal_done_valid = false;
+    {
+        const cudaError_t e = launch_pathtrace(c, rp, c->nrm[c->cur_nrm], (rt_push && filter && c->halo_push && c->rows.world > 1) ? (2 << P->atrous_nlevel) : 0, &gbuf_pushed);
+        c->rt_launch_stream = nullptr;
+        CK(e);
+    }
+    if (overlap) {
+        CK(cudaEventRecord(c->ev_rt_done, c->rt_stream));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_rt_done, 0));
+    }
     if (ev) CK(cudaEventRecord(ev[1], c->stream));
     if (P->denoise_enable) {
         int rc = denoise_soa(c, c->image, cam, P, ev, gbuf_pushed);
@@ -932,7 +979,7 @@ extern "C" int svgf_atrous_host(svgf_ctx *c, float *color_out, float *variance_o
     }
     AtrousArgs a;
     a.src_slot = 0;
-    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.lv_in = c->lv[0]; a.lv_out = c->lv[1]; a.dst_slot = 1; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl;
+    a.cv_in = c->cv[0]; a.cv_out = c->cv[1]; a.lv_in = c->lv[0]; a.lv_out = c->lv[1]; a.dst_slot = 1; a.nrm = c->nrm[0]; a.pos = c->pos; a.alb = c->alb; a.gnp = c->gnp; a.gzl = c->gzl; a.gset = c->gset;
     a.denoised_out = is_last ? c->denoised : nullptr; a.var_out = is_last ? c->var_out : nullptr;
     a.level = level; a.is_last = is_last != 0; a.blur_variance = P->blurvariance; a.addcolor = (P->sepcolor && P->addcolor);
     a.sigma_c = P->sigmal; a.sigma_n = P->sigman; a.sigma_x = P->sigmax;

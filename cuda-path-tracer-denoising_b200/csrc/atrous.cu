@@ -1112,7 +1112,7 @@ static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-enum { TM_PLANES = 2 * SVGF_NCV + 2, TM_LEVELS = SVGF_MAX_LEVELS + 1, TM_SHAPES = AT_NSHAPES };
+enum { TM_PLANES = 2 * SVGF_NCV + 4, TM_LEVELS = SVGF_MAX_LEVELS + 1, TM_SHAPES = AT_NSHAPES };      // cv x4, lv x4, {gnp, gzl} x 2 sets
 static inline CUtensorMap *tmap_at(svgf_ctx *c, int plane, int level, int shape) {
     return static_cast<CUtensorMap *>(c->tmaps) + ((plane * TM_LEVELS + level) * TM_SHAPES + shape);
 }
@@ -1140,7 +1140,10 @@ int atrous_build_tensor_maps(svgf_ctx *c) {
     }
     void *planes[TM_PLANES]; int fpp[TM_PLANES];
     for (int i = 0; i < SVGF_NCV; i++) { planes[i] = c->cv[i]; fpp[i] = 4; planes[SVGF_NCV + i] = c->lv[i]; fpp[SVGF_NCV + i] = 2; }
-    planes[2 * SVGF_NCV] = c->gnp; fpp[2 * SVGF_NCV] = 4; planes[2 * SVGF_NCV + 1] = c->gzl; fpp[2 * SVGF_NCV + 1] = 2;
+    for (int g = 0; g < 2; g++) {
+        planes[2 * SVGF_NCV + 2 * g] = c->gnp_set[g]; fpp[2 * SVGF_NCV + 2 * g] = 4;
+        planes[2 * SVGF_NCV + 2 * g + 1] = c->gzl_set[g]; fpp[2 * SVGF_NCV + 2 * g + 1] = 2;
+    }
     for (int pl = 0; pl < TM_PLANES; pl++)
         for (int level = 1; level <= SVGF_MAX_LEVELS; level++)
             for (int shp = 0; shp < TM_SHAPES; shp++) {
@@ -1169,8 +1172,8 @@ static int atrous_build_slide_maps(svgf_ctx *c, encode_fn_t encode) {
     if (!c->tmaps_slide) return 0;
     void *planes[TM_PLANES]; int fpp[TM_PLANES];
     for (int i = 0; i < SVGF_NCV; i++) { planes[i] = c->cv[i]; fpp[i] = 4; planes[SVGF_NCV + i] = c->lv[i]; fpp[SVGF_NCV + i] = 2; }
-    planes[2 * SVGF_NCV] = c->gnp; fpp[2 * SVGF_NCV] = 4; planes[2 * SVGF_NCV + 1] = c->gzl; fpp[2 * SVGF_NCV + 1] = 2;
-    for (int pl = 0; pl < TM_PLANES; pl++)
+    planes[2 * SVGF_NCV] = c->gnp_set[0]; fpp[2 * SVGF_NCV] = 4; planes[2 * SVGF_NCV + 1] = c->gzl_set[0]; fpp[2 * SVGF_NCV + 1] = 2;
+    for (int pl = 0; pl < 2 * SVGF_NCV + 2; pl++)       // (this A/B variant runs on G-buffer set 0 only: no cross-frame overlap)
         for (int level = 1; level <= SVGF_MAX_LEVELS; level++) {
             const cuuint64_t s = 1ull << level, W = c->W, H = c->H, f = fpp[pl];
             const cuuint64_t dims[4] = {f * s, (W + s - 1) / s, s, (H + s - 1) / s};
@@ -1340,7 +1343,7 @@ static void at_fill_level(svgf_ctx *c, const AtrousArgs &a, AtrousT &t) {
 static void at_set_maps(svgf_ctx *c, const AtrousArgs &a, AtrousT &t, int shape) {
     t.use_tma = 1;
     t.tm_cv = *tmap_at(c, a.src_slot, a.level, shape); t.tm_lv = *tmap_at(c, SVGF_NCV + a.src_slot, a.level, shape);
-    t.tm_np = *tmap_at(c, 2 * SVGF_NCV, a.level, shape); t.tm_zl = *tmap_at(c, 2 * SVGF_NCV + 1, a.level, shape);
+    t.tm_np = *tmap_at(c, 2 * SVGF_NCV + 2 * a.gset, a.level, shape); t.tm_zl = *tmap_at(c, 2 * SVGF_NCV + 2 * a.gset + 1, a.level, shape);
 }
 
 // Can the whole stage go out as one launch (atrous_stage_kernel)? TMA staging for every level, no in-place peer reads (single

@@ -1141,7 +1141,7 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
             cudaError_t e = cudaFuncSetAttribute(rt_kernel<MINB, PUSH, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                                      \
         }                                                                                                                        \
-        rt_kernel<MINB, PUSH, ML><<<grid, block, smem, c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh,    \
+        rt_kernel<MINB, PUSH, ML><<<grid, block, smem, c->rt_launch_stream ? c->rt_launch_stream : c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh,    \
                                                                     s.n_nodes, s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, \
                                                                     c->alb, c->image, c->stale_nm, c->stale_uv, c->gnp, c->gzl, push); \
     } while (0)

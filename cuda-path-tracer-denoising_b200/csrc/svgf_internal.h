@@ -176,6 +176,18 @@ struct svgf_ctx {
     bool scene_nan_possible = true, gbuf_nan_possible = true;
     int atrous_fused = 0;                   // SVGF_ATROUS_FUSED=1 (A/B): the a-trous stage as one launch (atrous_stage_kernel); measured slower, see atrous.cu
     unsigned *stage_ctr = nullptr; int stage_blocks = 0; bool stage_attr_set = false;
+    // Cross-frame overlap (single-GPU frames; option "frame_overlap" / SVGF_FRAME_OVERLAP=1, OFF by default): the path tracer of
+    // frame N + 1 runs on its own stream next to the a-trous stage of frame N. Bit-identical frames. Measured on B200
+    // (profiles/r2_ab_frame_overlap.txt): frames queued back to back gain 2-6 % (C2 745 -> 761 fps, C5 550 -> 583), but a caller
+    // that waits for every image (the pipelined e2e loop of bench.py) LOSES 4-19 % (C2 740 -> 714, C3 297 -> 242): the path
+    // tracer's blocks live ~58 us, so each of frame N's eleven denoise launches finds the SMs full of them and ramps up slowly,
+    // and with a-trous blocks resident the SM's carve-out is all shared memory, which costs the path tracer its L1. What the path tracer writes and the rest of the previous frame still reads
+    // exists twice (image, gnp, gzl, alb: `*_set`; c->image / gnp / gzl / alb are aliases of the current frame's set); everything
+    // else it writes (normals of two frames ago, positions) is last read by the previous frame's temporal pass, which it waits for.
+    int frame_overlap = 0, gset = 0;
+    float *image_set[2] = {nullptr, nullptr}; float4 *gnp_set[2] = {nullptr, nullptr}, *alb_set[2] = {nullptr, nullptr}; float2 *gzl_set[2] = {nullptr, nullptr};
+    cudaStream_t rt_stream = nullptr, rt_launch_stream = nullptr;      // rt_launch_stream: where launch_pathtrace puts its kernels (null: c->stream)
+    cudaEvent_t ev_rt_done = nullptr, ev_temporal_done = nullptr; bool temporal_done_valid = false;
     int halo_copy_from_rows = 32;           // sharded frames: levels whose next-level halo is at least this many rows push it with the copy kernel
     int opt_cuda_graph = 0;                 // 1: the frame's launches run as one CUDA graph, updated in place every frame (N1)
     cudaGraphExec_t graph_exec = nullptr; int frames_rendered = 0;
@@ -247,6 +259,7 @@ struct AtrousArgs {
     float *denoised_out; float *var_out;            // last level only (AoS vec3 + float plane)
     int level, is_last, blur_variance, addcolor;
     float sigma_c, sigma_n, sigma_x;
+    int gset = 0;                                   // which G-buffer set gnp/gzl belong to (selects their TMA descriptors)
     HaloIn wait{};                                  // sharded frames: flags to see before halo rows are read (n == 0: none)
     HaloOut ho{};                                   // ... and who gets this level's edge rows and its flag
 };

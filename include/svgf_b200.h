@@ -227,6 +227,10 @@ void *svgf_stream(svgf_ctx *ctx);
  *                                  stub). Single-GPU, whole-frame contexts.
  *   "cuda_graph"              0/1  (frame driver) the frame's kernels are launched as one CUDA graph that is
  *                                  re-captured and updated in place every frame; results are bit-identical.
+ *   "frame_overlap"           0/1  (frame driver) single-GPU frames: the path tracer of the next frame runs on a second stream next
+ *                                  to the a-trous stage of the current one (second set of the buffers both touch); bit-identical.
+ *                                  Helps when many frames are queued without waiting (+2-6 %), hurts a caller that waits for
+ *                                  every image (-4-19 %): off by default.
  *   "light_sampling_all"      0/1  every shadow ray samples one of the scene's emissive cubes/spheres (uniformly, contribution
  *                                  scaled by their number) instead of geoms[0] only (pathtrace.cu:359-361). */
 int svgf_set_option(svgf_ctx *ctx, const char *name, int value);

@@ -108,3 +108,47 @@ def test_cuda_graph_frames_are_bit_identical(scene, moving):
     for f, (a, b) in enumerate(zip(*outs)):
         for x, y, what in zip(a, b, ("image", "variance", "history_length", "pbo")):
             assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), "frame %d: %s differs with the CUDA graph" % (f, what)
+
+
+@pytest.mark.parametrize("case", [("cornell", 640, 360, 5, False, {}), ("bunny", 512, 288, 5, True, {}), ("room", 320, 200, 3, True, {"temporal_enable": 0}),
+                                  ("cornell", 256, 256, 5, False, {"toggle": 1})], ids=lambda c: "%s-%dx%d%s" % (c[0], c[1], c[2], "-".join([""] + list(c[5]))))
+def test_cross_frame_overlap_is_bit_identical(case, monkeypatch):
+    """Cross-frame overlap (csrc/api.cu: frame_body): on a single GPU the path tracer of frame N + 1 runs on its own stream next to
+    the a-trous stage of frame N, on a second set of the buffers both touch. Every frame's image, and the state the last frame
+    leaves, must be the bits of the serial schedule (SVGF_FRAME_OVERLAP=0) -- pipelined calls, frames queued back to back without
+    any synchronisation, a parameter change in the middle (denoiser off and on again: the running-mean path does not overlap),
+    a reset."""
+    scene, W, H, nl, moving, over = case
+    toggle = over.pop("toggle", 0) if isinstance(over, dict) else 0
+    over = {k: v for k, v in over.items() if k != "toggle"}
+    outs = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("SVGF_FRAME_OVERLAP", on)
+        m = svgf()
+        blob, R = m.open_scene(scene, W, H)
+        drv = blob.camera_driver(W, H, automate=moving)
+        bufs = [np.zeros((H, W, 3), np.float32) for _ in range(2)]
+        got = []
+        n = 9
+        for f in range(n):
+            P = m.default_params(atrous_nlevel=nl, **over)
+            if toggle and f in (4, 5):
+                P = m.default_params(atrous_nlevel=nl, denoise_enable=0)
+            R.pathtrace_async(drv.step(), P, f, bufs[f & 1])
+            if f >= 1:
+                R.wait_image(bufs[(f - 1) & 1]); got.append(bufs[(f - 1) & 1].copy())
+        R.wait_image(bufs[(n - 1) & 1]); got.append(bufs[(n - 1) & 1].copy())
+        # frames queued back to back, nothing waited for until the end
+        P = m.default_params(atrous_nlevel=nl, **over)
+        for f in range(n, n + 6):
+            R.pathtrace(drv.step(), P, f)
+        got.append(R.fetch("denoised")); got.append(R.fetch("variance")); got.append(R.fetch("history_length")); got.append(R.fetch("image")); got.append(R.fetch("gbuffer"))
+        R.reset()
+        drv = blob.camera_driver(W, H, automate=moving)
+        for f in range(3):
+            R.pathtrace(drv.step(), P, f)
+        got.append(R.fetch("denoised")); got.append(R.fetch("pbo"))
+        outs.append(got); R.close()
+    assert len(outs[0]) == len(outs[1])
+    for i, (a, b) in enumerate(zip(*outs)):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), "output %d differs between the overlapped and the serial schedule" % i

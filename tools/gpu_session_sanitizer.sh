@@ -5,6 +5,6 @@
 mkdir -p gpurun_out
 K='test_every_tile_shape_matches_oracle or test_tiny_and_ragged_sizes or test_sharded_equals_unsharded_bitwise or test_uneven_partition or test_async_equals_blocking or test_sliding_variant_matches_oracle'
 for tool in memcheck racecheck; do
-  timeout 1500 compute-sanitizer --tool $tool --target-processes all --print-limit 20 python -m pytest tests -m gpu -q -x -k "$K" > gpurun_out/sanitizer_$tool.log 2>&1
+  timeout 700 compute-sanitizer --tool $tool --target-processes all --print-limit 20 python -m pytest tests -m gpu -q -x -k "$K" > gpurun_out/sanitizer_$tool.log 2>&1
   echo "== $tool: exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/sanitizer_$tool.log | tail -5
 done
