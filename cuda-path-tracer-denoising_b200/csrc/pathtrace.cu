@@ -1088,7 +1088,7 @@ static cudaError_t launch_pathtrace_wavefront(svgf_ctx *c, const RtParams &p, fl
 // Loads every kernel of this file now (see svgf_preload_kernels, api.cu).
 void preload_pathtrace_kernels() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, rt_kernel<8, false, false>); cudaFuncGetAttributes(&a, rt_kernel<8, true, false>);
+    cudaFuncGetAttributes(&a, rt_kernel<8, false, false>); cudaFuncGetAttributes(&a, rt_kernel<8, true, false>); cudaFuncGetAttributes(&a, rt_kernel<7, false, false>);
     cudaFuncGetAttributes(&a, rt_kernel<4, false, false>); cudaFuncGetAttributes(&a, rt_kernel<4, true, false>);
     cudaFuncGetAttributes(&a, rt_kernel<8, false, true>); cudaFuncGetAttributes(&a, rt_kernel<8, true, true>);
     cudaFuncGetAttributes(&a, rt_persistent_kernel);
@@ -1152,7 +1152,16 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
     const bool do_push = push.peers.n > 0;
     if (p.n_lights > 1) { if (do_push) RT_LAUNCH(8, true, true); else RT_LAUNCH(8, false, true); }
     else if (minb == 4) { if (do_push) RT_LAUNCH(4, true, false); else RT_LAUNCH(4, false, false); }
-    else { if (do_push) RT_LAUNCH(8, true, false); else RT_LAUNCH(8, false, false); }
+#ifdef SVGF_RT_MINB_AB      // A/B build (tools/build_rt_ab.sh): another occupancy target for the default kernel
+    else { if (do_push) RT_LAUNCH(8, true, false); else RT_LAUNCH(SVGF_RT_MINB_AB, false, false); }
+#else
+    // 7 blocks/SM (73 registers) against 8 (64), measured on B200 (profiles/r2_ab_rt_blocks_per_sm.jsonl): a scene of cubes and
+    // spheres only is short of registers (C2 774 vs 805 us), a scene with meshes is short of warps to hide the BVH loads behind
+    // (C3 2909 vs 2800 us). 5 and 6 lose on both.
+    else if (do_push) RT_LAUNCH(8, true, false);
+    else if (s.n_tris == 0 && minb == 8) RT_LAUNCH(7, false, false);
+    else RT_LAUNCH(8, false, false);
+#endif
 #undef RT_LAUNCH
     return cudaGetLastError();
 }

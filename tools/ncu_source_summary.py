@@ -7,8 +7,11 @@ hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]; idx = {n: i for i, n in enumerate(h)}
 stall = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
 tot = collections.Counter(); byop = collections.Counter(); execs = collections.Counter(); samples = 0; hot = []
+seen = set()
 for r in rows[hi + 1:]:
     if len(r) < len(h) or r[0] == "Address": continue
+    if r[0] in seen: continue           # the page lists every instruction twice (SASS view and source-correlated view)
+    seen.add(r[0])
     src = r[idx["Source"]].strip()
     m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", src)
     op = m.group(2) if m else "?"
