@@ -272,13 +272,21 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---- end to end, pipelined: the image of frame N is waited for (= consumed) while frame N+1 renders ----
     barrier()
     t0 = time.perf_counter()
+    t_cam = t_submit = t_wait = 0.0                 # where the host's share of the loop goes (reported, not subtracted)
     for i in range(args.steps):
-        R.pathtrace_async(drv.step(), P, frame, bufs[i & 1]); frame += 1
+        ta = time.perf_counter()
+        cam_i = drv.step()
+        tb = time.perf_counter()
+        R.pathtrace_async(cam_i, P, frame, bufs[i & 1]); frame += 1
+        tc = time.perf_counter()
         if i >= 1:
             R.wait_image(bufs[(i - 1) & 1])
+        td = time.perf_counter()
+        t_cam += tb - ta; t_submit += tc - tb; t_wait += td - tc
     R.wait_image(bufs[(args.steps - 1) & 1])
     R.sync()
     ms_e2e = (time.perf_counter() - t0) * 1e3      # host clock: the last image has landed
+    host_split = {"camera_ms": t_cam * 1e3 / args.steps, "submit_ms": t_submit * 1e3 / args.steps, "wait_ms": t_wait * 1e3 / args.steps}
     barrier()
     clk = clocks.stop()
     if world > 1 and R.peer_error():
@@ -352,6 +360,7 @@ def run_ours(args, wl, rank, world, local_rank):
         "e2e": {"value": fps_e2e * px / 1e6, "unit": "Mpixels/sec", "fps": fps_e2e, "h2d_bytes_per_step": (84 + 80) * world,
                 "d2h_bytes_per_step": px * 12, "ms_per_step": ms_e2e / args.steps,
                 "api": "svgf_render_async + svgf_wait_image (one frame in flight, every image waited for; host clock)",
+                "host_ms_per_step": host_split,
                 "blocking": {"value": fps_blk * px / 1e6, "fps": fps_blk, "ms_per_step": ms_blk / args.steps,
                              "api": "svgf_render(..., host_image): returns with the image in place, like the reference's pathtrace()"},
                 "note": "every rank copies its own strip of the image to its host buffer each frame" if world > 1 else "whole image to host each frame"},

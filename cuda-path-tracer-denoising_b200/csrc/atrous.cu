@@ -170,6 +170,13 @@ struct AtrousT {
 // Pre-pass of a level: per-pixel luminance-weight scale  kl = log2(e) / (sqrt(max(blur3x3(variance), 0)) * sigma_l + 1e-6)
 // (denoise.cu:100-118,143). The 3x3 Gaussian lives in PIXEL space, i.e. across residue classes, so it is done here where
 // it is coalesced instead of per lattice point inside the tiled kernel. 8 B read (L1-shared) + 4 B written per pixel.
+// Programmatic dependent launch (at_launch_kernel): let the next kernel of the stream start launching, then wait until the
+// previous one has completed and its stores are visible. Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void at_pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // COHERENT: loads that must see what OTHER blocks of the same launch stored (the fused stage kernel): L2 only, never L1.
 template <bool COHERENT> __device__ __forceinline__ float4 at_ld4(const float4 *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
 template <bool COHERENT> __device__ __forceinline__ float at_ld1(const float *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
@@ -245,6 +252,7 @@ atrous_kl_kernel(const __grid_constant__ PeerPtr<const float2> lv, const __grid_
     // first and the last block row read such rows here (+-1 row); they wait for the neighbours' flags -- for every neighbour in
     // reach of the level, so that the tile kernel, which starts after this grid has drained, finds its whole apron in place.
     // Interior blocks start at once; the waiting blocks are a few dozen, so they cannot keep a producer off the SMs.
+    at_pdl_sync();
     if (wait.n > 0 && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) {
         if (threadIdx.x == 0 && threadIdx.y == 0) halo_wait(wait);
         __syncthreads();
@@ -425,6 +433,7 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     const int X0 = cg * AT_C;
     const int a0 = tile_x * AT_LX - 2, b0 = t.b_first + tile_y * LY - 2;
     const int tid = threadIdx.x;
+    at_pdl_sync();
 
     // does this block store edge rows into a neighbour's planes? (block-uniform; only such blocks fence at system scope)
     const bool pushes = k.cv_out != nullptr && halo_rows_touch(t.ho.peers, yc + (b0 + 2) * step, yc + (b0 + 1 + LY) * step);
@@ -1066,6 +1075,22 @@ void atrous_scales(float sigma_n, float sigma_x, float *kn, float *kx) {
     *kx = (float)(log2e / ((double)sigma_x + 1e-6));
 }
 
+// Programmatic dependent launch (the default; SVGF_PDL=0 for A/B): the kl pre-pass and the tile kernel of the a-trous chain are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, trigger their dependents as their first instruction
+// (griddepcontrol.launch_dependents) and wait for their prerequisite grid right after (griddepcontrol.wait, before the first
+// read of anything another kernel wrote). The next kernel's blocks are thus resident, past their launch latency and set-up, when
+// the previous grid's last block retires -- instead of the ~2-3 us between two dependent launches of a stream.
+static bool g_pdl = !getenv("SVGF_PDL") || atoi(getenv("SVGF_PDL")) != 0;
+template <class... KArgs, class... Args>
+static cudaError_t at_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ---- tile shapes ------------------------------------------------------------------------------------------------------
 // One entry per instantiation of the tiled kernel. `warp_rows` = lattice rows one warp covers (work is issued per warp, and a
 // warp whose patches all lie outside the strip exits right after the tile has landed).
@@ -1076,7 +1101,7 @@ struct AtShapeInfo {
 };
 template <int LX, int LY, int TY, int MINB> static void at_launch(dim3 grid, cudaStream_t st, const AtrousT &t) {
     using SH = AtShape<LX, LY, TY>;
-    atrous_tiled_kernel<LX, LY, TY, MINB><<<grid, SH::THREADS, SH::SMEM, st>>>(t);
+    (void)at_launch_kernel(atrous_tiled_kernel<LX, LY, TY, MINB, true>, grid, dim3(SH::THREADS), SH::SMEM, st, t);
 }
 template <int LX, int LY, int TY, int MINB> static AtShapeInfo at_info() {
     using SH = AtShape<LX, LY, TY>;
@@ -1086,9 +1111,9 @@ template <int LX, int LY, int TY, int MINB> static AtShapeInfo at_info() {
 // the two default shapes once more without the NaN guard of the distances (frames whose G-buffer cannot hold a NaN)
 template <int LX, int LY, int TY, int MINB> static void at_launch_nonan(dim3 grid, cudaStream_t st, const AtrousT &t) {
     using SH = AtShape<LX, LY, TY>;
-    atrous_tiled_kernel<LX, LY, TY, MINB, false><<<grid, SH::THREADS, SH::SMEM, st>>>(t);
+    (void)at_launch_kernel(atrous_tiled_kernel<LX, LY, TY, MINB, false>, grid, dim3(SH::THREADS), SH::SMEM, st, t);
 }
-enum { AT_NSHAPES = 11 };
+enum { AT_NSHAPES = 13 };
 static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
     at_info<16, 32, 4, 3>(),    // 0: 128 threads, 69 KB, 3 blocks/SM
     at_info<32, 16, 4, 3>(),    // 1: 128 threads, 69 KB, 3 blocks/SM
@@ -1101,6 +1126,8 @@ static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
     at_info<32, 8, 2, 5>(),     // 8: 128 threads, 41 KB, 5 blocks/SM (lattices of a few rows: strips of a sharded frame)
     at_info<16, 12, 2, 6>(),    // 9:  96 threads, 31 KB, 6-7 blocks/SM
     at_info<32, 12, 2, 3>(),    // 10: 192 threads, 55 KB, 3 blocks/SM
+    at_info<16, 16, 2, 4>(),    // 11: shape 2 at 4 blocks/SM (128 registers: more pairs in flight per warp, fewer warps) -- A/B
+    at_info<16, 16, 2, 3>(),    // 12: shape 2 at 3 blocks/SM (168 registers) -- A/B
 };
 
 // ---- TMA descriptors ------------------------------------------------------------------------------------------------
@@ -1433,7 +1460,7 @@ cudaError_t launch_atrous(svgf_ctx *c, const AtrousArgs &a) {
     // line, ~400 L1 wavefronts per warp on the pipe the tile's shared-memory reads also use. Parity was green; removed.)
     {
         dim3 b(32, 8), g(((c->W + 3) / 4 + 31) / 32, (rows + 7) / 8);
-        atrous_kl_kernel<<<g, b, 0, c->stream>>>(pv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c, a.wait);
+        (void)at_launch_kernel(atrous_kl_kernel, g, b, 0, c->stream, pv, t.ro, c->kl, c->W, c->H, k.row_begin, k.row_end, k.blur_variance, k.sigma_c, a.wait);
     }
     const int step = k.step;
     const int lat_w = (c->W + step - 1) / step;                                 // lattice columns per class

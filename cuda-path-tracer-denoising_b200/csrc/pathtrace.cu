@@ -1155,11 +1155,11 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
 #ifdef SVGF_RT_MINB_AB      // A/B build (tools/build_rt_ab.sh): another occupancy target for the default kernel
     else { if (do_push) RT_LAUNCH(8, true, false); else RT_LAUNCH(SVGF_RT_MINB_AB, false, false); }
 #else
-    // 7 blocks/SM (73 registers) against 8 (64), measured on B200 (profiles/r2_ab_rt_blocks_per_sm.jsonl): a scene of cubes and
-    // spheres only is short of registers (C2 774 vs 805 us), a scene with meshes is short of warps to hide the BVH loads behind
-    // (C3 2909 vs 2800 us). 5 and 6 lose on both.
+    // 7 blocks/SM (72 registers) against 8 (64), measured on B200 (profiles/r2_ab_rt_blocks_per_sm.jsonl): a scene of cubes and
+    // spheres with next to no mesh (cornell: 38 triangles, 11 BVH nodes) is short of registers (C2 774 vs 805 us), a scene with
+    // real meshes is short of warps to hide the BVH loads behind (room, 819 nodes: 2909 vs 2800 us). 5 and 6 lose on both.
     else if (do_push) RT_LAUNCH(8, true, false);
-    else if (s.n_tris == 0 && minb == 8) RT_LAUNCH(7, false, false);
+    else if (s.n_nodes <= 64 && minb == 8) RT_LAUNCH(7, false, false);
     else RT_LAUNCH(8, false, false);
 #endif
 #undef RT_LAUNCH
