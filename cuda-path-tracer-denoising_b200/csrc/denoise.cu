@@ -152,7 +152,13 @@ struct TemporalPush {           // sharded frames: the neighbours' copies of the
     float4 *cv[SVGF_MAX_RANKS - 1]; float2 *lv[SVGF_MAX_RANKS - 1];
 };
 
-__global__ void __launch_bounds__(256)
+// 8 blocks/SM (32 registers, full occupancy): the kernel waits on three dependent round trips to memory per pixel, so resident
+// warps are what hides them. Measured on B200, C2 / C5: 48 registers, 5 blocks 63.5 / 62.6 us; 40, 6 blocks 58.2 / 54.3;
+// 32, 8 blocks 56.1 / 52.8 (profiles/r2_ab_temporal_blocks_per_sm.txt).
+#ifndef SVGF_TEMPORAL_MINB
+#define SVGF_TEMPORAL_MINB 8
+#endif
+__global__ void __launch_bounds__(256, SVGF_TEMPORAL_MINB)
 temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
                 const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
                 const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,
