@@ -152,13 +152,13 @@ struct TemporalPush {           // sharded frames: the neighbours' copies of the
     float4 *cv[SVGF_MAX_RANKS - 1]; float2 *lv[SVGF_MAX_RANKS - 1];
 };
 
-// 8 blocks/SM (32 registers, full occupancy): the kernel waits on three dependent round trips to memory per pixel, so resident
-// warps are what hides them. Measured on B200, C2 / C5: 48 registers, 5 blocks 63.5 / 62.6 us; 40, 6 blocks 58.2 / 54.3;
-// 32, 8 blocks 56.1 / 52.8 (profiles/r2_ab_temporal_blocks_per_sm.txt).
-#ifndef SVGF_TEMPORAL_MINB
-#define SVGF_TEMPORAL_MINB 8
-#endif
-__global__ void __launch_bounds__(256, SVGF_TEMPORAL_MINB)
+// Occupancy hints are NOT safe here: with `__launch_bounds__(256, N)`, N >= 5, the kernel runs 8-12 % faster (32 registers, 8
+// blocks/SM: 56 us instead of 63.5 at C2) but the history lengths of moving-camera frames stop matching the reference's
+// (tests/test_gpu_parity.py, test_gpu_denoise_entry.py: 18 failures): the reprojected coordinate decides validity by exact float
+// comparisons, and the other schedule contracts or orders a handful of operations differently. Until the reprojection arithmetic
+// is pinned with explicit intrinsics the kernel keeps the compiler's own allocation (48 registers, 5 blocks/SM).
+// profiles/r2_ab_temporal_blocks_per_sm.txt has the timings.
+__global__ void __launch_bounds__(256)
 temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
                 const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
                 const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,
