@@ -84,17 +84,21 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
         }
         float pr = 0.f, pg = 0.f, pb = 0.f, pm1 = 0.f, pm2 = 0.f, phl = 0.f;
         if (valid) {
+            // The operations are spelled out (one rounding each, fused exactly where nvcc fuses the reference's expressions:
+            // `acc += w * h` is an FMA, the weights are plain products, `sumw += w` a plain add): left to the optimiser, another
+            // register budget re-associated this block and moved (int)phl across an integer for a few pixels per frame.
             float sumw = 0.0f;
-            const float w[4] = {(1 - fracx) * (1 - fracy), fracx * (1 - fracy), (1 - fracx) * fracy, fracx * fracy};
+            const float ofx = __fsub_rn(1.0f, fracx), ofy = __fsub_rn(1.0f, fracy);
+            const float w[4] = {__fmul_rn(ofx, ofy), __fmul_rn(fracx, ofy), __fmul_rn(ofx, fracy), __fmul_rn(fracx, fracy)};
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 if (v[s]) {
                     const int o = owner_of(ro, qi[s] / W);
                     const float4 hc = __ldg(&hist_cv.p[o][qi[s]]); const float2 hm = __ldg(&mom_hist.p[o][qi[s]]);
-                    pr += w[s] * hc.x; pg += w[s] * hc.y; pb += w[s] * hc.z;
-                    pm1 += w[s] * hm.x; pm2 += w[s] * hm.y;
-                    phl += w[s] * (float)__ldg(&hlen_tab.p[o][qi[s]]);
-                    sumw += w[s];
+                    pr = __fmaf_rn(w[s], hc.x, pr); pg = __fmaf_rn(w[s], hc.y, pg); pb = __fmaf_rn(w[s], hc.z, pb);
+                    pm1 = __fmaf_rn(w[s], hm.x, pm1); pm2 = __fmaf_rn(w[s], hm.y, pm2);
+                    phl = __fmaf_rn(w[s], (float)__ldg(&hlen_tab.p[o][qi[s]]), phl);
+                    sumw = __fadd_rn(sumw, w[s]);
                 }
             }
             if (sumw >= 0.01) {
@@ -112,9 +116,9 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
                         q = (int)(lx + (float)W * ly);
                         const int o = owner_of(ro, q / W);
                         const float4 hc = __ldg(&hist_cv.p[o][q]); const float2 hm = __ldg(&mom_hist.p[o][q]);
-                        pr += hc.x; pg += hc.y; pb += hc.z; pm1 += hm.x; pm2 += hm.y;
-                        phl += (float)__ldg(&hlen_tab.p[o][q]);
-                        cnt += 1.0f;
+                        pr = __fadd_rn(pr, hc.x); pg = __fadd_rn(pg, hc.y); pb = __fadd_rn(pb, hc.z); pm1 = __fadd_rn(pm1, hm.x); pm2 = __fadd_rn(pm2, hm.y);
+                        phl = __fadd_rn(phl, (float)__ldg(&hlen_tab.p[o][q]));
+                        cnt = __fadd_rn(cnt, 1.0f);
                     }
                 }
             }
@@ -152,13 +156,12 @@ struct TemporalPush {           // sharded frames: the neighbours' copies of the
     float4 *cv[SVGF_MAX_RANKS - 1]; float2 *lv[SVGF_MAX_RANKS - 1];
 };
 
-// Occupancy hints are NOT safe here: with `__launch_bounds__(256, N)`, N >= 5, the kernel runs 8-12 % faster (32 registers, 8
-// blocks/SM: 56 us instead of 63.5 at C2) but the history lengths of moving-camera frames stop matching the reference's
-// (tests/test_gpu_parity.py, test_gpu_denoise_entry.py: 18 failures): the reprojected coordinate decides validity by exact float
-// comparisons, and the other schedule contracts or orders a handful of operations differently. Until the reprojection arithmetic
-// is pinned with explicit intrinsics the kernel keeps the compiler's own allocation (48 registers, 5 blocks/SM).
-// profiles/r2_ab_temporal_blocks_per_sm.txt has the timings.
-__global__ void __launch_bounds__(256)
+// 8 blocks/SM (32 registers, full occupancy): the kernel sits out three dependent round trips to memory per pixel, and resident
+// warps are what hides them (C2 / C5: 63.5 / 62.6 us at the compiler's own 48 registers, 56 / 53 us here,
+// profiles/r2_ab_temporal_blocks_per_sm.txt). The hint changes how the optimiser fuses and re-associates the bilinear
+// accumulation of temporal_pixel -- with the arithmetic left to it, the history lengths of moving-camera frames stopped matching
+// the reference's (18 parity tests) -- which is why that block is written with explicit single-rounding intrinsics.
+__global__ void __launch_bounds__(256, 8)
 temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
                 const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
                 const __grid_constant__ PeerPtr<float4> hist_cv, const __grid_constant__ PeerPtr<float2> mom_hist,
