@@ -67,6 +67,11 @@ def main():
                "kernel": "atrous_tiled_kernel (+ atrous_kl_kernel pre-pass)", "per_launch_tiled_bytes": tiled, "per_launch_kl_bytes": kl,
                "dram_bytes_per_launch": sum(per_level) / max(n, 1),
                "algorithmic_bytes_per_launch_1080p": [116121600, 116121600, 116121600, 116121600, 141004800]}
+        # bench.py reports `roofline.traffic` from this file only while the a-trous kernel sources are the ones captured
+        import os, sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+        out["kernel_source_hash"] = bench.kernel_source_hash()
         json.dump(out, open(a.traffic_json, "w"), indent=1)
 
 
