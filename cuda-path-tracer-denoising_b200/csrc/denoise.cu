@@ -59,17 +59,20 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
     if (N > 0 && __float_as_int(ncur.w) != -1) {
         const float4 pp = pos[p];
         // prev_viewmat * vec4(position, 1): (m0 v0 + m1 v1) + (m2 v2 + m3 v3), glm type_mat4x4.inl:617-628
-        const float vx = (vm.m[0] * pp.x + vm.m[4] * pp.y) + (vm.m[8] * pp.z + vm.m[12] * 1.0f);
-        const float vy = (vm.m[1] * pp.x + vm.m[5] * pp.y) + (vm.m[9] * pp.z + vm.m[13] * 1.0f);
-        const float vz = (vm.m[2] * pp.x + vm.m[6] * pp.y) + (vm.m[10] * pp.z + vm.m[14] * 1.0f);
+        // (every operation below is spelled out with the rounding and the fusion nvcc gives the reference's expressions -- the
+        // product m1 v1 rounded, m0 v0 fused onto it; m2 v2 fused onto m3 * 1 -- because which pixel the history comes from, and
+        // with it the integer history length, hangs on the last bit of these coordinates)
+        const float vx = __fadd_rn(__fmaf_rn(vm.m[0], pp.x, __fmul_rn(vm.m[4], pp.y)), __fmaf_rn(vm.m[8], pp.z, vm.m[12]));
+        const float vy = __fadd_rn(__fmaf_rn(vm.m[1], pp.x, __fmul_rn(vm.m[5], pp.y)), __fmaf_rn(vm.m[9], pp.z, vm.m[13]));
+        const float vz = __fadd_rn(__fmaf_rn(vm.m[2], pp.x, __fmul_rn(vm.m[6], pp.y)), __fmaf_rn(vm.m[10], pp.z, vm.m[14]));
         // clip_rx = clip_ry = 1 reproduces the reference, which leaves out the FOV/aspect term (denoise.cu:201-207: exact only
         // for FOVY 45 and square frames; x * 1.0f is exact, so the default path keeps its bits). SURVEY.md 8(f) N4 switch
         // "reprojection_fov_aspect": 1 / (tan(fovy) * aspect) and 1 / tan(fovy), the inverse of generateRayFromCamera's scaling.
-        const float clipx = (vx / vz) * clip_rx, clipy = (vy / vz) * clip_ry;
-        const float ndcx = -clipx * 0.5f + 0.5f, ndcy = -clipy * 0.5f + 0.5f;
-        const float prevx = ndcx * W - 0.5f, prevy = ndcy * H - 0.5f;
+        const float clipx = __fmul_rn(__fdiv_rn(vx, vz), clip_rx), clipy = __fmul_rn(__fdiv_rn(vy, vz), clip_ry);
+        const float ndcx = __fmaf_rn(clipx, -0.5f, 0.5f), ndcy = __fmaf_rn(clipy, -0.5f, 0.5f);
+        const float prevx = __fmaf_rn(ndcx, (float)W, -0.5f), prevy = __fmaf_rn(ndcy, (float)H, -0.5f);
         const float floorx = floorf(prevx), floory = floorf(prevy);
-        const float fracx = prevx - floorx, fracy = prevy - floory;
+        const float fracx = __fsub_rn(prevx, floorx), fracy = __fsub_rn(prevy, floory);
         bool valid = (floorx >= 0 && floory >= 0 && floorx < W && floory < H);
         // glm::ivec2(floorx, floory) + offset: saturating cvt, wrapping integer add (as the reference's SASS)
         const int ifx = __float2int_rz(floorx), ify = __float2int_rz(floory);
