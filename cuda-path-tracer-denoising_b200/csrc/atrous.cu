@@ -302,10 +302,10 @@ __device__ __forceinline__ bool at_stage_tile(const AtrousT &t, float4 *s_cv, fl
         if (tid == 0) {
 #pragma unroll
             for (int par = 0; par < 2; par++) {     // a0 is even: window column ta has parity ta & 1 and pair index a0/2 + ta/2
-                cde::cp_async_bulk_tensor_5d_global_to_shared(s_cv + par * HALF, &t.tm_cv, 4 * X0, par, a0 >> 1, yc, b0, bar);
-                cde::cp_async_bulk_tensor_5d_global_to_shared(s_np + par * HALF, &t.tm_np, 4 * X0, par, a0 >> 1, yc, b0, bar);
-                cde::cp_async_bulk_tensor_5d_global_to_shared(s_zl + par * HALF, &t.tm_zl, 2 * X0, par, a0 >> 1, yc, b0, bar);
-                cde::cp_async_bulk_tensor_5d_global_to_shared(s_lv + par * HALF, &t.tm_lv, 2 * X0, par, a0 >> 1, yc, b0, bar);
+                cde::cp_async_bulk_tensor_5d_global_to_shared(s_cv + par * SH::HALFP, &t.tm_cv, 4 * X0, par, a0 >> 1, yc, b0, bar);
+                cde::cp_async_bulk_tensor_5d_global_to_shared(s_np + par * SH::HALFP, &t.tm_np, 4 * X0, par, a0 >> 1, yc, b0, bar);
+                cde::cp_async_bulk_tensor_5d_global_to_shared(s_zl + par * SH::HALFP, &t.tm_zl, 2 * X0, par, a0 >> 1, yc, b0, bar);
+                cde::cp_async_bulk_tensor_5d_global_to_shared(s_lv + par * SH::HALFP, &t.tm_lv, 2 * X0, par, a0 >> 1, yc, b0, bar);
             }
             token = cuda::device::barrier_arrive_tx(bar, 1, TILE * 48);
         } else {
@@ -423,9 +423,9 @@ atrous_tiled_kernel(const __grid_constant__ AtrousT t) {
     static_assert(SH::OK, "tile shape");
     constexpr int AT_LX = LX, AT_SW = SH::SW, AT_SH = SH::SH, AT_THREADS = SH::THREADS, TILE = SH::TILE, HALF = SH::HALF;
     extern __shared__ __align__(128) unsigned char at_smem_raw[];
-    float4 *s_cv = reinterpret_cast<float4 *>(at_smem_raw), *s_np = s_cv + TILE;
-    float2 *s_zl = reinterpret_cast<float2 *>(s_np + TILE), *s_lv = s_zl + TILE;
-    barrier_t &bar = *reinterpret_cast<barrier_t *>(at_smem_raw + TILE * 48);
+    float4 *s_cv = reinterpret_cast<float4 *>(at_smem_raw), *s_np = s_cv + SH::TILEP;
+    float2 *s_zl = reinterpret_cast<float2 *>(s_np + SH::TILEP), *s_lv = s_zl + SH::TILEP;
+    barrier_t &bar = *reinterpret_cast<barrier_t *>(at_smem_raw + SH::TILEP * 48);
     const AtrousK &k = t.k;
     const int W = k.W, H = k.H, step = k.step;
     const int cg = blockIdx.x % t.ncg, tile_x = blockIdx.x / t.ncg;
@@ -644,8 +644,8 @@ __device__ __forceinline__ void st_tile_item(const StageArgs &S, int L, int bx, 
     constexpr int AT_LX = SH::SW - 4, AT_TY = SH::TY, TILE = SH::TILE;
     const AtrousT &t = S.lvl[L];
     const AtrousK &k = t.k;
-    float4 *s_cv = reinterpret_cast<float4 *>(smem), *s_np = s_cv + TILE;
-    float2 *s_zl = reinterpret_cast<float2 *>(s_np + TILE), *s_lv = s_zl + TILE;
+    float4 *s_cv = reinterpret_cast<float4 *>(smem), *s_np = s_cv + SH::TILEP;
+    float2 *s_zl = reinterpret_cast<float2 *>(s_np + SH::TILEP), *s_lv = s_zl + SH::TILEP;
     const int W = k.W, step = k.step;
     const int cg = bx % t.ncg, tile_x = bx / t.ncg;
     const int X0 = cg * AT_C, a0 = tile_x * AT_LX - 2;
@@ -1113,7 +1113,7 @@ template <int LX, int LY, int TY, int MINB> static void at_launch_nonan(dim3 gri
     using SH = AtShape<LX, LY, TY>;
     (void)at_launch_kernel(atrous_tiled_kernel<LX, LY, TY, MINB, false>, grid, dim3(SH::THREADS), SH::SMEM, st, t);
 }
-enum { AT_NSHAPES = 13 };
+enum { AT_NSHAPES = 15 };
 static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
     at_info<16, 32, 4, 3>(),    // 0: 128 threads, 69 KB, 3 blocks/SM
     at_info<32, 16, 4, 3>(),    // 1: 128 threads, 69 KB, 3 blocks/SM
@@ -1128,6 +1128,8 @@ static const AtShapeInfo g_at_shapes[AT_NSHAPES] = {
     at_info<32, 12, 2, 3>(),    // 10: 192 threads, 55 KB, 3 blocks/SM
     at_info<16, 16, 2, 4>(),    // 11: shape 2 at 4 blocks/SM (128 registers: more pairs in flight per warp, fewer warps) -- A/B
     at_info<16, 16, 2, 3>(),    // 12: shape 2 at 3 blocks/SM (168 registers) -- A/B
+    at_info<16, 18, 3, 5>(),    // 13: 2 x 3 patches, 96 threads, 43 KB, 5 blocks/SM (15 warps, 128 registers); 540 and 270 lattice rows divide by 18 -- A/B
+    at_info<16, 16, 1, 5>(),    // 14: 2 x 1 patches, 256 threads, 38 KB, 5 blocks/SM (40 warps, <= 51 registers) -- A/B
 };
 
 // ---- TMA descriptors ------------------------------------------------------------------------------------------------

@@ -44,7 +44,7 @@ template <int LX_, int LY_, int PR_ = 2> struct PairShape {
     static constexpr int LX = LX_, LY = LY_, C = 2, PR = PR_;  // PR: centre rows per phase-2 thread (2 x PR patch)
     static constexpr int SW = LX + 4, SH = LY + 4;              // staged lattice points (tile + 2-point apron)
     static constexpr int GROWS = LY + 2;                        // rows whose forward pairs can reach a centre
-    static constexpr int TILE = SW * SH * C, HALF = SH * (SW / 2) * C;
+    static constexpr int TILE = SW * SH * C, HALF = SH * (SW / 2) * C, HALFP = HALF, TILEP = TILE;      // (no padding needed for these shapes: see OK)
     static constexpr int GN = GROWS * SW * C, GHALF = GROWS * (SW / 2) * C;
     static constexpr int NOFF = 12;
     static constexpr int THREADS = (LX / 2) * (LY / PR) * C;    // phase 2: one 2 x PR patch of centres per thread

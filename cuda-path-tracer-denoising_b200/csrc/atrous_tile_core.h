@@ -28,11 +28,13 @@ template <int LX, int LY, int TY_> struct AtShape {
     static constexpr int THREADS = (LX / AT_TX) * (LY / TY) * AT_C;
     static constexpr int TILE = SW * SH * AT_C;                     // taps
     static constexpr int HALF = SH * (SW / 2) * AT_C;               // taps of one column parity = one TMA box
-    static constexpr int SMEM = TILE * 48 + 16;                     // + mbarrier
-    // TMA destinations (every plane, and the second parity half of every plane) must be 128-byte aligned
-    static constexpr bool OK = HALF * 8 % 128 == 0 && TILE * 8 % 128 == 0 && THREADS % 32 == 0 && LX % 2 == 0 && LY % TY == 0;
+    // TMA destinations (every plane, and the second parity half of every plane) must be 128-byte aligned: the parity halves sit
+    // HALFP entries apart (HALF rounded up to 16 entries = 128 bytes of the 8-byte planes), a plane holds TILEP entries
+    static constexpr int HALFP = (HALF + 15) / 16 * 16, TILEP = 2 * HALFP;
+    static constexpr int SMEM = TILEP * 48 + 16;                    // + mbarrier
+    static constexpr bool OK = THREADS % 32 == 0 && LX % 2 == 0 && LY % TY == 0;
     // [column parity][lattice row][column pair][c]  -- the order a TMA box arrives in
-    PAIR_FN static int idx(int c, int tb, int ta) { return (ta & 1) * HALF + (tb * (SW / 2) + (ta >> 1)) * AT_C + c; }
+    PAIR_FN static int idx(int c, int tb, int ta) { return (ta & 1) * HALFP + (tb * (SW / 2) + (ta >> 1)) * AT_C + c; }
 };
 
 

@@ -13,8 +13,8 @@ static void run_level(const float *cv, const float *gnp, const float *gzl, const
     const int ncg = step / AT_C, lat_w = (W + step - 1) / step, b_first = row_begin / step;
     const int lat_rows = (row_end - 1) / step - b_first + 1;
     const int tiles_x = (lat_w + LX - 1) / LX, tiles_y = (lat_rows + LY - 1) / LY;
-    std::vector<float4> s_cv(SH::TILE), s_np(SH::TILE);
-    std::vector<float2> s_zl(SH::TILE), s_lv(SH::TILE);
+    std::vector<float4> s_cv(SH::TILEP), s_np(SH::TILEP);
+    std::vector<float2> s_zl(SH::TILEP), s_lv(SH::TILEP);
     for (int tile_y = 0; tile_y < tiles_y; tile_y++) for (int yc = 0; yc < step; yc++)
     for (int tile_x = 0; tile_x < tiles_x; tile_x++) for (int cg = 0; cg < ncg; cg++) {
         const int X0 = cg * AT_C, a0 = tile_x * LX - 2, b0 = b_first + tile_y * LY - 2;
@@ -58,7 +58,7 @@ extern "C" int tile_emu_level(const float *cv, const float *gnp, const float *gz
     switch (shape) {
         case 0: RUN(16, 32, 4); case 1: RUN(32, 16, 4); case 2: RUN(16, 16, 2); case 3: RUN(16, 32, 2); case 4: RUN(32, 16, 2);
         case 5: RUN(16, 24, 4); case 6: RUN(32, 12, 4); case 7: RUN(16, 32, 2); case 8: RUN(32, 8, 2); case 9: RUN(16, 12, 2);
-        case 10: RUN(32, 12, 2);
+        case 10: RUN(32, 12, 2); case 11: RUN(16, 16, 2); case 12: RUN(16, 16, 2); case 13: RUN(16, 18, 3); case 14: RUN(16, 16, 1);
     }
     return -1;
 }

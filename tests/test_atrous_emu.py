@@ -105,7 +105,7 @@ def test_emulated_strip_and_nan_normals(emu):
     assert_close(out[19:41, :, 3], ov[19:41], VAR_FLOOR, "strip variance")
 
 
-@pytest.mark.parametrize("shape", range(11))
+@pytest.mark.parametrize("shape", list(range(11)) + [13, 14])
 @pytest.mark.parametrize("case", [(96, 80, 1), (61, 45, 2), (50, 70, 4), (33, 17, 5), (5, 3, 1), (130, 40, 7)])
 def test_emulated_production_kernel_matches_oracle(tile_emu, case, shape):
     W, H, level = case

@@ -30,7 +30,7 @@ def test_level_matches_oracle(level, size):
     R.close()
 
 
-@pytest.mark.parametrize("shape", range(13))
+@pytest.mark.parametrize("shape", range(15))
 def test_every_tile_shape_matches_oracle(shape, monkeypatch):
     """The lattice-tiled kernel is instantiated for several tile shapes / patch heights (csrc/atrous.cu, g_at_shapes);
     launch_atrous picks one per level. Force each of them (SVGF_ATROUS_SHAPE is read at svgf_create) and check it against
