@@ -84,7 +84,7 @@ EXPORTS = ["svgf_params_default", "svgf_create", "svgf_destroy", "svgf_reset", "
            "svgf_set_profiling", "svgf_stream", "svgf_set_shard", "svgf_ipc_handles_size", "svgf_ipc_export",
            "svgf_ipc_connect", "svgf_peer_connect_local", "svgf_peer_error", "svgf_camera_init", "svgf_camera_step",
            "svgf_render_async", "svgf_wait_image", "svgf_register_host", "svgf_unregister_host", "svgf_scene_load", "svgf_scene_free", "svgf_scene_error", "svgf_scene_describe",
-           "svgf_set_option", "svgf_rebuild_bvh", "svgf_scene_camera", "svgf_scene_num_textures", "svgf_scene_texture_file", "svgf_scene_set_texture", "svgf_scene_mesh_boxes"]
+           "svgf_set_option", "svgf_rebuild_bvh", "svgf_refit_bvh", "svgf_scene_camera", "svgf_scene_num_textures", "svgf_scene_texture_file", "svgf_scene_set_texture", "svgf_scene_mesh_boxes"]
 
 _lib = None
 
@@ -109,6 +109,7 @@ def lib():
         L.svgf_render.argtypes = [vp, ctypes.POINTER(Camera), ctypes.POINTER(Params), ci, vp, vp]
         L.svgf_set_option.argtypes = [vp, cp, ci]
         L.svgf_rebuild_bvh.argtypes = [vp]
+        L.svgf_refit_bvh.argtypes = [vp, vp, ci]
         L.svgf_scene_load.argtypes = [ctypes.POINTER(vp), cp, cp]
         L.svgf_scene_free.argtypes = [vp]; L.svgf_scene_free.restype = None
         L.svgf_scene_error.argtypes = [vp]; L.svgf_scene_error.restype = ctypes.c_char_p
@@ -264,6 +265,11 @@ class Renderer:
     def rebuild_bvh(self):
         """Linear BVH built on the device over the context's triangles, swapped in for the uploaded tree (svgf_rebuild_bvh)."""
         self._ck(lib().svgf_rebuild_bvh(self.h), "svgf_rebuild_bvh")
+
+    def refit_bvh(self, triangles):
+        """New vertex data (n x 136-byte svgf_triangle records, create order) into the tree in place (svgf_refit_bvh)."""
+        t = np.ascontiguousarray(triangles).view(np.uint8).reshape(-1)
+        self._ck(lib().svgf_refit_bvh(self.h, t.ctypes.data, t.size // 136), "svgf_refit_bvh")
 
     def fetch_raw(self, name, count, dtype):
         a = np.empty(count, dtype)

@@ -334,6 +334,7 @@ int svgf_destroy(svgf_ctx *c) {
     }
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->legacy_fence) cudaEventDestroy(c->legacy_fence);
+    cudaFree(c->slot_of_input); cudaFree(c->bvh_parent); cudaFree(c->refit_stage);
     cudaFree(c->stage_ctr);
     for (auto &pf : c->prof_pool) for (int i = 0; i < 12; i++) cudaEventDestroy(pf.ev[i]);
     for (auto &r : c->registered_hosts) cudaHostUnregister(r.first);

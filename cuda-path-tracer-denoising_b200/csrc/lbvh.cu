@@ -62,6 +62,75 @@ __global__ void lbvh_reorder_kernel(const unsigned long long *keys, int n, const
     for (int q = 0; q < 3; q++) new_hot[3 * k + q] = hot[3 * slot + q];
     for (int q = 0; q < 4; q++) new_cold[4 * k + q] = cold[4 * slot + q];
 }
+// ---- refit (svgf_refit_bvh): new vertex data into the records, then the boxes of the SAME tree bottom-up ----
+__global__ void refit_tris_kernel(const svgf_triangle *tris, int n, const int *slot_of_input, float4 *hot, float4 *cold) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const svgf_triangle &t = tris[i];
+    const int k = slot_of_input[i];
+    const float *v0 = t.verts[0].pos, *v1 = t.verts[1].pos, *v2 = t.verts[2].pos;
+    // the packing of upload_scene (api.cu): hot {v0,id} {e1} {e2}, cold {n0,u0} {n1,v0} {n2,u1} {v1,u2,v2}; e = v - v0 in fp32
+    hot[3 * k] = make_float4(v0[0], v0[1], v0[2], __int_as_float(t.id));
+    hot[3 * k + 1] = make_float4(__fsub_rn(v1[0], v0[0]), __fsub_rn(v1[1], v0[1]), __fsub_rn(v1[2], v0[2]), 0.f);
+    hot[3 * k + 2] = make_float4(__fsub_rn(v2[0], v0[0]), __fsub_rn(v2[1], v0[1]), __fsub_rn(v2[2], v0[2]), 0.f);
+    const float *n0 = t.verts[0].normal, *n1 = t.verts[1].normal, *n2 = t.verts[2].normal;
+    cold[4 * k] = make_float4(n0[0], n0[1], n0[2], t.verts[0].uv[0]);
+    cold[4 * k + 1] = make_float4(n1[0], n1[1], n1[2], t.verts[0].uv[1]);
+    cold[4 * k + 2] = make_float4(n2[0], n2[1], n2[2], t.verts[1].uv[0]);
+    cold[4 * k + 3] = make_float4(t.verts[1].uv[1], t.verts[2].uv[0], t.verts[2].uv[1], 0.f);
+}
+// parent of every node of the pre-order array (left child = index + 1, right child = offset)
+__global__ void refit_parents_kernel(const float4 *nodes, int nn, int *parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    if (i == 0) parent[0] = -1;
+    const int meta = __float_as_int(nodes[2 * i].w), off = __float_as_int(nodes[2 * i + 1].w);
+    if ((meta & 0xffff) == 0) { parent[i + 1] = i; parent[off] = i; }
+}
+// One thread per LEAF: the union of its triangles' boxes (lbvh_tri_bounds: the points the intersection test itself uses, one ulp
+// of margin), then up the tree; the second child to arrive at a node forms the union of both children and goes on (min and max
+// are exact, so the result does not depend on who arrives first).
+__global__ void refit_boxes_kernel(float4 *nodes, int nn, const float4 *hot, const int *parent, int *flags) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nn) return;
+    const int meta = __float_as_int(nodes[2 * v].w), count = meta & 0xffff;
+    if (count == 0) return;
+    const int first = __float_as_int(nodes[2 * v + 1].w);
+    float b[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+    for (int q = 0; q < count; q++) {
+        float t6[6];
+        lbvh_tri_bounds(reinterpret_cast<const LbvhF4 *>(hot), first + q, t6);
+        for (int a = 0; a < 3; a++) { b[a] = lbvh_min(b[a], t6[a]); b[3 + a] = lbvh_max(b[3 + a], t6[3 + a]); }
+    }
+    volatile float4 *vn = nodes;
+    vn[2 * v].x = b[0]; vn[2 * v].y = b[1]; vn[2 * v].z = b[2];
+    vn[2 * v + 1].x = b[3]; vn[2 * v + 1].y = b[4]; vn[2 * v + 1].z = b[5];
+    while (true) {
+        const int p = parent[v];
+        if (p < 0) return;
+        __threadfence();                                    // this subtree's boxes first ...
+        if (atomicAdd(flags + p, 1) == 0) return;           // ... the sibling will come by and take them along
+        __threadfence();
+        const int lc = p + 1, rc = __float_as_int(vn[2 * p + 1].w);
+        vn[2 * p].x = lbvh_min(vn[2 * lc].x, vn[2 * rc].x); vn[2 * p].y = lbvh_min(vn[2 * lc].y, vn[2 * rc].y); vn[2 * p].z = lbvh_min(vn[2 * lc].z, vn[2 * rc].z);
+        vn[2 * p + 1].x = lbvh_max(vn[2 * lc + 1].x, vn[2 * rc + 1].x); vn[2 * p + 1].y = lbvh_max(vn[2 * lc + 1].y, vn[2 * rc + 1].y);
+        vn[2 * p + 1].z = lbvh_max(vn[2 * lc + 1].z, vn[2 * rc + 1].z);
+        v = p;
+    }
+}
+// after a rebuild: input triangle i now lives where its old slot went (new slot k holds old slot `low 32 bits of keys[k]`)
+__global__ void refit_remap_inv_kernel(const unsigned long long *keys, int n, int *new_slot_of_old) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) new_slot_of_old[(int)(unsigned)keys[k]] = k;
+}
+__global__ void refit_remap_kernel(int n, const int *new_slot_of_old, int *slot_of_input) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot_of_input[i] = new_slot_of_old[slot_of_input[i]];
+}
+__global__ void refit_iota_kernel(int n, int *a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
 }  // namespace
 
 #define LB(call)                                                                    \
@@ -106,6 +175,11 @@ extern "C" int svgf_rebuild_bvh(svgf_ctx *c) {
         lbvh_climb_kernel<<<gb, T, 0, st>>>(keys_sorted, n, tri_b6, left, right, parent, node_b6, size, flags);
         lbvh_emit_kernel<<<(nn + T - 1) / T, T, 0, st>>>(n, left, right, parent, size, axis, node_b6, reinterpret_cast<LbvhF4 *>(nodes));
         lbvh_reorder_kernel<<<gb, T, 0, st>>>(keys_sorted, n, c->scene.tri_hot, c->scene.tri_cold, new_hot, new_cold);
+        if (c->slot_of_input) {         // svgf_refit_bvh has been used: follow the triangles to their new slots (ints[0..n) is free again)
+            refit_remap_inv_kernel<<<gb, T, 0, st>>>(keys_sorted, n, ints);
+            refit_remap_kernel<<<gb, T, 0, st>>>(n, ints, c->slot_of_input);
+        }
+        cudaFree(c->bvh_parent); c->bvh_parent = nullptr;       // another tree: parents are recomputed on the next refit
         LB(cudaGetLastError());
         LB(cudaStreamSynchronize(st));
     }
@@ -116,5 +190,37 @@ extern "C" int svgf_rebuild_bvh(svgf_ctx *c) {
 done:
     cudaFree(tri_b6); cudaFree(scene6); cudaFree(node_b6); cudaFree(keys); cudaFree(keys_sorted); cudaFree(ints); cudaFree(tmp);
     cudaFree(nodes); cudaFree(new_hot); cudaFree(new_cold);
+    return rc;
+}
+
+// SURVEY.md 8(f) N3, second half: geometry that MOVES keeps its tree. New vertex data for all triangles (in the order they were
+// given to svgf_create) goes into the records, and the boxes of the tree in place -- the uploaded SAH tree or the one
+// svgf_rebuild_bvh built -- are recomputed bottom-up; topology, leaf contents and therefore the traversal order stay. A tree whose
+// triangles moved far apart traverses slowly (overlapping boxes) but stays correct: rebuild when that matters. Stream-ordered
+// with the frames; does not synchronise.
+extern "C" int svgf_refit_bvh(svgf_ctx *c, const svgf_triangle *triangles, int n_triangles) {
+    if (!c || !triangles) return SVGF_ERR_INVALID;
+    const int n = c->scene.n_tris, nn = c->scene.n_nodes;
+    if (n_triangles != n) { c->err = "svgf_refit_bvh: the triangle count differs from the scene's"; return SVGF_ERR_INVALID; }
+    if (n <= 0 || nn <= 0) return SVGF_OK;
+    int rc = SVGF_OK;
+    cudaStream_t st = c->stream;
+    const int T = 256;
+    LB(cudaSetDevice(c->device));
+    if (!c->slot_of_input) {
+        LB(cudaMalloc((void **)&c->slot_of_input, sizeof(int) * n));
+        refit_iota_kernel<<<(n + T - 1) / T, T, 0, st>>>(n, c->slot_of_input);      // svgf_create keeps the caller's order
+    }
+    if (!c->refit_stage) LB(cudaMalloc((void **)&c->refit_stage, sizeof(svgf_triangle) * (size_t)n));
+    if (!c->bvh_parent) {
+        LB(cudaMalloc((void **)&c->bvh_parent, sizeof(int) * 2 * (size_t)nn));      // parents, then arrival flags
+        refit_parents_kernel<<<(nn + T - 1) / T, T, 0, st>>>(c->scene.bvh, nn, c->bvh_parent);
+    }
+    LB(cudaMemcpyAsync(c->refit_stage, triangles, sizeof(svgf_triangle) * (size_t)n, cudaMemcpyHostToDevice, st));
+    refit_tris_kernel<<<(n + T - 1) / T, T, 0, st>>>(static_cast<const svgf_triangle *>(c->refit_stage), n, c->slot_of_input, c->scene.tri_hot, c->scene.tri_cold);
+    LB(cudaMemsetAsync(c->bvh_parent + nn, 0, sizeof(int) * (size_t)nn, st));
+    refit_boxes_kernel<<<(nn + T - 1) / T, T, 0, st>>>(c->scene.bvh, nn, c->scene.tri_hot, c->bvh_parent, c->bvh_parent + nn);
+    LB(cudaGetLastError());
+done:
     return rc;
 }

@@ -188,6 +188,7 @@ struct svgf_ctx {
     float *image_set[2] = {nullptr, nullptr}; float4 *gnp_set[2] = {nullptr, nullptr}, *alb_set[2] = {nullptr, nullptr}; float2 *gzl_set[2] = {nullptr, nullptr};
     cudaStream_t rt_stream = nullptr, rt_launch_stream = nullptr;      // rt_launch_stream: where launch_pathtrace puts its kernels (null: c->stream)
     cudaEvent_t ev_rt_done = nullptr, ev_temporal_done = nullptr; bool temporal_done_valid = false;
+    int *slot_of_input = nullptr, *bvh_parent = nullptr; void *refit_stage = nullptr;      // svgf_refit_bvh (lbvh.cu): where input triangle i lives, parents + flags of the tree in place, upload staging
     int halo_copy_from_rows = 32;           // sharded frames: levels whose next-level halo is at least this many rows push it with the copy kernel
     int opt_cuda_graph = 0;                 // 1: the frame's launches run as one CUDA graph, updated in place every frame (N1)
     cudaGraphExec_t graph_exec = nullptr; int frames_rendered = 0;

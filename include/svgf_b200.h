@@ -242,6 +242,11 @@ int svgf_set_option(svgf_ctx *ctx, const char *name, int value);
  * traversal is unchanged and frames match the host-built tree up to ties between equal hit distances. For geometry that
  * changes on the device; synchronises the context's stream. svgf_fetch names: "bvh_packed", "triangle_ids". */
 int svgf_rebuild_bvh(svgf_ctx *ctx);
+/* Geometry that moves keeps its tree: new vertex data for ALL triangles, in the order they were given to svgf_create, is written
+ * into the device records and the boxes of the tree in place (the uploaded one, or the one svgf_rebuild_bvh built) are recomputed
+ * bottom-up; topology and leaf contents stay, so the traversal order does too. Stream-ordered with the frames, no
+ * synchronisation. The reference has no counterpart (it rebuilds on the host and re-uploads through pathtraceInit). */
+int svgf_refit_bvh(svgf_ctx *ctx, const svgf_triangle *triangles, int n_triangles);
 
 /* ---- multi-GPU: a frame sharded by row strips, one process (context) per GPU -------------------------------- */
 /* Every rank holds full-frame planes and renders rows [row_starts[rank], row_starts[rank+1]); rows owned by other
