@@ -175,6 +175,95 @@ struct TriBest { float t, bx, by; int slot; };
 // `t_any` > 0: occlusion query -- return at the first triangle hit strictly in front of t_any (0 < t < t_any); which one is
 // irrelevant to the caller. (The closest-hit search would reject the mesh if its CLOSEST triangle sat at exactly t == 0; that
 // this differs needs a triangle hit at exactly 0 and another one before t_any on the same ray.)
+// Slab test of one node record against the ray, with the caller's cull distance (boundingbox.h:62-79 has no t-culling).
+__device__ __forceinline__ bool bvh_box_hit(const float4 &a, const float4 &b, const Ray &ray, const F3 invdir, float t_cull) {
+    const float txMin = (a.x - ray.origin.x) * invdir.x, txMax = (b.x - ray.origin.x) * invdir.x;
+    const float tyMin = (a.y - ray.origin.y) * invdir.y, tyMax = (b.y - ray.origin.y) * invdir.y;
+    const float tzMin = (a.z - ray.origin.z) * invdir.z, tzMax = (b.z - ray.origin.z) * invdir.z;
+    const float tmin = gmax(gmax(gmin(txMin, txMax), gmin(tyMin, tyMax)), gmin(tzMin, tzMax));
+    const float tmax = gmin(gmin(gmax(txMin, txMax), gmax(tyMin, tyMax)), gmax(tzMin, tzMax));
+    return !(tmax < 0) && !(tmin > tmax) && !(tmin > t_cull * 1.0001f + 1e-4f);
+}
+
+#ifndef SVGF_RT_BVH_PAIRED
+#define SVGF_RT_BVH_PAIRED 0
+#endif
+#if SVGF_RT_BVH_PAIRED
+// A/B variant (tools/build_rt_ab.sh, -DSVGF_RT_BVH_PAIRED=1), MEASURED SLOWER on B200 and therefore not the default: C3 room 3.11 vs
+// 2.80 ms, C5 bunny 1.52 vs 1.43, C2 0.87 vs 0.77 (profiles/r2_ab_rt_bvh_paired.txt) -- the two extra node records in flight cost
+// more in the 64-register kernel than the saved round trips return. BOTH children of an interior node are fetched and tested
+// together (four independent loads, one round trip to memory per level of the tree), the near one is entered with its record
+// already in registers and the far one is stacked only if the ray hits its box. The default loop (below) enters the near child,
+// stacks the far one untested and pays a dependent fetch for every node it pops, missed ones included. The set of nodes and triangles visited and their order are
+// exactly the same -- a far child rejected here would have been rejected when popped (the cull distance only shrinks), one that
+// passes is tested again when popped, with the cull distance of that moment, as before -- so the results are bit-identical.
+// (The reference's 64-entry stack drops subtrees when it overflows; with fewer entries stacked that could only differ for a tree
+// more than 64 levels deep.)
+__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, float t_bound, TriBest &best, float t_any = 0.f) {
+    if (sc.n_nodes == 0) return false;
+    bool hit = false;
+    const int neg[3] = {ray.direction.x < 0.f, ray.direction.y < 0.f, ray.direction.z < 0.f};
+    int top = 0, cur = 0;
+    int stack[64];
+    best.t = FLT_MAX; best.slot = -1; best.bx = best.by = 0.f;
+    float4 a = __ldg(&sc.bvh[0]), b = __ldg(&sc.bvh[1]);
+    bool pop = !bvh_box_hit(a, b, ray, invdir, fminf(best.t, t_bound));      // the root is tested like any node
+    while (true) {
+        if (pop) {      // next stacked node; it is tested (again) with the cull distance of NOW
+            if (top == 0) break;
+            cur = stack[--top];
+            a = __ldg(&sc.bvh[2 * cur]); b = __ldg(&sc.bvh[2 * cur + 1]);
+            pop = !bvh_box_hit(a, b, ray, invdir, fminf(best.t, t_bound));
+            continue;
+        }
+        // node `cur` with record (a, b) has passed its box test
+        const int meta = __float_as_int(a.w), off = __float_as_int(b.w);
+        const int count = meta & 0xffff;
+        if (count > 0) {
+            for (int i = 0; i < count; i++) {
+                const int slot = off + i;
+                const float4 h0 = __ldg(&sc.tri_hot[3 * slot]), h1 = __ldg(&sc.tri_hot[3 * slot + 1]), h2 = __ldg(&sc.tri_hot[3 * slot + 2]);
+                const F3 v0 = mk(h0.x, h0.y, h0.z), e1 = mk(h1.x, h1.y, h1.z), e2 = mk(h2.x, h2.y, h2.z);
+                const F3 p = cross(ray.direction, e2);
+                const float det = dot(e1, p);
+                if (det < FLT_EPSILON) continue;
+                const float f = 1.0f / det;
+                const F3 s = ray.origin - v0;
+                const float bx = f * dot(s, p);
+                if (bx < 0.0f) continue;
+                if (bx > 1.0f) continue;
+                const F3 q = cross(s, e1);
+                const float by = f * dot(ray.direction, q);
+                if (by < 0.0f) continue;
+                if (by + bx > 1.0f) continue;
+                const float bz = f * dot(e2, q);
+                if (!(bz >= 0.0f)) continue;
+                hit = true;
+                if (bz < best.t) { best.t = bz; best.bx = bx; best.by = by; best.slot = slot; }
+                if (bz > 0.0f && bz < t_any) { top = 0; t_bound = -FLT_MAX; }      // (light query, compiled out by default: ends the search through data)
+            }
+            pop = true;
+        } else if (top == 64) {
+            pop = true;                 // the reference drops both children of a node it meets with a full stack
+        } else {
+            const int L = cur + 1, R = off;
+            const float4 aL = __ldg(&sc.bvh[2 * L]), bL = __ldg(&sc.bvh[2 * L + 1]), aR = __ldg(&sc.bvh[2 * R]), bR = __ldg(&sc.bvh[2 * R + 1]);
+            const float t_cull = fminf(best.t, t_bound);
+            const bool hL = bvh_box_hit(aL, bL, ray, invdir, t_cull), hR = bvh_box_hit(aR, bR, ray, invdir, t_cull);
+            const bool r_first = neg[meta >> 16] != 0;                     // near child: the right one for a ray running against the split axis
+            const bool h_first = r_first ? hR : hL, h_second = r_first ? hL : hR;
+            const int first = r_first ? R : L, second = r_first ? L : R;
+            if (h_first & h_second) stack[top++] = second;
+            const bool go_first = h_first;
+            cur = go_first ? first : second;
+            const bool take_r = go_first == r_first;                       // the record that goes with `cur`
+            a = take_r ? aR : aL; b = take_r ? bR : bL;
+            pop = !(h_first | h_second);
+        }
+    }
+    return hit;
+}
+#else
 __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, float t_bound, TriBest &best, float t_any = 0.f) {
     if (sc.n_nodes == 0) return false;
     bool hit = false;
@@ -184,14 +273,7 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
     best.t = FLT_MAX; best.slot = -1; best.bx = best.by = 0.f;
     while (true) {
         const float4 a = __ldg(&sc.bvh[2 * cur]), b = __ldg(&sc.bvh[2 * cur + 1]);
-        // boundingbox.h:62-79 (no t-culling in the reference)
-        float txMin = (a.x - ray.origin.x) * invdir.x, txMax = (b.x - ray.origin.x) * invdir.x;
-        float tyMin = (a.y - ray.origin.y) * invdir.y, tyMax = (b.y - ray.origin.y) * invdir.y;
-        float tzMin = (a.z - ray.origin.z) * invdir.z, tzMax = (b.z - ray.origin.z) * invdir.z;
-        float tmin = gmax(gmax(gmin(txMin, txMax), gmin(tyMin, tyMax)), gmin(tzMin, tzMax));
-        float tmax = gmin(gmin(gmax(txMin, txMax), gmax(tyMin, tyMax)), gmax(tzMin, tzMax));
-        const float t_cull = fminf(best.t, t_bound);
-        const bool box_hit = !(tmax < 0) && !(tmin > tmax) && !(tmin > t_cull * 1.0001f + 1e-4f);
+        const bool box_hit = bvh_box_hit(a, b, ray, invdir, fminf(best.t, t_bound));
         if (box_hit) {
             const int meta = __float_as_int(a.w), off = __float_as_int(b.w);
             const int count = meta & 0xffff;
@@ -216,8 +298,6 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
                     if (!(bz >= 0.0f)) continue;
                     hit = true;
                     if (bz < best.t) { best.t = bz; best.bx = bx; best.by = by; best.slot = slot; }
-                    // occluder found: nothing else matters. Ends the search through DATA (everything still stacked is dropped,
-                    // every later box is culled) -- a `return` here changed where the warp reconverges and doubled the kernel time
                     if (bz > 0.0f && bz < t_any) { top = 0; t_bound = -FLT_MAX; }
                 }
                 if (top == 0) break;
@@ -235,6 +315,7 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
     }
     return hit;
 }
+#endif
 
 struct Isect {      // the live part of ShadeableIntersection (sceneStructs.h:104-111)
     float t; F3 n; int materialId, geomId; float u, v;
