@@ -84,7 +84,7 @@ EXPORTS = ["svgf_params_default", "svgf_create", "svgf_destroy", "svgf_reset", "
            "svgf_set_profiling", "svgf_stream", "svgf_set_shard", "svgf_ipc_handles_size", "svgf_ipc_export",
            "svgf_ipc_connect", "svgf_peer_connect_local", "svgf_peer_error", "svgf_camera_init", "svgf_camera_step",
            "svgf_render_async", "svgf_wait_image", "svgf_register_host", "svgf_unregister_host", "svgf_scene_load", "svgf_scene_free", "svgf_scene_error", "svgf_scene_describe",
-           "svgf_set_option", "svgf_rebuild_bvh", "svgf_refit_bvh", "svgf_scene_camera", "svgf_scene_num_textures", "svgf_scene_texture_file", "svgf_scene_set_texture", "svgf_scene_mesh_boxes"]
+           "svgf_set_option", "svgf_rebuild_bvh", "svgf_refit_bvh", "svgf_scene_camera", "svgf_scene_num_textures", "svgf_scene_texture_file", "svgf_scene_set_texture", "svgf_scene_mesh_boxes", "svgf_scene_load_textures", "svgf_jpeg_decode_memory"]
 
 _lib = None
 
@@ -391,6 +391,15 @@ class SceneFile:
         self.eye, self.lookat, self.up, self.fovy, self.res = eye, look, up, float(fovy.value), (int(res[0]), int(res[1]))
         self.texture_files = [lib().svgf_scene_texture_file(h, i).decode() for i in range(lib().svgf_scene_num_textures(h))]
 
+    def load_textures(self, textures_dir):
+        """Decodes every texture still without pixels from <textures_dir>/<file> (svgf_scene_load_textures: the library's own JPEG
+        decoder, byte-identical to the reference's stb_image). Returns how many textures have pixels now."""
+        lib().svgf_scene_load_textures.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        n = lib().svgf_scene_load_textures(self.h, textures_dir.encode())
+        if n < 0:
+            raise SvgfError("svgf_scene_load_textures failed")
+        return n
+
     def set_texture(self, index, pixels):
         """pixels: (H, W, C) uint8, row-major (what stb_image hands the reference, src/sceneStructs.h:193-199)."""
         a = np.ascontiguousarray(pixels, np.uint8)
@@ -434,6 +443,21 @@ def scene_path(name):
     if os.path.exists(name):
         return name
     return os.path.join(os.path.dirname(_HERE), "tests", "golden", "scenes", name + ".scene")
+
+
+def jpeg_decode(data):
+    """svgf_jpeg_decode_memory: bytes of a JPEG file -> (H, W, C) uint8, the pixels stb_image's stbi_load(..., 0) returns."""
+    L = lib()
+    L.svgf_jpeg_decode_memory.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                          ctypes.POINTER(ctypes.c_int), ctypes.c_void_p, ctypes.c_size_t]
+    b = np.frombuffer(bytes(data), np.uint8).copy()
+    w, h, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    if L.svgf_jpeg_decode_memory(b.ctypes.data, b.size, ctypes.byref(w), ctypes.byref(h), ctypes.byref(c), None, 0) != 0:
+        raise SvgfError("svgf_jpeg_decode_memory: not a JPEG this decoder reads")
+    out = np.zeros((h.value, w.value, c.value), np.uint8)
+    if L.svgf_jpeg_decode_memory(b.ctypes.data, b.size, ctypes.byref(w), ctypes.byref(h), ctypes.byref(c), out.ctypes.data, out.size) != 0:
+        raise SvgfError("svgf_jpeg_decode_memory failed")
+    return out
 
 
 def open_scene(name, W, H, device=0):

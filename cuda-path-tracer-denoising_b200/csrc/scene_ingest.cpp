@@ -13,8 +13,8 @@
 //   * the BVH builder's quirks: an all-zero box is "empty" for unions, 9 SAH buckets, <= 10 triangles per leaf,
 //     std::partition / std::nth_element for the splits, right subtree built before the left one (the order g++ evaluates
 //     the two recursive calls in MakeNode's argument list, bvhtree.cpp:87,133), pre-order flattening.
-// JPEG decoding is not part of this library: textures are reported by file name and attached as decoded RGB8 pixels
-// (svgf_scene_set_texture).
+// Textures are reported by file name; their pixels are either attached by the caller (svgf_scene_set_texture) or decoded here
+// from the JPEG files (svgf_scene_load_textures -> csrc/jpeg_decode.cpp).
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -27,6 +27,9 @@
 #include <vector>
 
 #include "../../include/svgf_b200.h"
+
+// csrc/jpeg_decode.cpp
+bool svgf_jpeg_decode(const unsigned char *bytes, size_t n, int *width, int *height, int *components, std::vector<unsigned char> &pixels, std::string &err);
 
 void svgf_mat4_inverse(const float *m, float *out16);      // camera.cpp (glm compute_inverse)
 
@@ -566,6 +569,38 @@ int svgf_scene_set_texture(svgf_scene *sc, int i, int width, int height, int com
     svgf_scene::Tex &t = sc->textures[i];
     t.w = width; t.h = height; t.comp = components;
     t.px.assign(pixels, pixels + (size_t)width * height * components);
+    return SVGF_OK;
+}
+// Decodes every texture that has no pixels yet from `<textures_dir>/<file name>` (JPEG: csrc/jpeg_decode.cpp, the bytes the
+// reference's stb_image produces). Returns the number of textures that now have pixels, or a negative status.
+int svgf_scene_load_textures(svgf_scene *sc, const char *textures_dir) {
+    if (!sc || !textures_dir) return SVGF_ERR_INVALID;
+    int have = 0;
+    for (size_t i = 0; i < sc->textures.size(); i++) {
+        svgf_scene::Tex &t = sc->textures[i];
+        if (!t.px.empty()) { have++; continue; }
+        const std::string path = std::string(textures_dir) + "/" + sc->texture_files[i];
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) { sc->err = "cannot open texture '" + path + "'"; continue; }
+        std::vector<unsigned char> bytes;
+        unsigned char buf[65536];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof(buf), f)) > 0) bytes.insert(bytes.end(), buf, buf + n);
+        fclose(f);
+        std::string why;
+        if (!svgf_jpeg_decode(bytes.data(), bytes.size(), &t.w, &t.h, &t.comp, t.px, why)) { t.px.clear(); sc->err = "texture '" + path + "': " + why; continue; }
+        have++;
+    }
+    return have;
+}
+int svgf_jpeg_decode_memory(const unsigned char *bytes, size_t n, int *width, int *height, int *components, unsigned char *out, size_t out_bytes) {
+    if (!bytes || !width || !height || !components) return SVGF_ERR_INVALID;
+    std::vector<unsigned char> px; std::string why;
+    if (!svgf_jpeg_decode(bytes, n, width, height, components, px, why)) return SVGF_ERR_INVALID;
+    if (out) {
+        if (out_bytes < px.size()) return SVGF_ERR_INVALID;
+        memcpy(out, px.data(), px.size());
+    }
     return SVGF_OK;
 }
 int svgf_scene_mesh_boxes(const svgf_scene *sc, float *out6, int max_boxes) {

@@ -293,8 +293,14 @@ const char *svgf_scene_error(const svgf_scene *scene);
 int svgf_scene_describe(svgf_scene *scene, int width, int height, svgf_scene_desc *desc);
 /* The CAMERA block: EYE / LOOKAT / UP / FOVY / RES, the inputs of svgf_camera_init. Any pointer may be NULL. */
 int svgf_scene_camera(const svgf_scene *scene, float eye[3], float lookat[3], float up[3], float *fovy, int res[2]);
-/* Textures are referenced by file name (TEXTURE lines, scene.cpp:213-219); decoding is the caller's (the reference uses
- * stb_image): attach RGB8 pixels, row-major, before svgf_scene_describe. */
+/* Textures are referenced by file name (TEXTURE lines, scene.cpp:213-219; the reference decodes "../scenes/Textures/<name>" with
+ * stb_image, sceneStructs.h:198-199). Either attach decoded pixels (RGB8, row-major) with svgf_scene_set_texture, or let
+ * svgf_scene_load_textures decode every texture still without pixels from `<textures_dir>/<name>`: a JPEG decoder (baseline and
+ * progressive, csrc/jpeg_decode.cpp) whose output is byte-identical to stb_image's for the reference's files. It returns how many
+ * textures have pixels afterwards (svgf_scene_error says why one is missing). svgf_jpeg_decode_memory is the decoder on its
+ * own: `out` may be NULL to ask for the size (width * height * components bytes). */
+int svgf_scene_load_textures(svgf_scene *scene, const char *textures_dir);
+int svgf_jpeg_decode_memory(const unsigned char *bytes, size_t n, int *width, int *height, int *components, unsigned char *out, size_t out_bytes);
 int svgf_scene_num_textures(const svgf_scene *scene);
 const char *svgf_scene_texture_file(const svgf_scene *scene, int index);
 int svgf_scene_set_texture(svgf_scene *scene, int index, int width, int height, int components, const unsigned char *pixels);

@@ -102,3 +102,33 @@ def test_errors_are_reported():
         m.SceneFile("/nonexistent/scene.txt")
     with pytest.raises(m.SvgfError, match="cannot open OBJ"):
         m.SceneFile(os.path.join(OWN_SCENES, "missing_mesh.txt"))
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["cornell", "room"])
+def test_textures_decoded_natively_equal_the_reference_loaders_bytes(name):
+    """The reference decodes its JPEG textures with stb_image (src/sceneStructs.h:198-199); svgf_scene_load_textures uses the
+    library's own decoder (csrc/jpeg_decode.cpp: baseline and progressive Huffman, stb_image's fixed-point IDCT, chroma
+    up-sampling and YCbCr conversion). The texels enter the image through Texture::getColor, so the bar is byte for byte:
+    wallpaper.jpg is progressive 4:4:4 with an Adobe marker, chair.jpg baseline 4:2:0. With it the whole ingest -- text scene,
+    OBJ meshes, BVH, textures -- is native: the description below is built without any pixels from outside."""
+    m = svgf()
+    blob = m.SceneBlob(m.scene_path(name))
+    sc = m.SceneFile(os.path.join(REF_SCENES, name + ".txt"))
+    assert sc.load_textures(os.path.join(REF_SCENES, "Textures")) == len(blob.textures)
+    d = sc.desc(64, 48)
+    assert d.n_textures == len(blob.textures)
+    for i, (w, h, c, px) in enumerate(blob.textures):
+        got = m.jpeg_decode(open(os.path.join(REF_SCENES, "Textures", sc.texture_files[i]), "rb").read())
+        assert got.shape == (h, w, c)
+        assert np.array_equal(got.reshape(-1), px), "%s: %d texels differ from stb_image's" % (sc.texture_files[i], int((got.reshape(-1) != px).sum()))
+
+
+def test_jpeg_decoder_rejects_what_it_does_not_read():
+    m = svgf()
+    for junk in (b"", b"not a jpeg", b"\xff\xd8\xff\xd9", b"\xff\xd8" + b"\xff\xc0\x00\x0b\x10\x00\x01\x00\x01\x01\x01\x11\x00"):      # empty, text, no frame, 16-bit samples
+        with pytest.raises(m.SvgfError):
+            m.jpeg_decode(junk)
+    sc = m.SceneFile(os.path.join(OWN_SCENES, "textured.txt")) if os.path.exists(os.path.join(OWN_SCENES, "textured.txt")) else None
+    if sc is not None and sc.texture_files:
+        assert sc.load_textures("/nonexistent") == 0        # a missing file is reported, not fatal

@@ -11,6 +11,6 @@ for tag in ${RT_AB_TAGS:-lq:-DSVGF_RT_LIGHT_QUERY lightfirst:-DSVGF_RT_LIGHT_FIR
 done
 wait
 for tag in ${RT_AB_TAGS:-lq:-DSVGF_RT_LIGHT_QUERY lightfirst:-DSVGF_RT_LIGHT_FIRST}; do name=${tag%%:*}
-  nvcc -ccbin /usr/bin/g++ -shared -gencode arch=compute_100a,code=sm_100a -o ../ab/libsvgf_$name.so build/api.o build/denoise.o build/atrous.o build/lbvh.o build/camera.o build/scene_ingest.o build_ab/pathtrace_$name.o -Xlinker --no-undefined -lcudart
+  nvcc -ccbin /usr/bin/g++ -shared -gencode arch=compute_100a,code=sm_100a -o ../ab/libsvgf_$name.so build/api.o build/denoise.o build/atrous.o build/lbvh.o build/camera.o build/scene_ingest.o build/jpeg_decode.o build_ab/pathtrace_$name.o -Xlinker --no-undefined -lcudart
 done
 ls -la ../ab
