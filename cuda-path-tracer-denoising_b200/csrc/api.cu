@@ -172,6 +172,9 @@ static int upload_scene(svgf_ctx *c, const svgf_scene_desc *d) {
     std::vector<TexD> td(d->n_textures);
     for (int i = 0; i < d->n_textures; i++) {
         const svgf_texture_desc &t = d->textures[i];
+        if (t.width <= 0 || t.height <= 0 || t.components <= 0 || !t.pixels) {
+            c->err = "texture without pixels"; return SVGF_ERR_INVALID;
+        }
         const size_t n = (size_t)t.width * t.height * t.components;
         unsigned char *dp = nullptr;
         CK(cudaMalloc((void **)&dp, n ? n : 1));
@@ -255,10 +258,14 @@ void svgf_params_default(svgf_params *p) {
 const char *svgf_last_error(const svgf_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
-    if (!out || !scene || scene->width <= 0 || scene->height <= 0 || scene->n_geoms <= 0 || scene->n_materials <= 0) {
+    if (!out || !scene || scene->width <= 0 || scene->height <= 0 || scene->n_geoms <= 0 || scene->n_materials <= 0 ||
+        !scene->geoms || !scene->materials || scene->n_triangles < 0 || scene->n_bvh_nodes < 0 || scene->n_textures < 0 ||
+        (scene->n_triangles > 0 && !scene->triangles) || (scene->n_bvh_nodes > 0 && !scene->bvh_nodes) ||
+        (scene->n_textures > 0 && !scene->textures)) {
         g_create_err = "svgf_create: invalid scene description";
         return SVGF_ERR_INVALID;
     }
+    if (out) *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
         g_create_err = "svgf_create: no usable CUDA device (this library has no CPU path)";

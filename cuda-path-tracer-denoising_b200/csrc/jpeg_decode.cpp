@@ -72,7 +72,7 @@ struct Dec {
             if (b == 0xff) {
                 int c = get8();
                 while (c == 0xff) c = get8();
-                if (c != 0) { marker = c; nomore = true; return; }
+                if (c != 0) { marker = c; nomore = true; b = 0; }       // past a marker the stream reads as zero bits
             }
             code_buffer |= b << (24 - code_bits);
             code_bits += 8;
@@ -112,9 +112,9 @@ struct Dec {
         if (t < 0 || t > 15) return fail("bad DC code");
         memset(data, 0, 64 * sizeof(short));
         const int diff = t ? extend_receive(t) : 0;
-        const int d = comp[c].dc_pred + diff;
+        const int d = (int)((uint32_t)comp[c].dc_pred + (uint32_t)diff);       // wraps on a damaged file, never overflows
         comp[c].dc_pred = d;
-        data[0] = (short)(d * dq[0]);
+        data[0] = (short)((uint32_t)d * dq[0]);
         int k = 1;
         do {
             const int rs = huff_decode(ac);
@@ -138,9 +138,9 @@ struct Dec {
             const int t = huff_decode(dc);
             if (t < 0 || t > 15) return fail("bad DC code");
             const int diff = t ? extend_receive(t) : 0;
-            const int d = comp[c].dc_pred + diff;
+            const int d = (int)((uint32_t)comp[c].dc_pred + (uint32_t)diff);
             comp[c].dc_pred = d;
-            data[0] = (short)(d * (1 << succ_low));
+            data[0] = (short)((uint32_t)d << succ_low);
         } else if (getbit()) {      // refinement: one more bit
             data[0] += (short)(1 << succ_low);
         }
@@ -213,47 +213,62 @@ struct Dec {
     // ---- inverse DCT: 12-bit fixed point, constants and rounding of stb_image's stbi__idct_block ----
     static inline int f2f(float x) { return (int)(x * 4096 + 0.5); }
     static inline uint8_t clamp8(int x) { return (unsigned)x > 255 ? (x < 0 ? 0 : 255) : (uint8_t)x; }
+    // All sums and products wrap modulo 2^32 (what stb_image's int arithmetic does on every real compiler): a damaged
+    // file may hold coefficients that overflow, and the result must be defined and the same everywhere.
+    struct W32 {
+        uint32_t u;
+        W32() : u(0) {}
+        W32(int x) : u((uint32_t)x) {}
+        friend W32 operator+(W32 a, W32 b) { W32 r; r.u = a.u + b.u; return r; }
+        friend W32 operator-(W32 a, W32 b) { W32 r; r.u = a.u - b.u; return r; }
+        friend W32 operator*(W32 a, W32 b) { W32 r; r.u = a.u * b.u; return r; }
+        W32 &operator+=(W32 b) { u += b.u; return *this; }
+        int sar(int n) const { return (int)(int32_t)u >> n; }       // arithmetic shift of the two's-complement value
+    };
     static void idct(uint8_t *out, int stride, const short d[64]) {
-        int val[64], *v = val;
+        W32 val[64], *v = val;
 #define SVGF_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                                                          \
-    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                                                                   \
+    W32 t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                                                                   \
     p2 = s2; p3 = s6;                                                                                                         \
-    p1 = (p2 + p3) * f2f(0.5411961f);                                                                                         \
-    t2 = p1 + p3 * f2f(-1.847759065f);                                                                                        \
-    t3 = p1 + p2 * f2f(0.765366865f);                                                                                         \
+    p1 = (p2 + p3) * W32(f2f(0.5411961f));                                                                                    \
+    t2 = p1 + p3 * W32(f2f(-1.847759065f));                                                                                   \
+    t3 = p1 + p2 * W32(f2f(0.765366865f));                                                                                    \
     p2 = s0; p3 = s4;                                                                                                         \
-    t0 = (p2 + p3) * 4096; t1 = (p2 - p3) * 4096;                                                                             \
+    t0 = (p2 + p3) * W32(4096); t1 = (p2 - p3) * W32(4096);                                                                   \
     x0 = t0 + t3; x3 = t0 - t3; x1 = t1 + t2; x2 = t1 - t2;                                                                   \
     t0 = s7; t1 = s5; t2 = s3; t3 = s1;                                                                                       \
     p3 = t0 + t2; p4 = t1 + t3; p1 = t0 + t3; p2 = t1 + t2;                                                                   \
-    p5 = (p3 + p4) * f2f(1.175875602f);                                                                                       \
-    t0 = t0 * f2f(0.298631336f); t1 = t1 * f2f(2.053119869f); t2 = t2 * f2f(3.072711026f); t3 = t3 * f2f(1.501321110f);       \
-    p1 = p5 + p1 * f2f(-0.899976223f); p2 = p5 + p2 * f2f(-2.562915447f);                                                     \
-    p3 = p3 * f2f(-1.961570560f); p4 = p4 * f2f(-0.390180644f);                                                               \
+    p5 = (p3 + p4) * W32(f2f(1.175875602f));                                                                                  \
+    t0 = t0 * W32(f2f(0.298631336f)); t1 = t1 * W32(f2f(2.053119869f));                                                       \
+    t2 = t2 * W32(f2f(3.072711026f)); t3 = t3 * W32(f2f(1.501321110f));                                                       \
+    p1 = p5 + p1 * W32(f2f(-0.899976223f)); p2 = p5 + p2 * W32(f2f(-2.562915447f));                                           \
+    p3 = p3 * W32(f2f(-1.961570560f)); p4 = p4 * W32(f2f(-0.390180644f));                                                     \
     t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
         const short *dd = d;
         for (int i = 0; i < 8; ++i, ++dd, ++v) {        // columns
             if (dd[8] == 0 && dd[16] == 0 && dd[24] == 0 && dd[32] == 0 && dd[40] == 0 && dd[48] == 0 && dd[56] == 0) {
-                const int dcterm = dd[0] * 4;
+                const W32 dcterm = W32(dd[0]) * W32(4);
                 v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dcterm;
             } else {
-                SVGF_IDCT_1D(dd[0], dd[8], dd[16], dd[24], dd[32], dd[40], dd[48], dd[56])
-                x0 += 512; x1 += 512; x2 += 512; x3 += 512;
-                v[0] = (x0 + t3) >> 10; v[56] = (x0 - t3) >> 10;
-                v[8] = (x1 + t2) >> 10; v[48] = (x1 - t2) >> 10;
-                v[16] = (x2 + t1) >> 10; v[40] = (x2 - t1) >> 10;
-                v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
+                SVGF_IDCT_1D(W32(dd[0]), W32(dd[8]), W32(dd[16]), W32(dd[24]), W32(dd[32]), W32(dd[40]), W32(dd[48]), W32(dd[56]))
+                const W32 r(512);
+                x0 += r; x1 += r; x2 += r; x3 += r;
+                v[0] = (x0 + t3).sar(10); v[56] = (x0 - t3).sar(10);
+                v[8] = (x1 + t2).sar(10); v[48] = (x1 - t2).sar(10);
+                v[16] = (x2 + t1).sar(10); v[40] = (x2 - t1).sar(10);
+                v[24] = (x3 + t0).sar(10); v[32] = (x3 - t0).sar(10);
             }
         }
         v = val;
         uint8_t *o = out;
         for (int i = 0; i < 8; ++i, v += 8, o += stride) {      // rows; the rounding constant also re-centres the samples on 128
             SVGF_IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
-            x0 += 65536 + (128 << 17); x1 += 65536 + (128 << 17); x2 += 65536 + (128 << 17); x3 += 65536 + (128 << 17);
-            o[0] = clamp8((x0 + t3) >> 17); o[7] = clamp8((x0 - t3) >> 17);
-            o[1] = clamp8((x1 + t2) >> 17); o[6] = clamp8((x1 - t2) >> 17);
-            o[2] = clamp8((x2 + t1) >> 17); o[5] = clamp8((x2 - t1) >> 17);
-            o[3] = clamp8((x3 + t0) >> 17); o[4] = clamp8((x3 - t0) >> 17);
+            const W32 r(65536 + (128 << 17));
+            x0 += r; x1 += r; x2 += r; x3 += r;
+            o[0] = clamp8((x0 + t3).sar(17)); o[7] = clamp8((x0 - t3).sar(17));
+            o[1] = clamp8((x1 + t2).sar(17)); o[6] = clamp8((x1 - t2).sar(17));
+            o[2] = clamp8((x2 + t1).sar(17)); o[5] = clamp8((x2 - t1).sar(17));
+            o[3] = clamp8((x3 + t0).sar(17)); o[4] = clamp8((x3 - t0).sar(17));
         }
 #undef SVGF_IDCT_1D
     }

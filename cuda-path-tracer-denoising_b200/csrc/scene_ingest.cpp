@@ -277,7 +277,8 @@ struct Builder {
         struct Bucket { int count = 0; Box bounds{{0, 0, 0}, {0, 0, 0}}; } bucket[NB];
         for (int i = start; i < end; i++) {
             int b = (int)(NB * offset_on(cb, prims[i].centroid, ax));
-            if (b == NB) b = NB - 1;
+            if (b >= NB) b = NB - 1;
+            if (b < 0) b = 0;
             bucket[b].bounds = unite(bucket[b].bounds, prims[i].bounds);
             bucket[b].count++;
         }
@@ -298,7 +299,9 @@ struct Builder {
                 if (b == NB) b = NB - 1;
                 return b <= split;
             });
-            return interior(n, ax, start, (int)(midp - &prims[0]), end);
+            const int mid = (int)(midp - &prims[0]);
+            if (mid == start || mid == end) return leaf(n, start, end, bounds);   // cannot happen with finite extents; never recurse on it
+            return interior(n, ax, start, mid, end);
         }
         return leaf(n, start, end, bounds);
     }
@@ -370,6 +373,11 @@ bool load_obj(svgf_scene &sc, const std::string &path, svgf_geom &g, const M4 &x
                 if (cs[q].v < 0 || (size_t)(3 * cs[q].v + 2) >= v.size()) { sc.err = "OBJ face references a missing vertex in " + path; return false; }
                 const V4 p = mulmv(xf, V4{v[3 * cs[q].v], v[3 * cs[q].v + 1], v[3 * cs[q].v + 2], 1.0f});
                 wp[q] = V3{p.x, p.y, p.z};
+                // the BVH builder (and the tracer) need ordered coordinates with finite extents
+                if (!(fabsf(p.x) <= 1e18f && fabsf(p.y) <= 1e18f && fabsf(p.z) <= 1e18f)) {
+                    sc.err = "non-finite or out-of-range vertex after the object's transform in " + path;
+                    return false;
+                }
                 memcpy(t.verts[q].pos, &wp[q], 12);
             }
             for (int a = 0; a < 3; a++) {                   // utilityCore::compareThreeVertex + running totals (scene.cpp:273-281)
