@@ -176,13 +176,44 @@ struct TriBest { float t, bx, by; int slot; };
 // irrelevant to the caller. (The closest-hit search would reject the mesh if its CLOSEST triangle sat at exactly t == 0; that
 // this differs needs a triangle hit at exactly 0 and another one before t_any on the same ray.)
 // Slab test of one node record against the ray, with the caller's cull distance (boundingbox.h:62-79 has no t-culling).
+#ifndef SVGF_RT_SLAB_PACKED
+#define SVGF_RT_SLAB_PACKED 2
+#endif
+#ifndef SVGF_RT_SLAB_UNROLL     // A/B (tools/build_rt_ab.sh): unrolling of the candidate loop over the geoms
+#define SVGF_RT_SLAB_UNROLL 1
+#endif
+constexpr int kSlabUnroll = SVGF_RT_SLAB_UNROLL;
+// Entry and exit parameters of a ray against a box {lo.xyz, hi.xyz}: (bound - origin) * invdir per axis. SVGF_RT_SLAB_PACKED (A/B,
+// tools/build_rt_ab.sh): the x and y axes travel as one register pair (FADD2/FMUL2, the same IEEE operations, two per issue slot).
+__device__ __forceinline__ void slab_params(const float4 &lo, const float4 &hi, const Ray &ray, const F3 invdir, float &tn, float &tf) {
+#if SVGF_RT_SLAB_PACKED
+    const float2 no = make_float2(-ray.origin.x, -ray.origin.y), iv = make_float2(invdir.x, invdir.y);
+    const float2 l = __fmul2_rn(__fadd2_rn(make_float2(lo.x, lo.y), no), iv), h = __fmul2_rn(__fadd2_rn(make_float2(hi.x, hi.y), no), iv);
+    const float ax = l.x, ay = l.y, bx = h.x, by = h.y;
+#else
+    const float ax = (lo.x - ray.origin.x) * invdir.x, bx = (hi.x - ray.origin.x) * invdir.x;
+    const float ay = (lo.y - ray.origin.y) * invdir.y, by = (hi.y - ray.origin.y) * invdir.y;
+#endif
+    const float az = (lo.z - ray.origin.z) * invdir.z, bz = (hi.z - ray.origin.z) * invdir.z;
+    tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+}
 __device__ __forceinline__ bool bvh_box_hit(const float4 &a, const float4 &b, const Ray &ray, const F3 invdir, float t_cull) {
+#if SVGF_RT_SLAB_PACKED >= 2
+    const float2 no = make_float2(-ray.origin.x, -ray.origin.y), iv = make_float2(invdir.x, invdir.y);
+    const float2 l = __fmul2_rn(__fadd2_rn(make_float2(a.x, a.y), no), iv), h = __fmul2_rn(__fadd2_rn(make_float2(b.x, b.y), no), iv);
+    const float tzMin = (a.z - ray.origin.z) * invdir.z, tzMax = (b.z - ray.origin.z) * invdir.z;
+    const float tmin = gmax(gmax(gmin(l.x, h.x), gmin(l.y, h.y)), gmin(tzMin, tzMax));
+    const float tmax = gmin(gmin(gmax(l.x, h.x), gmax(l.y, h.y)), gmax(tzMin, tzMax));
+    return !(tmax < 0) && !(tmin > tmax) && !(tmin > t_cull * 1.0001f + 1e-4f);
+#else
     const float txMin = (a.x - ray.origin.x) * invdir.x, txMax = (b.x - ray.origin.x) * invdir.x;
     const float tyMin = (a.y - ray.origin.y) * invdir.y, tyMax = (b.y - ray.origin.y) * invdir.y;
     const float tzMin = (a.z - ray.origin.z) * invdir.z, tzMax = (b.z - ray.origin.z) * invdir.z;
     const float tmin = gmax(gmax(gmin(txMin, txMax), gmin(tyMin, tyMax)), gmin(tzMin, tzMax));
     const float tmax = gmin(gmin(gmax(txMin, txMax), gmax(tyMin, tyMax)), gmax(tzMin, tzMax));
     return !(tmax < 0) && !(tmin > tmax) && !(tmin > t_cull * 1.0001f + 1e-4f);
+#endif
 }
 
 #ifndef SVGF_RT_BVH_PAIRED
@@ -264,6 +295,88 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
     return hit;
 }
 #else
+#ifndef SVGF_RT_TRI_FLAT
+#define SVGF_RT_TRI_FLAT 0
+#endif
+#ifndef SVGF_RT_BVH_WW
+#define SVGF_RT_BVH_WW 0
+#endif
+// Triangle::Intersect over glm::intersectRayTriangle for the triangle in `slot`. SVGF_RT_TRI_FLAT (A/B, tools/build_rt_ab.sh): the
+// same expressions without the early exits -- every lane of a leaf runs the whole test and one predicate decides -- so that lanes
+// rejected at different stages do not drift apart inside the loop.
+__device__ __forceinline__ void tri_test(const SceneView &sc, const Ray &ray, int slot, bool &hit, TriBest &best, float t_any, int &top,
+                                         float &t_bound) {
+    const float4 h0 = __ldg(&sc.tri_hot[3 * slot]), h1 = __ldg(&sc.tri_hot[3 * slot + 1]), h2 = __ldg(&sc.tri_hot[3 * slot + 2]);
+    const F3 v0 = mk(h0.x, h0.y, h0.z), e1 = mk(h1.x, h1.y, h1.z), e2 = mk(h2.x, h2.y, h2.z);
+    const F3 p = cross(ray.direction, e2);
+    const float det = dot(e1, p);
+#if SVGF_RT_TRI_FLAT
+    const float f = 1.0f / det;
+    const F3 s = ray.origin - v0;
+    const float bx = f * dot(s, p);
+    const F3 q = cross(s, e1);
+    const float by = f * dot(ray.direction, q);
+    const float bz = f * dot(e2, q);
+    // the reference's chain of rejections, comparison for comparison (a NaN passes where it passes there)
+    const bool ok = !(det < FLT_EPSILON) & !(bx < 0.0f) & !(bx > 1.0f) & !(by < 0.0f) & !(by + bx > 1.0f) & (bz >= 0.0f);
+    if (ok) {
+        hit = true;
+        if (bz < best.t) { best.t = bz; best.bx = bx; best.by = by; best.slot = slot; }
+        if (bz > 0.0f && bz < t_any) { top = 0; t_bound = -FLT_MAX; }
+    }
+#else
+    if (det < FLT_EPSILON) return;
+    const float f = 1.0f / det;
+    const F3 s = ray.origin - v0;
+    const float bx = f * dot(s, p);
+    if (bx < 0.0f) return;
+    if (bx > 1.0f) return;
+    const F3 q = cross(s, e1);
+    const float by = f * dot(ray.direction, q);
+    if (by < 0.0f) return;
+    if (by + bx > 1.0f) return;
+    const float bz = f * dot(e2, q);
+    if (!(bz >= 0.0f)) return;
+    hit = true;
+    if (bz < best.t) { best.t = bz; best.bx = bx; best.by = by; best.slot = slot; }
+    if (bz > 0.0f && bz < t_any) { top = 0; t_bound = -FLT_MAX; }      // (light query, compiled out by default: ends the search through data)
+#endif
+}
+#if SVGF_RT_BVH_WW
+// A/B variant (tools/build_rt_ab.sh): "while-while" form of the same walk. The inner loop runs down to the next leaf whose box the
+// ray hits, the lanes of a warp meet again at its exit, and only then are the triangles tested -- in the default loop a lane at a
+// leaf runs its triangle tests while the lanes at interior nodes wait, and the other way round. Nodes and triangles are visited
+// in the same order with the same cull distances, so the results are the same bits.
+__device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, float t_bound, TriBest &best, float t_any = 0.f) {
+    if (sc.n_nodes == 0) return false;
+    bool hit = false;
+    const int neg[3] = {ray.direction.x < 0.f, ray.direction.y < 0.f, ray.direction.z < 0.f};
+    int top = 0, cur = 0;
+    int stack[64];
+    best.t = FLT_MAX; best.slot = -1; best.bx = best.by = 0.f;
+    while (true) {
+        int off = 0, count = 0;
+        while (true) {
+            const float4 a = __ldg(&sc.bvh[2 * cur]), b = __ldg(&sc.bvh[2 * cur + 1]);
+            if (bvh_box_hit(a, b, ray, invdir, fminf(best.t, t_bound))) {
+                const int meta = __float_as_int(a.w), o = __float_as_int(b.w);
+                if ((meta & 0xffff) > 0) { off = o; count = meta & 0xffff; break; }
+                if (top == 64) { cur = stack[--top]; continue; }
+                if (neg[meta >> 16]) { stack[top++] = cur + 1; cur = o; }
+                else { stack[top++] = o; cur = cur + 1; }
+            } else {
+                if (top == 0) break;
+                cur = stack[--top];
+            }
+        }
+        if (count == 0) break;
+        for (int i = 0; i < count; i++) tri_test(sc, ray, off + i, hit, best, t_any, top, t_bound);
+        if (top == 0) break;
+        cur = stack[--top];
+    }
+    return hit;
+}
+#else
 __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdir, float t_bound, TriBest &best, float t_any = 0.f) {
     if (sc.n_nodes == 0) return false;
     bool hit = false;
@@ -278,28 +391,7 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
             const int meta = __float_as_int(a.w), off = __float_as_int(b.w);
             const int count = meta & 0xffff;
             if (count > 0) {
-                for (int i = 0; i < count; i++) {
-                    const int slot = off + i;
-                    const float4 h0 = __ldg(&sc.tri_hot[3 * slot]), h1 = __ldg(&sc.tri_hot[3 * slot + 1]), h2 = __ldg(&sc.tri_hot[3 * slot + 2]);
-                    const F3 v0 = mk(h0.x, h0.y, h0.z), e1 = mk(h1.x, h1.y, h1.z), e2 = mk(h2.x, h2.y, h2.z);
-                    const F3 p = cross(ray.direction, e2);
-                    const float det = dot(e1, p);
-                    if (det < FLT_EPSILON) continue;
-                    const float f = 1.0f / det;
-                    const F3 s = ray.origin - v0;
-                    const float bx = f * dot(s, p);
-                    if (bx < 0.0f) continue;
-                    if (bx > 1.0f) continue;
-                    const F3 q = cross(s, e1);
-                    const float by = f * dot(ray.direction, q);
-                    if (by < 0.0f) continue;
-                    if (by + bx > 1.0f) continue;
-                    const float bz = f * dot(e2, q);
-                    if (!(bz >= 0.0f)) continue;
-                    hit = true;
-                    if (bz < best.t) { best.t = bz; best.bx = bx; best.by = by; best.slot = slot; }
-                    if (bz > 0.0f && bz < t_any) { top = 0; t_bound = -FLT_MAX; }
-                }
+                for (int i = 0; i < count; i++) tri_test(sc, ray, off + i, hit, best, t_any, top, t_bound);
                 if (top == 0) break;
                 cur = stack[--top];
             } else {
@@ -315,6 +407,7 @@ __device__ bool intersectBVH(const SceneView &sc, const Ray &ray, const F3 invdi
     }
     return hit;
 }
+#endif
 #endif
 
 struct Isect {      // the live part of ShadeableIntersection (sceneStructs.h:104-111)
@@ -359,7 +452,7 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
         unsigned cubes = 0, spheres = 0;
         float near_tn = FLT_MAX; int near_j = -1;       // candidate whose bounds the ray enters first
         const int n = min(32, sc.n_geoms - base);
-#pragma unroll 1
+#pragma unroll kSlabUnroll
         for (int j = 0; j < n; j++) {
             const GeomD &g = sc.geoms[base + j];
             if (g.type == 2) { any_mesh = true; continue; }
@@ -367,11 +460,16 @@ __device__ bool computeIntersection(const SceneView &sc, const Ray &ray, Isect &
             // then runs as in the reference); 0 * inf only arises for a ray lying IN a padded face plane, which is outside
             // the real surface by ~50x the rounding of the exact test, so dropping that NaN (fminf/fmaxf) can only reject
             // true misses.
+#if SVGF_RT_SLAB_PACKED
+            float tn, tf;
+            slab_params(*reinterpret_cast<const float4 *>(g.aabb_min), *reinterpret_cast<const float4 *>(g.aabb_max), ray, invdir, tn, tf);
+#else
             const float ax = (g.aabb_min[0] - ray.origin.x) * invdir.x, bx = (g.aabb_max[0] - ray.origin.x) * invdir.x;
             const float ay = (g.aabb_min[1] - ray.origin.y) * invdir.y, by = (g.aabb_max[1] - ray.origin.y) * invdir.y;
             const float az = (g.aabb_min[2] - ray.origin.z) * invdir.z, bz = (g.aabb_max[2] - ray.origin.z) * invdir.z;
             const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
             const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+#endif
             if (tf < tn || tf < 0.f) continue;      // the exact test would return -1 (no hit)
             if (g.type == 1) cubes |= 1u << j; else spheres |= 1u << j;
             if (tn < near_tn) { near_tn = tn; near_j = j; }
@@ -636,7 +734,16 @@ struct RtPush {
 // ML: "light_sampling_all" (the reference samples geoms[0] only, pathtrace.cu:359-361): every shadow ray
 // picks one of the emissive cubes/spheres uniformly (one more random number per shadow ray) and its contribution is scaled by
 // their number. A separate instantiation: the default kernel carries none of it.
-template <int MINB, bool PUSH, bool ML>
+// CP: "compaction" (A/B, SVGF_RT_COMPACT=1). Paths end at different depths (the light, the open side of the room, the depth limit), and
+// a warp runs until its longest path has ended: on cornell a third of the lanes of the warps that still run are dead. With CP the
+// block meets after every bounce; when its live paths fit into fewer warps than they occupy, they move (20 words each, through shared
+// memory) into the lowest threads of the block and the freed warps only attend the barriers from then on. Which thread carries a
+// path cannot change its pixel: everything is keyed by the pixel index, the RNG is re-seeded from (pixel, frame + depth).
+constexpr int CP_WORDS = 20, CP_WARPS = RT_BX * RT_BY / 32;
+__host__ __device__ inline size_t cp_smem_offset(size_t scene_bytes) { return (scene_bytes + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t cp_smem_bytes() { return 2 * CP_WARPS * sizeof(int) + (size_t)CP_WORDS * RT_BX * RT_BY * sizeof(unsigned); }
+
+template <int MINB, bool PUSH, bool ML, bool CP = false>
 __global__ void __launch_bounds__(RT_BX *RT_BY, MINB)
 rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf_material *__restrict__ g_materials,
           int n_materials, const float4 *__restrict__ bvh, int n_nodes, const float4 *__restrict__ tri_hot,
@@ -646,12 +753,17 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
           float4 *__restrict__ gnp_out, float2 *__restrict__ gzl_out, const __grid_constant__ RtPush push) {
     extern __shared__ __align__(16) unsigned char smem[];
     GeomS *s_geoms; svgf_material *s_mats;
-    stage_scene(smem, g_geoms, n_geoms, g_materials, n_materials, threadIdx.y * RT_BX + threadIdx.x, RT_BX * RT_BY, s_geoms, s_mats);
+    static_assert(!(CP && PUSH), "the compacting kernel does not push halo rows");
+    const int tid = threadIdx.y * RT_BX + threadIdx.x;
+    stage_scene(smem, g_geoms, n_geoms, g_materials, n_materials, tid, RT_BX * RT_BY, s_geoms, s_mats);
     __syncthreads();
     const int x = blockIdx.x * RT_BX + threadIdx.x;
     const int y = P.row_begin + blockIdx.y * RT_BY + threadIdx.y;
-    if (x >= P.W || y >= P.row_end) return;
-    const int idx = x + y * P.W;
+    bool alive = !(x >= P.W || y >= P.row_end);
+    if (!CP && !alive) return;
+    int idx = x + y * P.W;
+    int *cp_cnt = reinterpret_cast<int *>(smem + cp_smem_offset(scene_smem_bytes(n_geoms, n_materials)));
+    unsigned *cp_state = reinterpret_cast<unsigned *>(cp_cnt + 2 * CP_WARPS);
 
     SceneView sc;
     sc.geoms = s_geoms; sc.n_geoms = n_geoms; sc.materials = s_mats; sc.bvh = bvh; sc.n_nodes = n_nodes;
@@ -680,6 +792,9 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
     int shadow_light = 0;   // the geom the shadow ray in flight aims at (ML only; otherwise geoms[0])
     bool pushed_rows = false;   // PUSH: this thread stored G-buffer rows into a neighbour's planes
 
+    for (int round = 0;; round++) {     // CP: one trip per bounce of the block; otherwise a single trip
+    if (!CP || alive) {
+    bool finished = true;               // the path has ended (every exit of the loop below but the CP one at its bottom)
     while (true) {
         Isect res; res.geomId = -2; res.materialId = 0; res.t = 0.f; res.n = mk(0, 0, 0); res.u = res.v = 0.f;
         const int lightIdx = ML ? shadow_light : 0;
@@ -745,18 +860,67 @@ rt_kernel(RtParams P, const GeomD *__restrict__ g_geoms, int n_geoms, const svgf
         scatterRay(seg, ipos, inrm, sc.materials[is.materialId], seed);
         cur = seg.ray;
         kind = Q_PATH;
+        if (CP) { finished = false; break; }        // bounce boundary: the block takes stock
     }
-    float *img = image + 3 * (size_t)idx;
-    if (P.denoise) { img[0] = acc.x; img[1] = acc.y; img[2] = acc.z; }
-    else {          // running mean, pathtrace.cu:398
-        const float f = (float)P.frame, f1 = (float)(P.frame + 1);
-        F3 old = mk(img[0], img[1], img[2]);
-        F3 nw = old * f / f1 + acc / f1;
-        img[0] = nw.x; img[1] = nw.y; img[2] = nw.z;
+    if (finished) {
+        float *img = image + 3 * (size_t)idx;
+        if (P.denoise) { img[0] = acc.x; img[1] = acc.y; img[2] = acc.z; }
+        else {          // running mean, pathtrace.cu:398
+            const float f = (float)P.frame, f1 = (float)(P.frame + 1);
+            F3 old = mk(img[0], img[1], img[2]);
+            F3 nw = old * f / f1 + acc / f1;
+            img[0] = nw.x; img[1] = nw.y; img[2] = nw.z;
+        }
+        if (any_hit) {
+            stale_nm[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.materialId));
+            stale_uv[idx] = make_float2(is.u, is.v);
+        }
+        alive = false;
     }
-    if (any_hit) {
-        stale_nm[idx] = make_float4(is.n.x, is.n.y, is.n.z, __int_as_float(is.materialId));
-        stale_uv[idx] = make_float2(is.u, is.v);
+    }
+    if (!CP) break;
+    {   // every thread of the block, alive or not, comes through here once per round
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        const int lane = tid & 31, w = tid >> 5;
+        int *cnt = cp_cnt + (round & 1) * CP_WARPS;     // two sets: a fast warp may post round r+1 while a slow one still reads round r
+        if (lane == 0) cnt[w] = __popc(bal);
+        __syncthreads();
+        int total = 0, before = 0, warps_now = 0;
+#pragma unroll
+        for (int i = 0; i < CP_WARPS; i++) { const int n = cnt[i]; total += n; before += i < w ? n : 0; warps_now += n > 0; }
+        if (total == 0) break;
+        if (((total + 31) >> 5) < warps_now) {
+            constexpr int NT = RT_BX * RT_BY;
+            if (alive) {
+                unsigned *d = cp_state + before + __popc(bal & ((1u << lane) - 1u));
+                d[0 * NT] = (unsigned)idx;
+                d[1 * NT] = __float_as_uint(cur.origin.x); d[2 * NT] = __float_as_uint(cur.origin.y); d[3 * NT] = __float_as_uint(cur.origin.z);
+                d[4 * NT] = __float_as_uint(cur.direction.x); d[5 * NT] = __float_as_uint(cur.direction.y); d[6 * NT] = __float_as_uint(cur.direction.z);
+                d[7 * NT] = __float_as_uint(seg.color.x); d[8 * NT] = __float_as_uint(seg.color.y); d[9 * NT] = __float_as_uint(seg.color.z);
+                d[10 * NT] = __float_as_uint(acc.x); d[11 * NT] = __float_as_uint(acc.y); d[12 * NT] = __float_as_uint(acc.z);
+                d[13 * NT] = ((unsigned)depth & 0x0fffffffu) | (seg.diffuse ? 0x10000000u : 0u) | (any_hit ? 0x20000000u : 0u) | (stale_loaded ? 0x40000000u : 0u);
+                d[14 * NT] = __float_as_uint(is.n.x); d[15 * NT] = __float_as_uint(is.n.y); d[16 * NT] = __float_as_uint(is.n.z);
+                d[17 * NT] = (unsigned)is.materialId; d[18 * NT] = __float_as_uint(is.u); d[19 * NT] = __float_as_uint(is.v);
+            }
+            __syncthreads();
+            alive = tid < total;
+            if (alive) {
+                const unsigned *d = cp_state + tid;
+                idx = (int)d[0 * NT];
+                cur.origin = mk(__uint_as_float(d[1 * NT]), __uint_as_float(d[2 * NT]), __uint_as_float(d[3 * NT]));
+                cur.direction = mk(__uint_as_float(d[4 * NT]), __uint_as_float(d[5 * NT]), __uint_as_float(d[6 * NT]));
+                seg.ray = cur;
+                seg.color = mk(__uint_as_float(d[7 * NT]), __uint_as_float(d[8 * NT]), __uint_as_float(d[9 * NT]));
+                acc = mk(__uint_as_float(d[10 * NT]), __uint_as_float(d[11 * NT]), __uint_as_float(d[12 * NT]));
+                const unsigned f = d[13 * NT];
+                depth = (int)(f & 0x0fffffffu); seg.diffuse = (f & 0x10000000u) != 0; any_hit = (f & 0x20000000u) != 0; stale_loaded = (f & 0x40000000u) != 0;
+                is.n = mk(__uint_as_float(d[14 * NT]), __uint_as_float(d[15 * NT]), __uint_as_float(d[16 * NT]));
+                is.materialId = (int)d[17 * NT]; is.u = __uint_as_float(d[18 * NT]); is.v = __uint_as_float(d[19 * NT]);
+                kind = Q_PATH;
+            }
+            // (the next stores into cp_state follow the next round's barrier, which every thread reaches after these loads)
+        }
+    }
     }
     if (PUSH && pushed_rows) __threadfence_system();     // in the neighbours' memory before any later flag of this rank
 }
@@ -1172,6 +1336,7 @@ void preload_pathtrace_kernels() {
     cudaFuncGetAttributes(&a, rt_kernel<8, false, false>); cudaFuncGetAttributes(&a, rt_kernel<8, true, false>); cudaFuncGetAttributes(&a, rt_kernel<7, false, false>);
     cudaFuncGetAttributes(&a, rt_kernel<4, false, false>); cudaFuncGetAttributes(&a, rt_kernel<4, true, false>);
     cudaFuncGetAttributes(&a, rt_kernel<8, false, true>); cudaFuncGetAttributes(&a, rt_kernel<8, true, true>);
+    cudaFuncGetAttributes(&a, rt_kernel<7, false, false, true>); cudaFuncGetAttributes(&a, rt_kernel<8, false, false, true>);
     cudaFuncGetAttributes(&a, rt_persistent_kernel);
     cudaFuncGetAttributes(&a, wf_generate_kernel); cudaFuncGetAttributes(&a, wf_intersect_kernel); cudaFuncGetAttributes(&a, wf_reset_counts_kernel);
     cudaFuncGetAttributes(&a, wf_shade_kernel); cudaFuncGetAttributes(&a, wf_shade_shadow_kernel);
@@ -1216,13 +1381,15 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
         for (int i = 0; i < push.peers.n; i++) { push.gnp[i] = c->p_gnp.p[push.peers.rank[i]]; push.gzl[i] = c->p_gzl.p[push.peers.rank[i]]; }
         if (pushed) *pushed = true;
     }
-#define RT_LAUNCH(MINB, PUSH, ML)                                                                                                \
+#define RT_LAUNCH(MINB, PUSH, ML, ...)                                                                                           \
     do {                                                                                                                         \
-        if (smem > 48 * 1024) {                                                                                                  \
-            cudaError_t e = cudaFuncSetAttribute(rt_kernel<MINB, PUSH, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        auto kern = rt_kernel<MINB, PUSH, ML, ##__VA_ARGS__>;                                                                    \
+        const size_t sm = (0, ##__VA_ARGS__) ? cp_smem_offset(smem) + cp_smem_bytes() : smem;                                    \
+        if (sm > 48 * 1024) {                                                                                                    \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                    \
             if (e != cudaSuccess) return e;                                                                                      \
         }                                                                                                                        \
-        rt_kernel<MINB, PUSH, ML><<<grid, block, smem, c->rt_launch_stream ? c->rt_launch_stream : c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh,    \
+        kern<<<grid, block, sm, c->rt_launch_stream ? c->rt_launch_stream : c->stream>>>(p, s.geoms, s.n_geoms, s.materials, s.n_materials, s.bvh, \
                                                                     s.n_nodes, s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, \
                                                                     c->alb, c->image, c->stale_nm, c->stale_uv, c->gnp, c->gzl, push); \
     } while (0)
@@ -1230,6 +1397,8 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
     // 84 B of spills) run 15-30 % faster than 4 blocks/SM (110 registers, none); 10 and 12 were slower again (measured on
     // B200: C2 0.93/0.80/0.86/0.89 ms, C3 3.73/2.82/2.85/2.92 ms for 4/8/10/12). SVGF_RT_MINBLOCKS=4 keeps the A/B.
     static const int minb = getenv("SVGF_RT_MINBLOCKS") ? atoi(getenv("SVGF_RT_MINBLOCKS")) : 8;
+    // A/B: 1 = compacting kernel for the scenes that run at 7 blocks/SM, 2 = for every unsharded frame (see rt_kernel, CP)
+    static const int rt_compact = getenv("SVGF_RT_COMPACT") ? atoi(getenv("SVGF_RT_COMPACT")) : 0;
     const bool do_push = push.peers.n > 0;
     if (p.n_lights > 1) { if (do_push) RT_LAUNCH(8, true, true); else RT_LAUNCH(8, false, true); }
     else if (minb == 4) { if (do_push) RT_LAUNCH(4, true, false); else RT_LAUNCH(4, false, false); }
@@ -1240,6 +1409,8 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
     // spheres with next to no mesh (cornell: 38 triangles, 11 BVH nodes) is short of registers (C2 774 vs 805 us), a scene with
     // real meshes is short of warps to hide the BVH loads behind (room, 819 nodes: 2909 vs 2800 us). 5 and 6 lose on both.
     else if (do_push) RT_LAUNCH(8, true, false);
+    else if (rt_compact == 1 && s.n_nodes <= 64 && minb == 8) RT_LAUNCH(7, false, false, true);
+    else if (rt_compact == 2) RT_LAUNCH(8, false, false, true);
     else if (s.n_nodes <= 64 && minb == 8) RT_LAUNCH(7, false, false);
     else RT_LAUNCH(8, false, false);
 #endif
