@@ -46,7 +46,18 @@ __device__ __forceinline__ float gmax(float x, float y) { return x > y ? x : y; 
 __device__ __forceinline__ float gabs(float x) { return x >= 0.0f ? x : -x; }
 
 // glm mat4 * vec4 -> xyz, (m0 v0 + m1 v1) + (m2 v2 + m3 v3)   (intersections.h:36-38)
+#ifndef SVGF_RT_MV_PACKED       // A/B (tools/build_rt_ab.sh): rows x and y of the product as one register pair (FMUL2/FFMA2/FADD2), the same
+#define SVGF_RT_MV_PACKED 0     // operations with the same roundings as the scalar form the compiler makes of the loop below
+#endif
 __device__ __forceinline__ F3 multiplyMV(const float *m, F3 v, float w) {
+#if SVGF_RT_MV_PACKED
+    const float2 c0 = make_float2(m[0], m[1]), c1 = make_float2(m[4], m[5]), c2 = make_float2(m[8], m[9]), c3 = make_float2(m[12], m[13]);
+    const float2 a0 = __ffma2_rn(c0, make_float2(v.x, v.x), __fmul2_rn(c1, make_float2(v.y, v.y)));
+    const float2 a1 = __ffma2_rn(c2, make_float2(v.z, v.z), __fmul2_rn(c3, make_float2(w, w)));
+    const float2 xy = __fadd2_rn(a0, a1);
+    const float z0 = __fmaf_rn(m[2], v.x, __fmul_rn(m[6], v.y)), z1 = __fmaf_rn(m[10], v.z, __fmul_rn(m[14], w));
+    return mk(xy.x, xy.y, __fadd_rn(z0, z1));
+#else
     float o[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
@@ -55,14 +66,19 @@ __device__ __forceinline__ F3 multiplyMV(const float *m, F3 v, float w) {
         o[r] = add0 + add1;
     }
     return mk(o[0], o[1], o[2]);
+#endif
 }
 
 struct Ray { F3 origin, direction; };
 
 // interactions.h:10-30
+#ifndef SVGF_RT_TEA_UNROLL      // A/B (tools/build_rt_ab.sh): rounds per trip of the hash loop
+#define SVGF_RT_TEA_UNROLL 1
+#endif
+constexpr int kTeaUnroll = SVGF_RT_TEA_UNROLL;
 __device__ __forceinline__ unsigned int initRand(unsigned int val0, unsigned int val1) {
     unsigned int v0 = val0, v1 = val1, s0 = 0;
-#pragma unroll 1
+#pragma unroll kTeaUnroll
     for (unsigned int n = 0; n < 16; n++) {
         s0 += 0x9e3779b9;
         v0 += ((v1 << 4) + 0xa341316c) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4);
@@ -1381,10 +1397,10 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
         for (int i = 0; i < push.peers.n; i++) { push.gnp[i] = c->p_gnp.p[push.peers.rank[i]]; push.gzl[i] = c->p_gzl.p[push.peers.rank[i]]; }
         if (pushed) *pushed = true;
     }
-#define RT_LAUNCH(MINB, PUSH, ML, ...)                                                                                           \
+#define RT_LAUNCH_X(MINB, PUSH, ML, CP)                                                                                          \
     do {                                                                                                                         \
-        auto kern = rt_kernel<MINB, PUSH, ML, ##__VA_ARGS__>;                                                                    \
-        const size_t sm = (0, ##__VA_ARGS__) ? cp_smem_offset(smem) + cp_smem_bytes() : smem;                                    \
+        auto kern = rt_kernel<MINB, PUSH, ML, CP>;                                                                               \
+        const size_t sm = CP ? cp_smem_offset(smem) + cp_smem_bytes() : smem;                                                    \
         if (sm > 48 * 1024) {                                                                                                    \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                    \
             if (e != cudaSuccess) return e;                                                                                      \
@@ -1393,6 +1409,7 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
                                                                     s.n_nodes, s.tri_hot, s.tri_cold, s.textures, nrm_out, c->pos, \
                                                                     c->alb, c->image, c->stale_nm, c->stale_uv, c->gnp, c->gzl, push); \
     } while (0)
+#define RT_LAUNCH(MINB, PUSH, ML) RT_LAUNCH_X(MINB, PUSH, ML, false)
     // Occupancy beats registers here: the kernel waits on dependent fp32 chains and BVH loads, so 8 blocks/SM (64 registers,
     // 84 B of spills) run 15-30 % faster than 4 blocks/SM (110 registers, none); 10 and 12 were slower again (measured on
     // B200: C2 0.93/0.80/0.86/0.89 ms, C3 3.73/2.82/2.85/2.92 ms for 4/8/10/12). SVGF_RT_MINBLOCKS=4 keeps the A/B.
@@ -1409,11 +1426,12 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
     // spheres with next to no mesh (cornell: 38 triangles, 11 BVH nodes) is short of registers (C2 774 vs 805 us), a scene with
     // real meshes is short of warps to hide the BVH loads behind (room, 819 nodes: 2909 vs 2800 us). 5 and 6 lose on both.
     else if (do_push) RT_LAUNCH(8, true, false);
-    else if (rt_compact == 1 && s.n_nodes <= 64 && minb == 8) RT_LAUNCH(7, false, false, true);
-    else if (rt_compact == 2) RT_LAUNCH(8, false, false, true);
+    else if (rt_compact == 1 && s.n_nodes <= 64 && minb == 8) RT_LAUNCH_X(7, false, false, true);
+    else if (rt_compact == 2) RT_LAUNCH_X(8, false, false, true);
     else if (s.n_nodes <= 64 && minb == 8) RT_LAUNCH(7, false, false);
     else RT_LAUNCH(8, false, false);
 #endif
 #undef RT_LAUNCH
+#undef RT_LAUNCH_X
     return cudaGetLastError();
 }
