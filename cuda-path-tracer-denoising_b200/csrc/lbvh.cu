@@ -187,6 +187,7 @@ extern "C" int svgf_rebuild_bvh(svgf_ctx *c) {
     cudaFree(c->scene.bvh); cudaFree(c->scene.tri_hot); cudaFree(c->scene.tri_cold);
     c->scene.bvh = nodes; c->scene.tri_hot = new_hot; c->scene.tri_cold = new_cold; c->scene.n_nodes = nn;
     nodes = nullptr; new_hot = nullptr; new_cold = nullptr;
+    c->temporal_done_valid = false;
 done:
     cudaFree(tri_b6); cudaFree(scene6); cudaFree(node_b6); cudaFree(keys); cudaFree(keys_sorted); cudaFree(ints); cudaFree(tmp);
     cudaFree(nodes); cudaFree(new_hot); cudaFree(new_cold);
@@ -221,6 +222,9 @@ extern "C" int svgf_refit_bvh(svgf_ctx *c, const svgf_triangle *triangles, int n
     LB(cudaMemsetAsync(c->bvh_parent + nn, 0, sizeof(int) * (size_t)nn, st));
     refit_boxes_kernel<<<(nn + T - 1) / T, T, 0, st>>>(c->scene.bvh, nn, c->scene.tri_hot, c->bvh_parent, c->bvh_parent + nn);
     LB(cudaGetLastError());
+    // an overlapped next frame (option frame_overlap) starts its path tracer on another stream after the previous frame's temporal
+    // pass only: make it wait for everything queued on this stream so far, the refit included
+    c->temporal_done_valid = false;
 done:
     return rc;
 }

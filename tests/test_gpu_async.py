@@ -152,3 +152,29 @@ def test_cross_frame_overlap_is_bit_identical(case, monkeypatch):
     assert len(outs[0]) == len(outs[1])
     for i, (a, b) in enumerate(zip(*outs)):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), "output %d differs between the overlapped and the serial schedule" % i
+
+
+def test_overlapped_frames_wait_for_a_bvh_refit(monkeypatch):
+    """With frame_overlap the next frame's path tracer starts on its own stream as soon as the previous frame's temporal pass is
+    done. A svgf_refit_bvh queued between two frames writes the triangle records and the tree that path tracer reads: it must be
+    ordered before it (csrc/lbvh.cu invalidates the hand-over event). Frames queued back to back, meshes moved every frame,
+    nothing synchronised in between: the bits of the serial schedule."""
+    outs = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("SVGF_FRAME_OVERLAP", on)
+        m = svgf()
+        W, H = 320, 200
+        blob, R = m.open_scene("bunny", W, H)
+        n = blob.counts["tris"]
+        base = np.ascontiguousarray(blob.triangles).view(np.uint8).reshape(n, 136).copy()
+        drv = blob.camera_driver(W, H)
+        P = m.default_params(atrous_nlevel=3)
+        for f in range(8):
+            moved = base.view(np.float32).reshape(n, 34).copy()
+            moved[:, [1, 9, 17]] += 0.05 * f
+            R.refit_bvh(moved.view(np.uint8))
+            R.pathtrace(drv.step(), P, f)
+        outs.append([R.fetch("denoised"), R.fetch("image"), R.fetch("gbuffer"), R.fetch("history_length")])
+        R.close()
+    for a, b, what in zip(outs[0], outs[1], ("denoised", "image", "gbuffer", "history_length")):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), "%s differs between the overlapped and the serial schedule" % what
