@@ -16,23 +16,29 @@
 
 namespace {
 
-__device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, float by, float bz) {
-    // glm::distance(a, b) = length(b - a), detail/func_geometric.inl:108-111
-    const float dx = bx - ax, dy = by - ay, dz = bz - az;
-    return sqrtf(dx * dx + dy * dy + dz * dz);
-}
-
 // isReprjValid, denoise.cu:172-182, for a tap at float coordinates (px, py) of the previous frame.
 // Returns the linear index of the tap through `q`.
+// Which rank's planes hold row `row` of the previous frame. SINGLE (one strip = the whole frame): always mine, and the table lookups
+// fold into one pointer per plane. The row of a tap is known from its coordinates; only frames of 2^24 pixels and more, where the
+// reference's float index arithmetic stops being exact, divide the (rounded) index.
+template <bool SINGLE> struct TapOwner {
+    const RowOwner &ro; int me; int W; bool exact;
+    __device__ __forceinline__ int operator()(int row, int q) const { return SINGLE ? me : owner_of(ro, exact ? row : q / W); }
+};
+template <bool SINGLE>
 __device__ __forceinline__ bool reprj_valid(int W, int H, float px, float py, const float4 &ncur,
-                                            const PeerPtr<float4> &nrm_prev, const RowOwner &ro, int &q) {
+                                            const PeerPtr<float4> &nrm_prev, const TapOwner<SINGLE> &own, int &q) {
     // NaN coordinates pass the reference's bounds test and index garbage (undefined); rejected here.
     if (!(px >= 0.f) || !(px < (float)W) || !(py >= 0.f) || !(py < (float)H)) return false;
     q = (int)(px + py * (float)W);
-    const float4 np = __ldg(&nrm_prev.p[owner_of(ro, q / W)][q]);
+    const float4 np = __ldg(&nrm_prev.p[own((int)py, q)][q]);
     const int gprev = __float_as_int(np.w), gcur = __float_as_int(ncur.w);
     if (gprev == -1 || gprev != gcur) return false;
-    if (dist3(np.x, np.y, np.z, ncur.x, ncur.y, ncur.z) > 1e-1f) return false;
+    // glm::distance(n_prev, n_cur) = length(n_cur - n_prev) (detail/func_geometric.inl:108-111) > 1e-1f without the square root: the correctly rounded sqrtf is monotonic, and 0x3c23d70b
+    // (0.010000001f) is the largest float whose root is still <= 0.1f, so the comparison of the squares decides identically
+    // (NaN: false both ways). Saves an IEEE square root (~10 instructions) per tap in a kernel that is short of issue slots.
+    const float dx = ncur.x - np.x, dy = ncur.y - np.y, dz = ncur.z - np.z;
+    if (dx * dx + dy * dy + dz * dz > __uint_as_float(0x3c23d70bu)) return false;
     return true;
 }
 
@@ -46,11 +52,13 @@ struct TemporalOut { float4 cv; float2 lv, mom; int hlen; };
 // history length 4.
 // (Requesting the four taps' history records together with their normals -- two dependent round trips to memory instead of
 // three -- was measured on B200 and is SLOWER, 69.6 vs 62 us at C2: 64 registers instead of 47 cost a resident block per SM.)
+template <bool SINGLE>
 __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const float *__restrict__ image, const float4 *__restrict__ nrm_cur,
                                                       const PeerPtr<float4> &nrm_prev, const float4 *__restrict__ pos, const PeerPtr<float4> &hist_cv,
                                                       const PeerPtr<float2> &mom_hist, const PeerPtr<int> &hlen_tab, const RowOwner &ro, int me,
                                                       const Mat4 &vm, float color_alpha_min, float moment_alpha_min, float clip_rx, float clip_ry,
                                                       int hist_cap) {
+    const TapOwner<SINGLE> own{ro, me, W, (long long)W * H < (1ll << 24)};
     const int N = hlen_tab.p[me][p];     // own pixel (denoise.cu:194)
     const float sr = image[3 * (size_t)p], sg = image[3 * (size_t)p + 1], sb = image[3 * (size_t)p + 2];
     const float4 ncur = nrm_cur[p];
@@ -81,7 +89,7 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
         for (int s = 0; s < 4; s++) {
             const int lx = (int)((unsigned)ifx + (unsigned)(s & 1)), ly = (int)((unsigned)ify + (unsigned)(s >> 1));
             qi[s] = 0;
-            v[s] = reprj_valid(W, H, (float)lx, (float)ly, ncur, nrm_prev, ro, qi[s]);
+            v[s] = reprj_valid<SINGLE>(W, H, (float)lx, (float)ly, ncur, nrm_prev, own, qi[s]);
             qi[s] = lx + ly * W;
             valid = valid && v[s];
         }
@@ -96,7 +104,7 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 if (v[s]) {
-                    const int o = owner_of(ro, qi[s] / W);
+                    const int o = SINGLE ? me : owner_of(ro, (int)((unsigned)ify + (unsigned)(s >> 1)));      // a valid tap lies in the image: its row is ly
                     const float4 hc = __ldg(&hist_cv.p[o][qi[s]]); const float2 hm = __ldg(&mom_hist.p[o][qi[s]]);
                     pr = __fmaf_rn(w[s], hc.x, pr); pg = __fmaf_rn(w[s], hc.y, pg); pb = __fmaf_rn(w[s], hc.z, pb);
                     pm1 = __fmaf_rn(w[s], hm.x, pm1); pm2 = __fmaf_rn(w[s], hm.y, pm2);
@@ -105,7 +113,9 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
                 }
             }
             if (sumw >= 0.01) {
-                pr /= sumw; pg /= sumw; pb /= sumw; pm1 /= sumw; pm2 /= sumw; phl /= sumw;
+                // (x / 1.0f is x: a camera at rest reprojects onto pixel centres, the weights are {1, 0, 0, 0}, and six IEEE
+                // divides per pixel go away)
+                if (sumw != 1.0f) { pr /= sumw; pg /= sumw; pb /= sumw; pm1 /= sumw; pm2 /= sumw; phl /= sumw; }
                 valid = true;
             }
         }
@@ -115,9 +125,9 @@ __device__ __forceinline__ TemporalOut temporal_pixel(int W, int H, int p, const
                 for (int xx = -1; xx <= 1; xx++) {
                     const float lx = floorx + (float)xx, ly = floory + (float)yy;
                     int q = 0;
-                    if (reprj_valid(W, H, lx, ly, ncur, nrm_prev, ro, q)) {
+                    if (reprj_valid<SINGLE>(W, H, lx, ly, ncur, nrm_prev, own, q)) {
                         q = (int)(lx + (float)W * ly);
-                        const int o = owner_of(ro, q / W);
+                        const int o = own((int)ly, q);
                         const float4 hc = __ldg(&hist_cv.p[o][q]); const float2 hm = __ldg(&mom_hist.p[o][q]);
                         pr = __fadd_rn(pr, hc.x); pg = __fadd_rn(pg, hc.y); pb = __fadd_rn(pb, hc.z); pm1 = __fadd_rn(pm1, hm.x); pm2 = __fadd_rn(pm2, hm.y);
                         phl = __fadd_rn(phl, (float)__ldg(&hlen_tab.p[o][q]));
@@ -164,6 +174,7 @@ struct TemporalPush {           // sharded frames: the neighbours' copies of the
 // profiles/r2_ab_temporal_blocks_per_sm.txt). The hint changes how the optimiser fuses and re-associates the bilinear
 // accumulation of temporal_pixel -- with the arithmetic left to it, the history lengths of moving-camera frames stopped matching
 // the reference's (18 parity tests) -- which is why that block is written with explicit single-rounding intrinsics.
+template <bool SINGLE>
 __global__ void __launch_bounds__(256, 8)
 temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restrict__ image,
                 const float4 *__restrict__ nrm_cur, const __grid_constant__ PeerPtr<float4> nrm_prev, const float4 *__restrict__ pos,
@@ -176,7 +187,7 @@ temporal_kernel(int W, int H, int row_begin, int row_end, const float *__restric
     const int y = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     if (x < W && y < row_end) {
         const int p = x + y * W;
-        const TemporalOut o = temporal_pixel(W, H, p, image, nrm_cur, nrm_prev, pos, hist_cv, mom_hist, hlen_tab, ro, me, vm,
+        const TemporalOut o = temporal_pixel<SINGLE>(W, H, p, image, nrm_cur, nrm_prev, pos, hist_cv, mom_hist, hlen_tab, ro, me, vm,
                                              color_alpha_min, moment_alpha_min, clip_rx, clip_ry, hist_cap);
         hlen_out[p] = o.hlen; mom_acc[p] = o.mom; acc_cv[p] = o.cv; acc_lv[p] = o.lv;
         for (unsigned m = halo_targets(push.ho.peers, y); m; m &= m - 1) {
@@ -358,7 +369,7 @@ inline dim3 grid2d(int W, int rows, dim3 b) { return dim3((W + b.x - 1) / b.x, (
 
 void preload_denoise_kernels() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, temporal_kernel); cudaFuncGetAttributes(&a, no_temporal_kernel); cudaFuncGetAttributes(&a, spatial_variance_kernel);
+    cudaFuncGetAttributes(&a, temporal_kernel<true>); cudaFuncGetAttributes(&a, temporal_kernel<false>); cudaFuncGetAttributes(&a, no_temporal_kernel); cudaFuncGetAttributes(&a, spatial_variance_kernel);
     cudaFuncGetAttributes(&a, pack_pbo_kernel); cudaFuncGetAttributes(&a, debug_view_kernel); cudaFuncGetAttributes(&a, cv_to_outputs_kernel);
     cudaFuncGetAttributes(&a, aos_to_soa_kernel); cudaFuncGetAttributes(&a, soa_to_aos_kernel); cudaFuncGetAttributes(&a, copy_f3_kernel);
     cudaFuncGetAttributes(&a, signal_kernel); cudaFuncGetAttributes(&a, wait_kernel);
@@ -411,9 +422,12 @@ cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_c
     push.ho = ho;
     for (int i = 0; i < ho.peers.n; i++) { push.cv[i] = acc_cv_peers.p[ho.peers.rank[i]]; push.lv[i] = acc_lv_peers.p[ho.peers.rank[i]]; }
     dim3 b(32, 8);
-    temporal_kernel<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
-                                                                 nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lv, mom_acc,
-                                                                 hlen_out, vm, color_alpha, moment_alpha, clip_rx, clip_ry, c->opt_history_cap, push);
+    // one strip = the whole frame (every table entry is this context's own plane): no owner lookups (SVGF_TEMPORAL_SINGLE=0: A/B)
+    static const bool single_ok = !(getenv("SVGF_TEMPORAL_SINGLE") && atoi(getenv("SVGF_TEMPORAL_SINGLE")) == 0);
+    auto kern = (c->rows.world == 1 && single_ok) ? temporal_kernel<true> : temporal_kernel<false>;
+    kern<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
+                                                      nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lv, mom_acc,
+                                                      hlen_out, vm, color_alpha, moment_alpha, clip_rx, clip_ry, c->opt_history_cap, push);
     return cudaGetLastError();
 }
 
