@@ -132,3 +132,55 @@ def test_jpeg_decoder_rejects_what_it_does_not_read():
     sc = m.SceneFile(os.path.join(OWN_SCENES, "textured.txt")) if os.path.exists(os.path.join(OWN_SCENES, "textured.txt")) else None
     if sc is not None and sc.texture_files:
         assert sc.load_textures("/nonexistent") == 0        # a missing file is reported, not fatal
+
+
+JPEG_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg")
+
+
+def _jpeg_cases():
+    import json
+    return sorted(json.load(open(os.path.join(JPEG_GOLDEN, "index.json"))).items())
+
+
+@pytest.mark.parametrize("name,whc", _jpeg_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_jpeg_decoder_equals_stb_image_on_every_coding_mode(name, whc):
+    """tests/golden/jpeg: small files in every mode the decoder reads -- baseline and progressive, 4:4:4 / 4:2:2 / 4:2:0, greyscale,
+    sizes that are not a multiple of the MCU, optimised Huffman tables, restart intervals, a single pixel -- with the bytes the
+    reference's stb_image returned for them (make_fixtures.py, run where /root/reference exists). Byte for byte."""
+    m = svgf()
+    w, h, c = whc
+    want = np.fromfile(os.path.join(JPEG_GOLDEN, name + ".rgb"), dtype=np.uint8)
+    got = m.jpeg_decode(open(os.path.join(JPEG_GOLDEN, name + ".jpg"), "rb").read())
+    assert got.shape == (h, w, c)
+    assert np.array_equal(got.reshape(-1), want), "%s: %d bytes differ from stb_image's" % (name, int((got.reshape(-1) != want).sum()))
+
+
+def test_jpeg_decoder_survives_damaged_files():
+    """A deterministic slice of tools/fuzz/fuzz_jpeg.cpp through the C ABI: truncated, bit-flipped and spliced copies of the
+    fixtures either decode to an image of the announced size or are rejected with an error -- never anything else."""
+    m = svgf()
+    rng = np.random.default_rng(7)
+    decoded = rejected = 0
+    for name, _ in _jpeg_cases():
+        base = np.frombuffer(open(os.path.join(JPEG_GOLDEN, name + ".jpg"), "rb").read(), dtype=np.uint8)
+        for it in range(60):
+            v = base.copy()
+            mode = it % 4
+            if mode == 0:
+                v = v[:int(rng.integers(0, len(v)))]
+            elif mode == 1:
+                for _ in range(int(rng.integers(1, 6))):
+                    v[int(rng.integers(0, len(v)))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            elif mode == 2:
+                for _ in range(int(rng.integers(1, 6))):
+                    v[int(rng.integers(0, len(v)))] = np.uint8(rng.integers(0, 256))
+            else:
+                a, b = sorted(int(x) for x in rng.integers(0, len(v), 2))
+                v = np.concatenate([v[:a], v[b:]])
+            try:
+                img = m.jpeg_decode(v.tobytes())
+                assert img.ndim == 3 and img.shape[2] in (1, 3) and img.size > 0
+                decoded += 1
+            except m.SvgfError:
+                rejected += 1
+    assert decoded > 0 and rejected > 0
