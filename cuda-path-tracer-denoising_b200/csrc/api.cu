@@ -277,6 +277,7 @@ int svgf_create(svgf_ctx **out, const svgf_scene_desc *scene, int device) {
     c->device = device; c->W = scene->width; c->H = scene->height; c->px = (size_t)c->W * c->H;
     c->shard = svgf_shard{0, 1, 0, c->H};
     if (const char *v = getenv("SVGF_RT_VARIANT")) c->rt_variant = (!strcmp(v, "wavefront") || !strcmp(v, "1")) ? 1 : ((!strcmp(v, "persistent") || !strcmp(v, "2")) ? 2 : 0);
+    if (const char *v = getenv("SVGF_RT_COMPACT")) c->rt_compact = atoi(v);       // A/B testing
     if (const char *v = getenv("SVGF_HALO")) c->halo_push = strcmp(v, "pull") != 0;      // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_VARIANT")) c->atrous_variant = (atoi(v) == 1 || atoi(v) == 3 || atoi(v) == 4 || atoi(v) == 5) ? atoi(v) : 2;    // A/B testing
     if (const char *v = getenv("SVGF_ATROUS_BANDS")) c->atrous_slide_bands = atoi(v);

@@ -1414,8 +1414,9 @@ cudaError_t launch_pathtrace(svgf_ctx *c, const RtParams &p, float4 *nrm_out, in
     // 84 B of spills) run 15-30 % faster than 4 blocks/SM (110 registers, none); 10 and 12 were slower again (measured on
     // B200: C2 0.93/0.80/0.86/0.89 ms, C3 3.73/2.82/2.85/2.92 ms for 4/8/10/12). SVGF_RT_MINBLOCKS=4 keeps the A/B.
     static const int minb = getenv("SVGF_RT_MINBLOCKS") ? atoi(getenv("SVGF_RT_MINBLOCKS")) : 8;
-    // A/B: 1 = compacting kernel for the scenes that run at 7 blocks/SM, 2 = for every unsharded frame (see rt_kernel, CP)
-    static const int rt_compact = getenv("SVGF_RT_COMPACT") ? atoi(getenv("SVGF_RT_COMPACT")) : 0;
+    // A/B (SVGF_RT_COMPACT, read at svgf_create): 1 = compacting kernel for the scenes that run at 7 blocks/SM, 2 = for every
+    // frame that pushes no halo rows (see rt_kernel, CP)
+    const int rt_compact = c->rt_compact;
     const bool do_push = push.peers.n > 0;
     if (p.n_lights > 1) { if (do_push) RT_LAUNCH(8, true, true); else RT_LAUNCH(8, false, true); }
     else if (minb == 4) { if (do_push) RT_LAUNCH(4, true, false); else RT_LAUNCH(4, false, false); }

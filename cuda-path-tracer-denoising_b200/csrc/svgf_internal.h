@@ -136,6 +136,7 @@ struct svgf_ctx {
     int atrous_pair_rows = 2;           // SVGF_ATROUS_PAIR_ROWS: centre rows per thread in phase 2 of the pair kernel (1 = 256-thread blocks)
     int atrous_probe = 0;               // SVGF_ATROUS_PROBE: timing probes of the tiled kernel (results are garbage)
     int atrous_shape = -1, atrous_shape_level[SVGF_MAX_LEVELS + 1] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    int rt_compact = 0;                 // A/B (SVGF_RT_COMPACT): 1 = compacting rt_kernel for scenes with next to no mesh, 2 = always (see rt_kernel, CP)
     int rt_variant = 0;                 // 0 = state machine, one pixel per thread (default), 1 = wavefront (stage kernels +
                                         // ballot-compacted queues), 2 = persistent state machine with work refill
     unsigned int *rt_counter = nullptr; int rt_blocks = 0;
