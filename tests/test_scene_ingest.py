@@ -184,3 +184,43 @@ def test_jpeg_decoder_survives_damaged_files():
             except m.SvgfError:
                 rejected += 1
     assert decoded > 0 and rejected > 0
+
+
+def test_scene_reader_survives_damaged_files(tmp_path):
+    """A deterministic slice of tools/fuzz/fuzz_scene.cpp and fuzz_obj.cpp through the C ABI: damaged scene texts and OBJ files are
+    either loaded (and described) or rejected with a message -- no crash, no endless BVH recursion on non-finite vertices."""
+    import shutil
+    m = svgf()
+    rng = np.random.default_rng(11)
+    words = [b"MATERIAL", b"OBJECT", b"CAMERA", b"mesh", b"cube", b"sphere", b"TRANS", b"SCALE", b"nan", b"inf", b"1e38", b"-1", b"\n", b" "]
+    models = tmp_path / "Models"
+    shutil.copytree(os.path.join(OWN_SCENES, "Models"), models)
+    loaded = rejected = 0
+    for name in ("two_meshes.txt", "two_lights.txt"):
+        base = open(os.path.join(OWN_SCENES, name), "rb").read()
+        for it in range(80):
+            v = bytearray(base)
+            for _ in range(int(rng.integers(1, 5))):
+                pos = int(rng.integers(0, max(1, len(v))))
+                mode = int(rng.integers(0, 4))
+                if mode == 0: del v[pos:]
+                elif mode == 1 and v: v[pos] = int(rng.integers(32, 127))
+                elif mode == 2: v[pos:pos] = words[int(rng.integers(0, len(words)))]
+                elif v: del v[pos:pos + int(rng.integers(1, 30))]
+            f = tmp_path / "s.txt"
+            f.write_bytes(bytes(v))
+            try:
+                sc = m.SceneFile(str(f), str(models))
+                loaded += 1
+            except m.SvgfError as e:
+                assert str(e)
+                rejected += 1
+    # OBJ files with vertices that overflow or are not numbers at all
+    for junk in (b"v nan 0 0\nv 0 1 0\nv 1 0 0\nf 1 2 3\n", b"v 1e39 0 0\nv 0 1 0\nv 1 0 0\nf 1 2 3\n" * 1,
+                 b"v 0 0 0\nv 0 1 0\nv 1 0 0\n" + b"f 1 2 3\n" * 40, b"f 1 2 3\n", b"v 0 0 0\nf 1 1 1 1 1 1 1\n"):
+        (models / "quad.obj").write_bytes(junk)
+        try:
+            m.SceneFile(os.path.join(OWN_SCENES, "two_meshes.txt"), str(models)); loaded += 1
+        except m.SvgfError:
+            rejected += 1
+    assert loaded > 0 and rejected > 0
