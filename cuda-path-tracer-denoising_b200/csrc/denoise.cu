@@ -422,11 +422,12 @@ cudaError_t launch_temporal(svgf_ctx *c, const float *image, const float4 *nrm_c
     push.ho = ho;
     for (int i = 0; i < ho.peers.n; i++) { push.cv[i] = acc_cv_peers.p[ho.peers.rank[i]]; push.lv[i] = acc_lv_peers.p[ho.peers.rank[i]]; }
     dim3 b(32, 8);
-    // one strip = the whole frame (every table entry is this context's own plane): no owner lookups (SVGF_TEMPORAL_SINGLE=0: A/B)
+    // one strip = the whole frame (every table entry is this context's own plane, entry 0 as good as any: a strip set with
+    // svgf_set_shard on an unconnected context may carry any rank number): no owner lookups (SVGF_TEMPORAL_SINGLE=0: A/B)
     static const bool single_ok = !(getenv("SVGF_TEMPORAL_SINGLE") && atoi(getenv("SVGF_TEMPORAL_SINGLE")) == 0);
     auto kern = (c->rows.world == 1 && single_ok) ? temporal_kernel<true> : temporal_kernel<false>;
     kern<<<grid2d(c->W, rows, b), b, 0, c->stream>>>(c->W, c->H, c->shard.row_begin, c->shard.row_end, image, nrm_cur,
-                                                      nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->shard.rank, acc_cv, acc_lv, mom_acc,
+                                                      nrm_prev, pos, hist_cv, mom_hist, hlen_in, c->rows, c->rows.world == 1 ? 0 : c->shard.rank, acc_cv, acc_lv, mom_acc,
                                                       hlen_out, vm, color_alpha, moment_alpha, clip_rx, clip_ry, c->opt_history_cap, push);
     return cudaGetLastError();
 }
